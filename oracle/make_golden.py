@@ -1,0 +1,157 @@
+"""ORACLE — test infrastructure, not product code.
+
+Generates tests/golden/*.pt by running the REAL reference (/root/reference, imported in the
+build container through oracle/ref_loader.py) on seeded weights and inputs.  The fixtures
+hold inputs and reference outputs only; weights are regenerated from the seed by
+``lightdiffusion_b200.sd15.seeded_state_dict`` (CPU generator, identical on every host).
+
+    python -m oracle.make_golden            # writes tests/golden/
+
+Every fixture records the call that produced it (LD.py line of the entry point).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from lightdiffusion_b200 import sd15  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+UNET_SEED, VAE_SEED = 1234, 99
+INIT = dict(bias_std=0.05, norm_jitter=0.1)   # non-trivial biases / affine params
+
+
+def _conds(b, ctx_dim, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(b, 77, ctx_dim, generator=g), torch.randn(b, 77, ctx_dim, generator=g)
+
+
+def golden_schedules(R):
+    ms = R.ModelSamplingDiscrete(R.sm_SD15({}))
+    out = {
+        "sigmas_table": ms.sigmas.clone(),
+        "karras20": R.calculate_sigmas(ms, "karras", 20),
+        "karras8": R.calculate_sigmas(ms, "karras", 8),
+        "normal10": R.calculate_sigmas(ms, "normal", 10),
+        "normal22": R.calculate_sigmas(ms, "normal", 22),
+        "probe_sigmas": torch.tensor([14.6146, 5.0, 1.0, 0.3, 0.0292, 20.0, 0.01]),
+    }
+    out["probe_timesteps"] = ms.timestep(out["probe_sigmas"])
+    out["probe_t"] = torch.tensor([0.0, 10.5, 500.25, 998.9, 999.0])
+    out["probe_sigma_of_t"] = ms.sigma(out["probe_t"])
+    out["source"] = "ModelSamplingDiscrete LD.py:1280-1351, calculate_sigmas LD.py:3045"
+    torch.save(out, os.path.join(OUT, "schedules.pt"))
+
+
+def golden_unet(R, tag, cfg, hw, b):
+    """Reference BaseModel.apply_model (LD.py:5828) and sampling_function (LD.py:2609)."""
+    sd = sd15.seeded_state_dict(sd15.unet_param_shapes(cfg), UNET_SEED, **INIT)
+    model = ref_loader.build_ref_model(R, cfg, sd)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(b, 4, hw, hw, generator=g)
+    ctx = torch.randn(b, 77, cfg.context_dim, generator=g)
+    sig = torch.tensor([5.0, 0.3][:b] if b <= 2 else [5.0] * b)
+    with torch.inference_mode():
+        t = model.model_sampling.timestep(sig).float()
+        xc = x / (sig.view(-1, 1, 1, 1) ** 2 + 1) ** 0.5
+        eps = model.diffusion_model(xc, t, context=ctx, transformer_options={}).float()
+        den = model.apply_model(x, sig, c_crossattn=ctx, transformer_options={})
+        # CFG through the reference's own cond batching
+        pos, neg = _conds(b, cfg.context_dim, 3)
+        cfg_den = R.sampling_function(model, x, sig, R.convert_cond([[neg, {}]]), R.convert_cond([[pos, {}]]),
+                                      7.0, model_options={"transformer_options": {}})
+    out = dict(x=x, ctx=ctx, sigma=sig, timestep=t, eps=eps.clone(), denoised=den.clone(),
+               pos=pos, neg=neg, cfg_denoised=cfg_den.clone(), cfg_scale=7.0,
+               unet_seed=UNET_SEED, init=INIT, cfg=cfg,
+               n_params=sum(p.numel() for p in model.diffusion_model.parameters()),
+               source="UNetModel1.forward LD.py:5688, apply_model LD.py:5828, sampling_function LD.py:2609")
+    torch.save(out, os.path.join(OUT, f"unet_{tag}.pt"))
+    return model, sd
+
+
+def golden_samplers(R, model, cfg, hw):
+    """Reference sample() (LD.py:3010) with dpmpp_2m_sde eta=0 and sample1() euler_ancestral."""
+    dev = torch.device("cpu")
+    patcher = R.ModelPatcher(model, load_device=dev, offload_device=dev, current_device=dev)
+    b = 2
+    pos, neg = _conds(b, cfg.context_dim, 5)
+    lat = torch.zeros(b, 4, hw, hw)
+    noise = R.prepare_noise(lat, 42)
+    sig = R.calculate_sigmas(model.model_sampling, "karras", 6)
+    traj = []
+
+    with torch.inference_mode():
+        z = R.sample(patcher, noise, [[pos, {}]], [[neg, {}]], 7.0, dev,
+                     R.ksampler("dpmpp_2m_sde", {"eta": 0.0}), sig,
+                     model_options=patcher.model_options, latent_image=lat, disable_pbar=True, seed=42)
+        # Euler ancestral, hires-style: normal scheduler, denoise 0.45 (LD.py:10592-10603)
+        lat2 = torch.randn(b, 4, hw, hw, generator=torch.Generator().manual_seed(9)) * 0.5
+        noise2 = R.prepare_noise(lat2, 43)
+        ks = R.KSampler1(patcher, steps=4, device=dev, sampler="euler_ancestral", scheduler="normal",
+                         denoise=0.45, model_options=patcher.model_options)
+        sig2 = ks.sigmas.clone()
+        torch.manual_seed(1001)       # default_noise_sampler draws torch.randn_like from the global RNG
+        z2 = ks.sample(noise2, [[pos, {}]], [[neg, {}]], 8.0, latent_image=lat2, disable_pbar=True, seed=43)
+    out = dict(pos=pos, neg=neg, noise=noise, sigmas=sig, z_dpmpp2m=z.clone(), cfg_scale=7.0,
+               lat2=lat2, noise2=noise2, sigmas2=sig2, z_euler_a=z2.clone(), cfg_scale2=8.0,
+               euler_global_seed=1001, traj=traj,
+               source="sample LD.py:3010 (dpmpp_2m_sde eta=0, LD.py:1174); KSampler1.sample LD.py:3106 (euler_ancestral LD.py:907)")
+    torch.save(out, os.path.join(OUT, "samplers_tiny.pt"))
+
+
+def golden_sampler_toy(R):
+    """The two sampler functions on a closed-form linear denoiser D(x,s) = x / (1 + s^2)."""
+    def model(x, sigma, **kw):
+        return x / (1.0 + sigma.view(-1, 1, 1, 1) ** 2)
+    ms = R.ModelSamplingDiscrete(R.sm_SD15({}))
+    sig = R.calculate_sigmas(ms, "karras", 20)
+    g = torch.Generator().manual_seed(11)
+    x0 = torch.randn(3, 4, 8, 8, generator=g) * sig[0]
+    a = R.sample_dpmpp_2m_sde(model, x0.clone(), sig, extra_args={}, disable=True, eta=0.0,
+                              noise_sampler=lambda s, sn: torch.zeros_like(x0))
+    torch.manual_seed(77)
+    b = R.sample_euler_ancestral(model, x0.clone(), sig, extra_args={}, disable=True)
+    torch.save(dict(x0=x0, sigmas=sig, dpmpp2m=a, euler_a=b, euler_global_seed=77,
+                    source="sample_dpmpp_2m_sde LD.py:1174 (eta=0), sample_euler_ancestral LD.py:907"),
+               os.path.join(OUT, "samplers_toy.pt"))
+
+
+def golden_vae(R):
+    """Reference VAE.decode (LD.py:6357) on a small latent."""
+    sd = sd15.seeded_state_dict(sd15.vae_decoder_param_shapes(), VAE_SEED, **INIT)
+    vae = ref_loader.build_ref_vae(R, sd)
+    z = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(5))
+    with torch.inference_mode():
+        img = vae.decode(z)
+    n_dec = sum(p.numel() for n, p in vae.first_stage_model.named_parameters() if n.startswith("decoder."))
+    torch.save(dict(z=z, image=img.clone(), vae_seed=VAE_SEED, init=INIT, n_decoder_params=n_dec,
+                    source="VAE.decode LD.py:6357 -> Decoder.forward LD.py:3857"),
+               os.path.join(OUT, "vae_decode.pt"))
+
+
+def main():
+    assert ref_loader.reference_available(), "needs /root/reference (build container only)"
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    R = ref_loader.load_reference()
+    golden_schedules(R)
+    golden_sampler_toy(R)
+    tiny = sd15.tiny_unet_config()
+    model, _ = golden_unet(R, "tiny", tiny, hw=16, b=2)
+    golden_samplers(R, model, tiny, hw=16)
+    del model
+    golden_vae(R)
+    golden_unet(R, "sd15_lat8", sd15.SD15_UNET, hw=8, b=2)   # real SD1.5 dims, small latent
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,94 @@
+"""Pins the oracle restatement (oracle/ldm_oracle.py) to golden vectors produced by the REAL
+reference code (oracle/make_golden.py, run in the build container).  CPU only."""
+import torch
+
+from lightdiffusion_b200 import sd15
+from oracle import ldm_oracle as O
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def test_schedules(golden):
+    g = golden("schedules.pt")
+    table = O.make_sigmas_table()
+    assert torch.equal(table.sigmas, g["sigmas_table"])
+    assert abs(float(table.sigma_min) - 0.029167) < 1e-6 and abs(float(table.sigma_max) - 14.614641) < 1e-5
+    assert torch.equal(O.calculate_sigmas("karras", 20, table), g["karras20"])
+    assert torch.equal(O.calculate_sigmas("karras", 8, table), g["karras8"])
+    assert torch.equal(O.calculate_sigmas("normal", 10, table), g["normal10"])
+    assert torch.equal(O.calculate_sigmas("normal", 22, table), g["normal22"])
+    assert torch.equal(O.timestep_of_sigma(g["probe_sigmas"], table.log_sigmas), g["probe_timesteps"])
+    assert torch.equal(O.sigma_of_timestep(g["probe_t"], table.log_sigmas), g["probe_sigma_of_t"])
+    # SURVEY.md §4 known answers
+    k = O.calculate_sigmas("karras", 20, table)
+    assert abs(float(k[1]) - 11.7254) < 1e-3 and abs(float(k[10]) - 1.0908) < 1e-3 and float(k[-1]) == 0
+
+
+def test_denoise_schedule_slice(golden):
+    g = golden("samplers_tiny.pt")
+    s = O.sigmas_for_denoise("normal", 4, 0.45)
+    assert torch.equal(s, g["sigmas2"])
+
+
+def test_samplers_toy(golden):
+    g = golden("samplers_toy.pt")
+
+    def model(x, sigma, **kw):
+        return x / (1.0 + sigma.view(-1, 1, 1, 1) ** 2)
+    a = O.sample_dpmpp_2m(model, g["x0"].clone(), g["sigmas"])
+    assert torch.equal(a, g["dpmpp2m"])
+    torch.manual_seed(g["euler_global_seed"])
+    b = O.sample_euler_ancestral(model, g["x0"].clone(), g["sigmas"])
+    assert torch.equal(b, g["euler_a"])
+
+
+def _check_unet(g, cfg):
+    sd = sd15.seeded_state_dict(sd15.unet_param_shapes(cfg), g["unet_seed"], **g["init"])
+    assert sd15.count_params(sd15.unet_param_shapes(cfg)) == g["n_params"]
+    with torch.inference_mode():
+        eps = O.unet_forward(sd, cfg, g["x"] / (g["sigma"].view(-1, 1, 1, 1) ** 2 + 1) ** 0.5,
+                             g["timestep"], g["ctx"])
+        assert rel(eps, g["eps"]) < 2e-5
+        den = O.apply_model(sd, cfg, g["x"], g["sigma"], g["ctx"])
+        assert rel(den, g["denoised"]) < 2e-5
+        model = O.cfg_denoiser(sd, cfg, g["pos"], g["neg"], g["cfg_scale"])
+        assert rel(model(g["x"], g["sigma"]), g["cfg_denoised"]) < 2e-5
+    return sd
+
+
+def test_unet_tiny(golden):
+    g = golden("unet_tiny.pt")
+    _check_unet(g, g["cfg"])
+
+
+def test_unet_sd15_dims(golden):
+    g = golden("unet_sd15_lat8.pt")
+    assert g["n_params"] == 859520964                  # 859.521 M
+    _check_unet(g, sd15.SD15_UNET)
+
+
+def test_samplers_tiny_model(golden):
+    gu, g = golden("unet_tiny.pt"), golden("samplers_tiny.pt")
+    cfg = gu["cfg"]
+    sd = sd15.seeded_state_dict(sd15.unet_param_shapes(cfg), gu["unet_seed"], **gu["init"])
+    with torch.inference_mode():
+        z = O.sample_latent(sd, cfg, g["noise"], g["pos"], g["neg"], g["cfg_scale"], g["sigmas"], "dpmpp_2m")
+        assert rel(z, g["z_dpmpp2m"]) < 1e-4
+        torch.manual_seed(g["euler_global_seed"])
+        z2 = O.sample_latent(sd, cfg, g["noise2"], g["pos"], g["neg"], g["cfg_scale2"], g["sigmas2"],
+                             "euler_ancestral", latent=g["lat2"])
+        assert rel(z2, g["z_euler_a"]) < 1e-4
+
+
+def test_vae_decode(golden):
+    g = golden("vae_decode.pt")
+    shapes = sd15.vae_decoder_param_shapes()
+    assert sum(v for k, v in ((k, torch.Size(s).numel()) for k, s in shapes.items())
+               if k.startswith("decoder.")) == g["n_decoder_params"]
+    sd = sd15.seeded_state_dict(shapes, g["vae_seed"], **g["init"])
+    with torch.inference_mode():
+        img = O.vae_decode(sd, sd15.SD15_VAE, g["z"])
+    assert img.shape == g["image"].shape == (2, 64, 64, 3)
+    assert rel(img, g["image"]) < 2e-5
