@@ -1,0 +1,190 @@
+/* ldx.h — C ABI of libldx.so, the B200 (sm_100a) kernels behind the reference's operator surface.
+ *
+ * The reference (Aatrick/LightDiffusion, one file: LightDiffusion.py = "LD.py") has no native code
+ * and no FFI; every FLOP on its hot path is a torch library call made from four late-bound Python
+ * seams.  This header is what a Python shim binds with ctypes to replace those
+ * calls; each entry point cites the reference call site it stands in for.
+ *
+ * Conventions
+ *   - plain pointers are DEVICE pointers unless the name ends in _host; no torch types cross the ABI
+ *   - activations are fp16, channels-last ("NHWC": [B, H, W, C], pixel pitch given in elements)
+ *   - weights are fp16 [N, K] row-major (torch Linear layout); 3x3 conv weights are packed
+ *     [Cout][tap = ky*3+kx][ceil64(Cin)] by ldx_pack_conv3x3
+ *   - every call enqueues on the given cudaStream_t (void*; NULL = legacy default stream),
+ *     returns 0 on success and a negative LDX_E_* otherwise; ldx_last_error_string() explains
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ */
+#ifndef LDX_H_
+#define LDX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDX_OK 0
+#define LDX_E_INVALID (-1)   /* bad argument / unsupported shape */
+#define LDX_E_CUDA (-2)      /* CUDA runtime or driver error */
+#define LDX_E_NODEVICE (-3)  /* no sm_100 device */
+
+typedef void* ldx_stream_t;
+
+int ldx_version(void);
+/* sizeof() of the ABI structs, for binding self-checks: 0 gemm_desc, 1 generic_op, 2 src, 3 seg. */
+int ldx_sizeof(int what);
+const char* ldx_last_error_string(void);
+/* 0 if a CUDA device with compute capability 10.x is present. */
+int ldx_device_check(void);
+
+/* ------------------------------------------------------------------ implicit GEMM (tcgen05 + TMA)
+ * One kernel serves F.linear (LD.py:2368), 1x1 and 3x3 F.conv2d (LD.py:2382; stride 1, stride 2,
+ * nearest-2x-upsampled input, channel-concatenated input) as
+ *     out[b,y,x,n] = epilogue( sum_seg sum_c src[seg.src][b, y+seg.dy, x+seg.dx, seg.c0+c] * w[n, k] )
+ * where the K axis of w is the concatenation of the segments' channel ranges, each padded to 64.
+ * Out-of-range (y+dy, x+dx, c) read as zero (conv zero padding).
+ */
+typedef struct {
+  const void* ptr;          /* fp16 */
+  int32_t C, W, H, B;       /* extents seen by the kernel */
+  int64_t sw, sh, sb;       /* strides in elements for W, H, B (channel stride is 1) */
+} ldx_src_t;
+
+typedef struct {
+  int32_t src;              /* index into ldx_gemm_desc_t.src */
+  int32_t c0;               /* first channel */
+  int32_t dx, dy;           /* spatial shift of this tap */
+  int32_t nchunks;          /* number of 64-channel K chunks */
+} ldx_seg_t;
+
+#define LDX_MAX_SRC 4
+#define LDX_MAX_SEG 16
+
+#define LDX_EPI_SILU 1      /* out = silu(acc + bias)            (time_embed, LD.py:5380-5388) */
+#define LDX_EPI_GEGLU 2     /* out[:, j] = a * gelu_erf(gate)     (GEGLU.forward, LD.py:4513-4515);
+                               weight rows must be interleaved by ldx_pack_geglu; out has N/2 columns */
+#define LDX_EPI_OUT_F32 4   /* store fp32 instead of fp16 */
+
+typedef struct {
+  ldx_src_t src[LDX_MAX_SRC];
+  int32_t nsrc;
+  ldx_seg_t seg[LDX_MAX_SEG];
+  int32_t nseg;
+  const void* w;            /* fp16 [N, ldw] */
+  int64_t ldw;
+  int32_t N;
+  int32_t W, H, B;          /* output domain; a plain GEMM with M rows uses W=M, H=1, B=1 */
+  void* out;
+  int64_t o_sx, o_sy, o_sb, o_off;   /* out element address = o_off + b*o_sb + y*o_sy + x*o_sx + n */
+  const float* bias;        /* [N] fp32 or NULL */
+  const float* rowadd;      /* [B, ld_rowadd] fp32 or NULL: added per batch index (timestep embedding
+                               broadcast h + emb_out[:, :, None, None], LD.py:5279-5285) */
+  int64_t ld_rowadd;
+  const void* residual;     /* fp16 [(b*H+y)*W+x, ldr] or NULL (x + h, LD.py:5287; x += n, LD.py:4142) */
+  int64_t ldr;
+  int32_t flags;            /* LDX_EPI_* */
+  int32_t bn;               /* N tile (multiple of 32, <= 256); 0 = choose */
+} ldx_gemm_desc_t;
+
+int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream);
+
+/* One-time weight layout transforms (ldx_pack_weights_* of SURVEY.md §8b). */
+/* torch conv weight [Cout, Cin, 3, 3] fp16 -> [Cout, 9 * ceil64(Cin)] fp16 (tap-major, zero padded). */
+int ldx_pack_conv3x3(const void* w_oihw, void* w_packed, int cout, int cin, ldx_stream_t stream);
+/* Same, for "nearest 2x upsample then conv3x3" (Upsample1.forward LD.py:5142-5152, Upsample.forward
+ * LD.py:3507-3511): folds the 3x3 taps onto the low-resolution grid -> 4 output-parity phases of
+ * 2x2 taps: [4 phases][Cout][4 * ceil64(Cin)] fp16, summed in fp32. */
+int ldx_pack_upconv3x3(const void* w_oihw, void* w_packed, int cout, int cin, ldx_stream_t stream);
+/* GEGLU proj weight [2*F, K] (+ bias[2*F]) -> rows interleaved in blocks of `half_bn` so that one
+ * output tile holds matching value/gate columns. */
+int ldx_pack_geglu(const void* w, const float* bias, void* w_packed, float* bias_packed, int two_f, int k,
+                   int half_bn, ldx_stream_t stream);
+
+/* ------------------------------------------------------------------ normalisation (HBM bound)
+ * GroupNorm(32, C) over NHWC input, optionally over the channel concatenation of two tensors
+ * (th.cat([h, hsp], 1) LD.py:5749 followed by ResBlock in_layers, LD.py:5220-5232), optionally
+ * followed by SiLU.  Replaces torch.nn.GroupNorm.forward (LD.py:2390-2395, 3931-3939) + nn.SiLU.
+ * stats: fp32 workspace of B * LDX_GN_STATS_FLOATS floats (per-slab partial sums).  */
+#define LDX_GN_STATS_FLOATS 4096
+int ldx_group_norm(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1,
+                   int B, int HW, float eps, const float* gamma, const float* beta, int silu,
+                   void* y, int64_t ldy, float* stats, ldx_stream_t stream);
+/* LayerNorm over the last dim (F.layer_norm, LD.py:2403), eps 1e-5, fp16 in/out. */
+int ldx_layer_norm(const void* x, int64_t ldx_, int rows, int C, float eps, const float* gamma,
+                   const float* beta, void* y, int64_t ldy, ldx_stream_t stream);
+
+/* ------------------------------------------------------------------ attention (tcgen05 flash)
+ * optimized_attention(q, k, v, heads) (LD.py:3966-3988): softmax(q k^T / sqrt(d)) v per head, no
+ * mask.  q [B, Nq, heads*d], k/v [B, Nk, heads*d] fp16 with row pitches ldq/ldk/ldv/ldo (elements).
+ * d in {40, 64, 80, 128, 160}. */
+int ldx_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                  void* o, int64_t ldo, int B, int Nq, int Nk, int heads, int d, ldx_stream_t stream);
+
+/* ------------------------------------------------------------------ data movement / small ops */
+/* x fp32 NCHW [B,C,H,W] * (1/sqrt(sigma_b^2+1)) -> fp16 NHWC [B,H,W,Cpad], extra channels zero
+ * (EPS.calculate_input LD.py:1259-1261 + the .to(dtype) of apply_model LD.py:5842). sigma may be NULL. */
+int ldx_nchw_to_nhwc_scaled(const float* x, const float* sigma, void* y, int B, int C, int H, int W,
+                            int Cpad, ldx_stream_t stream);
+/* timestep = argmin_i |log sigma - log_sigmas[i]| (ModelSamplingDiscrete.timestep LD.py:1336-1339),
+ * then [cos(t f) | sin(t f)] as fp16 [B, dim] (timestep_embedding LD.py:803-812). */
+int ldx_timestep_embedding(const float* sigma, const float* log_sigmas, int n_sigmas, void* emb, int B,
+                           int dim, ldx_stream_t stream);
+/* nearest-neighbour 2x upsample, NHWC fp16 (F.interpolate mode="nearest", LD.py:5149). */
+int ldx_upsample_nearest2x(const void* x, void* y, int B, int H, int W, int C, ldx_stream_t stream);
+/* eps fp16 NHWC [B,H,W,ldc] (first C channels) -> denoised fp32 NCHW = x - eps * sigma_b
+ * (EPS.calculate_denoised LD.py:1263-1265, .float() LD.py:5859). */
+int ldx_eps_to_denoised(const void* eps, int64_t lde, const float* x, const float* sigma, float* den,
+                        int B, int C, int H, int W, ldx_stream_t stream);
+/* Same, fused with classifier-free guidance: eps holds the [uncond..., cond...] batch of 2b samples,
+ * x/sigma are the b-sample latents; out = u + (c - u) * scale on the denoised predictions
+ * (calc_cond_batch chunk LD.py:2569 + cfg_function LD.py:2594-2606). */
+int ldx_cfg_denoised(const void* eps, int64_t lde, const float* x, const float* sigma, float scale,
+                     float* den, int b, int C, int H, int W, ldx_stream_t stream);
+/* cfg_function on two fp32 predictions (LD.py:2605). */
+int ldx_cfg_combine(const float* cond, const float* uncond, float scale, float* out, int64_t n,
+                    ldx_stream_t stream);
+/* decoded fp16 NHWC [B,H,W,ldc] (first 3 channels) -> clamp((v+1)/2, 0, 1) fp32 NHWC [B,H,W,3]
+ * (VAE.process_output + movedim, LD.py:6296-6298, 6377-6380). */
+int ldx_vae_postprocess(const void* dec, int64_t ldc, float* img, int64_t npix, ldx_stream_t stream);
+/* row softmax of fp16 [rows, n] scaled by `scale`, in place (VAE AttnBlock d=512 path, LD.py:3591-3602). */
+int ldx_softmax_rows(void* s, int64_t lds, int64_t rows, int n, float scale, ldx_stream_t stream);
+
+/* ------------------------------------------------------------------ sampler updates (HBM bound)
+ * One DPM++ 2M step (sample_dpmpp_2m_sde with eta=0, LD.py:1209-1236), in place on x:
+ *   x = c_x * x + c_d * denoised + c_o * (denoised - old_denoised)        (c_o = 0 on the first step)
+ * The host computes c_* from the sigmas exactly as the reference does. n = element count (fp32). */
+int ldx_dpmpp2m_step(float* x, const float* denoised, const float* old_denoised, float c_x, float c_d,
+                     float c_o, int64_t n, ldx_stream_t stream);
+/* One Euler-ancestral step (LD.py:929-936), in place on x:
+ *   x = x + (x - denoised) / sigma * (sigma_down - sigma) + noise * noise_scale   (noise may be NULL) */
+int ldx_euler_ancestral_step(float* x, const float* denoised, const float* noise, float sigma,
+                             float sigma_down, float noise_scale, int64_t n, ldx_stream_t stream);
+
+/* ------------------------------------------------------------------ recorded programs
+ * A program is an ordered list of the calls above with all arguments frozen (TMA descriptors built
+ * once).  ldx_program_run replays it on a stream; it is what a CUDA graph captures. */
+enum {
+  LDX_OP_GEMM = 1, LDX_OP_GROUP_NORM = 2, LDX_OP_LAYER_NORM = 3, LDX_OP_ATTENTION = 4,
+  LDX_OP_NCHW_TO_NHWC = 5, LDX_OP_TIMESTEP_EMB = 6, LDX_OP_UPSAMPLE2X = 7, LDX_OP_EPS_TO_DENOISED = 8,
+  LDX_OP_CFG_DENOISED = 9, LDX_OP_VAE_POST = 10, LDX_OP_SOFTMAX = 11
+};
+typedef struct {
+  int32_t kind;
+  int32_t i[16];
+  int64_t l[8];
+  float f[4];
+  const void* p[10];
+} ldx_generic_op_t;          /* argument slots for the non-GEMM ops, in the order of the C signature */
+
+typedef struct ldx_program ldx_program_t;
+ldx_program_t* ldx_program_create(void);
+int ldx_program_add_gemm(ldx_program_t* prog, const ldx_gemm_desc_t* d);
+int ldx_program_add_op(ldx_program_t* prog, const ldx_generic_op_t* op);
+int ldx_program_num_launches(const ldx_program_t* prog);
+int ldx_program_run(ldx_program_t* prog, ldx_stream_t stream);
+void ldx_program_destroy(ldx_program_t* prog);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDX_H_ */

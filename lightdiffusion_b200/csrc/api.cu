@@ -1,0 +1,148 @@
+// C-ABI glue: error reporting, device check and recorded programs (ldx_program_*).
+#include <string.h>
+
+#include <vector>
+
+#include "internal.h"
+
+namespace ldx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return LDX_E_CUDA;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+int attention_prepare_op(const ldx_generic_op_t* op, void** handle);
+int attention_run_handle(void* handle, cudaStream_t st);
+void attention_free_handle(void* handle);
+
+struct ProgOp {
+  int kind;
+  GemmLaunch* gemm = nullptr;
+  void* attn = nullptr;
+  ldx_generic_op_t gen;
+  int launches = 1;
+};
+
+}  // namespace ldx
+
+using namespace ldx;
+
+struct ldx_program {
+  std::vector<ProgOp> ops;
+};
+
+extern "C" int ldx_version(void) { return 1; }
+
+extern "C" int ldx_sizeof(int what) {
+  switch (what) {
+    case 0: return (int)sizeof(ldx_gemm_desc_t);
+    case 1: return (int)sizeof(ldx_generic_op_t);
+    case 2: return (int)sizeof(ldx_src_t);
+    case 3: return (int)sizeof(ldx_seg_t);
+  }
+  return -1;
+}
+
+extern "C" const char* ldx_last_error_string(void) { return g_err; }
+
+extern "C" int ldx_device_check(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device (%s)", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    return LDX_E_NODEVICE;
+  }
+  int dev = 0, major = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (major != 10) {
+    set_error("device compute capability %d.x is not sm_100", major);
+    return LDX_E_NODEVICE;
+  }
+  return LDX_OK;
+}
+
+extern "C" ldx_program_t* ldx_program_create(void) { return new ldx_program; }
+
+extern "C" int ldx_program_add_gemm(ldx_program_t* prog, const ldx_gemm_desc_t* d) {
+  LDX_CHECK_ARG(prog && d, "program_add_gemm: null");
+  GemmLaunch* g = new GemmLaunch;
+  int rc = gemm_prepare(d, g);
+  if (rc) {
+    delete g;
+    return rc;
+  }
+  ProgOp op;
+  op.kind = LDX_OP_GEMM;
+  op.gemm = g;
+  prog->ops.push_back(op);
+  return LDX_OK;
+}
+
+extern "C" int ldx_program_add_op(ldx_program_t* prog, const ldx_generic_op_t* gop) {
+  LDX_CHECK_ARG(prog && gop, "program_add_op: null");
+  ProgOp op;
+  op.kind = gop->kind;
+  op.gen = *gop;
+  if (gop->kind == LDX_OP_ATTENTION) {
+    int rc = attention_prepare_op(gop, &op.attn);
+    if (rc) return rc;
+  } else if (gop->kind == LDX_OP_GROUP_NORM) {
+    op.launches = 2;
+  } else if (gop->kind == LDX_OP_GEMM) {
+    set_error("use ldx_program_add_gemm for GEMM ops");
+    return LDX_E_INVALID;
+  }
+  prog->ops.push_back(op);
+  return LDX_OK;
+}
+
+extern "C" int ldx_program_num_launches(const ldx_program_t* prog) {
+  if (!prog) return 0;
+  int n = 0;
+  for (const ProgOp& op : prog->ops) n += op.launches;
+  return n;
+}
+
+extern "C" int ldx_program_run(ldx_program_t* prog, ldx_stream_t stream) {
+  LDX_CHECK_ARG(prog, "program_run: null");
+  cudaStream_t st = as_stream(stream);
+  for (size_t i = 0; i < prog->ops.size(); ++i) {
+    const ProgOp& op = prog->ops[i];
+    int rc;
+    if (op.kind == LDX_OP_GEMM) rc = gemm_launch(op.gemm, st);
+    else if (op.kind == LDX_OP_ATTENTION) rc = attention_run_handle(op.attn, st);
+    else rc = run_generic_op(&op.gen, st);
+    if (rc) return rc;
+  }
+  return LDX_OK;
+}
+
+extern "C" void ldx_program_destroy(ldx_program_t* prog) {
+  if (!prog) return;
+  for (ProgOp& op : prog->ops) {
+    delete op.gemm;
+    if (op.attn) attention_free_handle(op.attn);
+  }
+  delete prog;
+}

@@ -1,0 +1,16 @@
+#!/bin/bash
+# Builds libldx.so in-tree for sm_100a (nvcc cross-compiles without a GPU).
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
+OBJS=""
+for f in api gemm elementwise attention; do
+  if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ internal.h -nt build/$f.o ] || [ ../../include/ldx.h -nt build/$f.o ]; then
+    mkdir -p build
+    $NVCC $FLAGS -c $f.cu -o build/$f.o 2> build/$f.log || { cat build/$f.log; exit 1; }
+  fi
+  OBJS="$OBJS build/$f.o"
+done
+$NVCC -shared -o ../libldx.so $OBJS -lcudart_static -lpthread -ldl -lrt
+echo "built $(cd .. && pwd)/libldx.so"

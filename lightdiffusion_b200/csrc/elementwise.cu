@@ -1,0 +1,583 @@
+// HBM-bound kernels of the SD1.5 hot path: GroupNorm(+SiLU) over NHWC (optionally over a channel
+// concat of two tensors), LayerNorm, layout conversion with EPS input scaling, timestep embedding,
+// nearest upsample, eps -> denoised (+ CFG), VAE post-process, sampler updates.
+// All are vectorised to 16-byte accesses and sized to a multiple of the SM count.
+// Roofline: HBM; algorithmic bytes are stated per kernel.
+#include "common.cuh"
+#include "internal.h"
+
+namespace ldx {
+
+// ----------------------------------------------------------------------------- GroupNorm
+// Pass 1 (stats): per (b, slab) partial sums per group.  bytes: read B*HW*C*2.
+// Pass 2 (apply): y = [silu]((x - mean) * rstd * gamma + beta).  bytes: read + write B*HW*C*2.
+// Each thread owns a fixed 8-channel vector, so its per-channel accumulators / affine params stay
+// in registers; the channel->group reduction is done in a fixed order (bit-reproducible).
+struct GnArgs {
+  const __half* x0; const __half* x1;
+  int c0, c1; int64_t ld0, ld1;
+  int HW, C, cpg, nvec, P, pix_per_slab, nslab;
+  float eps; int silu;
+  const float* gamma; const float* beta;
+  __half* y; int64_t ldy;
+  float* partial;   // [B][nslab][32][2]
+};
+
+__device__ __forceinline__ uint4 gn_load(const GnArgs& a, int b, int pix, int vec) {
+  const int c = vec * 8;
+  if (c < a.c0) return __ldg(reinterpret_cast<const uint4*>(a.x0 + ((int64_t)b * a.HW + pix) * a.ld0 + c));
+  return __ldg(reinterpret_cast<const uint4*>(a.x1 + ((int64_t)b * a.HW + pix) * a.ld1 + (c - a.c0)));
+}
+
+__global__ void gn_stats_kernel(const GnArgs a) {
+  extern __shared__ float sm[];          // [P][C][2]
+  const int b = blockIdx.x, slab = blockIdx.y;
+  const int vec = threadIdx.x % a.nvec, pl = threadIdx.x / a.nvec;
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  const int p_begin = slab * a.pix_per_slab;
+  const int p_end = min(a.HW, p_begin + a.pix_per_slab);
+  if (pl < a.P) {
+    for (int pix = p_begin + pl; pix < p_end; pix += a.P) {
+      const uint4 v = gn_load(a, b, pix, vec);
+      const float2 f0 = unpack_h2(v.x), f1 = unpack_h2(v.y), f2 = unpack_h2(v.z), f3 = unpack_h2(v.w);
+      const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sm[((size_t)pl * a.C + vec * 8 + j) * 2 + 0] = s[j];
+      sm[((size_t)pl * a.C + vec * 8 + j) * 2 + 1] = ss[j];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    float acc = 0.f;
+    for (int pl2 = 0; pl2 < a.P; ++pl2)
+      for (int c = g * a.cpg; c < (g + 1) * a.cpg; ++c) acc += sm[((size_t)pl2 * a.C + c) * 2 + which];
+    a.partial[(((size_t)b * a.nslab + slab) * 32 + g) * 2 + which] = acc;
+  }
+}
+
+__global__ void gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_slab_apply) {
+  __shared__ float s_mean[32], s_rstd[32];
+  const int b = blockIdx.x, slab = blockIdx.y;
+  if (threadIdx.x < 32) {
+    double s = 0.0, ss = 0.0;
+    for (int k = 0; k < a.nslab; ++k) {
+      s += (double)a.partial[(((size_t)b * a.nslab + k) * 32 + threadIdx.x) * 2 + 0];
+      ss += (double)a.partial[(((size_t)b * a.nslab + k) * 32 + threadIdx.x) * 2 + 1];
+    }
+    const double n = (double)a.HW * a.cpg;
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  __syncthreads();
+  const int vec = threadIdx.x % a.nvec, pl = threadIdx.x / a.nvec;
+  if (pl >= a.P) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = vec * 8 + j;
+    const int g = c / a.cpg;
+    const float w = a.gamma[c] * s_rstd[g];
+    sc[j] = w;
+    sh[j] = a.beta[c] - s_mean[g] * w;
+  }
+  const int p_begin = slab * pix_per_slab_apply;
+  const int p_end = min(a.HW, p_begin + pix_per_slab_apply);
+  for (int pix = p_begin + pl; pix < p_end; pix += a.P) {
+    const uint4 v = gn_load(a, b, pix, vec);
+    const float2 f0 = unpack_h2(v.x), f1 = unpack_h2(v.y), f2 = unpack_h2(v.z), f3 = unpack_h2(v.w);
+    float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = f[j] * sc[j] + sh[j];
+      if (a.silu) f[j] = silu_f(f[j]);
+    }
+    uint4 o;
+    o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(a.y + ((int64_t)b * a.HW + pix) * a.ldy + vec * 8) = o;
+  }
+}
+
+static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1, int B, int HW,
+                           float eps, const float* gamma, const float* beta, int silu, void* y, int64_t ldy,
+                           float* stats, cudaStream_t stream) {
+  const int C = c0 + (x1 ? c1 : 0);
+  LDX_CHECK_ARG(x0 && y && stats && gamma && beta, "group_norm: null pointer");
+  LDX_CHECK_ARG(C % 32 == 0 && c0 % 8 == 0 && C % 8 == 0, "group_norm: C=%d (c0=%d) must be a multiple of 32 / 8", C, c0);
+  LDX_CHECK_ARG(ld0 % 8 == 0 && ldy % 8 == 0 && (!x1 || ld1 % 8 == 0), "group_norm: pitches must be multiples of 8");
+  LDX_CHECK_ARG(C <= 8192, "group_norm: C too large");
+  GnArgs a;
+  a.x0 = (const __half*)x0; a.x1 = (const __half*)x1;
+  a.c0 = c0; a.c1 = c1; a.ld0 = ld0; a.ld1 = ld1;
+  a.HW = HW; a.C = C; a.cpg = C / 32; a.nvec = C / 8;
+  a.P = a.nvec >= 256 ? 1 : 256 / a.nvec;
+  if (a.P > HW) a.P = HW;
+  const int threads = ((a.nvec * a.P + 31) / 32) * 32;
+  LDX_CHECK_ARG(threads <= 1024, "group_norm: C too large for one block");
+  // stats workspace holds [B][nslab][32][2]; nslab bounded so that it fits LDX_GN_MAX_SLABS
+  const int sms = num_sms();
+  int nslab = (4 * sms + B - 1) / B;
+  const int max_slabs = (HW + a.P - 1) / a.P;
+  if (nslab > max_slabs) nslab = max_slabs;
+  if (nslab > 64) nslab = 64;
+  if (nslab < 1) nslab = 1;
+  int pps = (HW + nslab - 1) / nslab;
+  pps = (pps + a.P - 1) / a.P * a.P;
+  nslab = (HW + pps - 1) / pps;
+  a.pix_per_slab = pps; a.nslab = nslab;
+  a.eps = eps; a.silu = silu; a.gamma = gamma; a.beta = beta;
+  a.y = (__half*)y; a.ldy = ldy; a.partial = stats;
+  const size_t smem = (size_t)a.P * C * 2 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    LDX_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+    attr = true;
+  }
+  LDX_CHECK_ARG(smem <= 128 * 1024, "group_norm: smem");
+  gn_stats_kernel<<<dim3(B, nslab), threads, smem, stream>>>(a);
+  LDX_CUDA(cudaGetLastError());
+  // apply: more slabs for bandwidth
+  int nslab2 = (8 * sms + B - 1) / B;
+  if (nslab2 > max_slabs) nslab2 = max_slabs;
+  if (nslab2 < 1) nslab2 = 1;
+  int pps2 = (HW + nslab2 - 1) / nslab2;
+  pps2 = (pps2 + a.P - 1) / a.P * a.P;
+  nslab2 = (HW + pps2 - 1) / pps2;
+  gn_apply_kernel<<<dim3(B, nslab2), threads, 0, stream>>>(a, nslab2, pps2);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
+}
+
+// ----------------------------------------------------------------------------- LayerNorm
+// One warp per row, row held in registers (two-pass variance). bytes: read + write rows*C*2.
+template <int VPL>
+__global__ void layer_norm_kernel(const __half* __restrict__ x, int64_t ldx_, int rows, int C, float eps,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  __half* __restrict__ y, int64_t ldy) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C >> 3;
+  const __half* xr = x + (int64_t)warp * ldx_;
+  float f[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
+      const float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
+      f[i][0] = a.x; f[i][1] = a.y; f[i][2] = b.x; f[i][3] = b.y; f[i][4] = c.x; f[i][5] = c.y; f[i][6] = d.x; f[i][7] = d.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += f[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / C;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var += d * d; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / C + eps);
+  __half* yr = y + (int64_t)warp * ldy;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * __ldg(gamma + v * 8 + j) + __ldg(beta + v * 8 + j);
+      uint4 u;
+      u.x = pack_h2(o[0], o[1]); u.y = pack_h2(o[2], o[3]); u.z = pack_h2(o[4], o[5]); u.w = pack_h2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(yr + v * 8) = u;
+    }
+  }
+}
+
+static int layer_norm_impl(const void* x, int64_t ldx_, int rows, int C, float eps, const float* gamma,
+                           const float* beta, void* y, int64_t ldy, cudaStream_t stream) {
+  LDX_CHECK_ARG(x && y && gamma && beta, "layer_norm: null pointer");
+  LDX_CHECK_ARG(C % 8 == 0 && C <= 2048 && ldx_ % 8 == 0 && ldy % 8 == 0, "layer_norm: C=%d unsupported", C);
+  const int threads = 256;
+  const int blocks = (rows * 32 + threads - 1) / threads;
+  const int vpl = (C / 8 + 31) / 32;
+  const __half* xx = (const __half*)x;
+  __half* yy = (__half*)y;
+  if (vpl <= 2) layer_norm_kernel<2><<<blocks, threads, 0, stream>>>(xx, ldx_, rows, C, eps, gamma, beta, yy, ldy);
+  else if (vpl <= 5) layer_norm_kernel<5><<<blocks, threads, 0, stream>>>(xx, ldx_, rows, C, eps, gamma, beta, yy, ldy);
+  else layer_norm_kernel<8><<<blocks, threads, 0, stream>>>(xx, ldx_, rows, C, eps, gamma, beta, yy, ldy);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
+}
+
+// ----------------------------------------------------------------------------- layout / small ops
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
+                                    __half* __restrict__ y, int B, int C, int HW, int Cpad) {
+  const int64_t total = (int64_t)B * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / HW);
+    const int pix = (int)(i % HW);
+    float scale = 1.f;
+    if (sigma) { const float s = sigma[b]; scale = 1.0f / sqrtf(s * s + 1.0f); }
+    __half* o = y + i * Cpad;
+    for (int c = 0; c < Cpad; ++c) {
+      float v = 0.f;
+      if (c < C) {
+        const float xv = x[((int64_t)b * C + c) * HW + pix];
+        v = sigma ? xv / sqrtf(sigma[b] * sigma[b] + 1.0f) : xv;
+      }
+      o[c] = __float2half_rn(v);
+    }
+    (void)scale;
+  }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ sigma, const float* __restrict__ log_sigmas,
+                                          int n_sigmas, __half* __restrict__ emb, int dim) {
+  __shared__ float s_best[32];
+  __shared__ int s_idx[32];
+  __shared__ int s_t;
+  const int b = blockIdx.x;
+  const float ls = logf(sigma[b]);
+  float best = 3.4e38f;
+  int idx = 0x7fffffff;
+  for (int i = threadIdx.x; i < n_sigmas; i += blockDim.x) {
+    const float d = fabsf(ls - log_sigmas[i]);
+    if (d < best || (d == best && i < idx)) { best = d; idx = i; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ob < best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    for (int w = 1; w < nw; ++w)
+      if (s_best[w] < best || (s_best[w] == best && s_idx[w] < idx)) { best = s_best[w]; idx = s_idx[w]; }
+    s_t = idx;
+  }
+  __syncthreads();
+  const float t = (float)s_t;
+  const int half_dim = dim / 2;
+  for (int i = threadIdx.x; i < half_dim; i += blockDim.x) {
+    const float freq = expf(-9.210340371976184f * (float)i / (float)half_dim);   // ln(10000)
+    const float arg = t * freq;
+    emb[(int64_t)b * dim + i] = __float2half_rn(cosf(arg));
+    emb[(int64_t)b * dim + half_dim + i] = __float2half_rn(sinf(arg));
+  }
+}
+
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int H, int W, int cvec) {
+  const int64_t total = (int64_t)B * (2 * H) * (2 * W) * cvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cvec);
+    int64_t r = i / cvec;
+    const int X = (int)(r % (2 * W)); r /= (2 * W);
+    const int Y = (int)(r % (2 * H));
+    const int b = (int)(r / (2 * H));
+    y[i] = __ldg(x + (((int64_t)b * H + (Y >> 1)) * W + (X >> 1)) * cvec + v);
+  }
+}
+
+// eps NHWC fp16 -> denoised NCHW fp32 = x - eps * sigma
+__global__ void eps_to_denoised_kernel(const __half* __restrict__ eps, int64_t lde, const float* __restrict__ x,
+                                       const float* __restrict__ sigma, float* __restrict__ den, int B, int C, int HW) {
+  const int64_t total = (int64_t)B * C * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const int b = (int)(i / ((int64_t)HW * C));
+    const float e = __half2float(eps[((int64_t)b * HW + pix) * lde + c]);
+    den[i] = x[i] - e * sigma[b];
+  }
+}
+
+// eps holds [uncond(b) ; cond(b)] ; out = du + (dc - du) * scale with d* = x - eps* * sigma
+__global__ void cfg_denoised_kernel(const __half* __restrict__ eps, int64_t lde, const float* __restrict__ x,
+                                    const float* __restrict__ sigma, float scale, float* __restrict__ den, int nb,
+                                    int C, int HW) {
+  const int64_t total = (int64_t)nb * C * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const int b = (int)(i / ((int64_t)HW * C));
+    const float eu = __half2float(eps[((int64_t)b * HW + pix) * lde + c]);
+    const float ec = __half2float(eps[((int64_t)(b + nb) * HW + pix) * lde + c]);
+    const float xv = x[i], s = sigma[b];
+    const float du = xv - eu * s, dc = xv - ec * s;
+    den[i] = du + (dc - du) * scale;
+  }
+}
+
+__global__ void cfg_combine_kernel(const float* __restrict__ c, const float* __restrict__ u, float scale,
+                                   float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = u[i] + (c[i] - u[i]) * scale;
+}
+
+__global__ void vae_post_kernel(const __half* __restrict__ dec, int64_t ldc, float* __restrict__ img, int64_t npix) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix * 3; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / 3;
+    const int c = (int)(i % 3);
+    const float v = (__half2float(dec[pix * ldc + c]) + 1.0f) / 2.0f;
+    img[i] = fminf(fmaxf(v, 0.0f), 1.0f);
+  }
+}
+
+// in-place row softmax(scale * s), fp16 storage, fp32 math; one block per row
+__global__ void softmax_rows_kernel(__half* __restrict__ s, int64_t lds, int n, float scale) {
+  __shared__ float red[32];
+  __half* row = s + (int64_t)blockIdx.x * lds;
+  float m = -3.4e38f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, __half2float(row[i]) * scale);
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -3.4e38f;
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  m = red[0];
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += expf(__half2float(row[i]) * scale - m);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) red[0] = v;
+  }
+  __syncthreads();
+  const float inv = 1.0f / red[0];
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    row[i] = __float2half_rn(expf(__half2float(row[i]) * scale - m) * inv);
+}
+
+// ----------------------------------------------------------------------------- sampler updates
+// bytes per element: dpmpp2m 16 (read x, d, old; write x), euler-a 16 (read x, d, noise; write x)
+__global__ void dpmpp2m_step_kernel(float* __restrict__ x, const float* __restrict__ d, const float* __restrict__ od,
+                                    float cx, float cd, float co, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // reference order (LD.py:1214-1226): x = cx*x + cd*d ; x = x + co*(d - old)
+    float v = cx * x[i] + cd * d[i];
+    if (od) v = v + co * (d[i] - od[i]);
+    x[i] = v;
+  }
+}
+
+__global__ void euler_ancestral_step_kernel(float* __restrict__ x, const float* __restrict__ d,
+                                            const float* __restrict__ noise, float sigma, float dt, float ns,
+                                            int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    // reference order (LD.py:931-936): d = (x - denoised)/sigma ; x = x + d*dt ; x = x + noise*s_noise*sigma_up
+    const float xv = x[i];
+    float v = xv + ((xv - d[i]) / sigma) * dt;
+    if (noise) v = v + noise[i] * ns;
+    x[i] = v;
+  }
+}
+
+static inline int ew_blocks(int64_t n, int threads = 256) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+int run_generic_op(const ldx_generic_op_t* op, cudaStream_t st) {
+  const int32_t* i = op->i;
+  const int64_t* l = op->l;
+  const float* f = op->f;
+  const void* const* p = op->p;
+  switch (op->kind) {
+    case LDX_OP_GROUP_NORM:
+      // p: x0, x1, gamma, beta, y, stats ; i: c0, c1, B, HW, silu ; l: ld0, ld1, ldy ; f: eps
+      return group_norm_impl(p[0], i[0], l[0], p[1], i[1], l[1], i[2], i[3], f[0], (const float*)p[2],
+                             (const float*)p[3], i[4], (void*)p[4], l[2], (float*)p[5], st);
+    case LDX_OP_LAYER_NORM:
+      // p: x, gamma, beta, y ; i: rows, C ; l: ldx, ldy ; f: eps
+      return layer_norm_impl(p[0], l[0], i[0], i[1], f[0], (const float*)p[1], (const float*)p[2], (void*)p[3], l[1], st);
+    case LDX_OP_NCHW_TO_NHWC: {
+      // p: x, sigma, y ; i: B, C, H, W, Cpad
+      const int64_t n = (int64_t)i[0] * i[2] * i[3];
+      nchw_to_nhwc_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)p[0], (const float*)p[1], (__half*)p[2], i[0],
+                                                        i[1], i[2] * i[3], i[4]);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
+    }
+    case LDX_OP_TIMESTEP_EMB:
+      // p: sigma, log_sigmas, emb ; i: n_sigmas, B, dim
+      timestep_embedding_kernel<<<i[1], 256, 0, st>>>((const float*)p[0], (const float*)p[1], i[0], (__half*)p[2], i[2]);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
+    case LDX_OP_UPSAMPLE2X: {
+      // p: x, y ; i: B, H, W, C
+      LDX_CHECK_ARG(i[3] % 8 == 0, "upsample: C must be a multiple of 8");
+      const int64_t n = (int64_t)i[0] * 4 * i[1] * i[2] * (i[3] / 8);
+      upsample2x_kernel<<<ew_blocks(n), 256, 0, st>>>((const uint4*)p[0], (uint4*)p[1], i[0], i[1], i[2], i[3] / 8);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
+    }
+    case LDX_OP_EPS_TO_DENOISED: {
+      // p: eps, x, sigma, den ; i: B, C, H, W ; l: lde
+      const int64_t n = (int64_t)i[0] * i[1] * i[2] * i[3];
+      eps_to_denoised_kernel<<<ew_blocks(n), 256, 0, st>>>((const __half*)p[0], l[0], (const float*)p[1],
+                                                           (const float*)p[2], (float*)p[3], i[0], i[1], i[2] * i[3]);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
+    }
+    case LDX_OP_CFG_DENOISED: {
+      // p: eps, x, sigma, den ; i: b, C, H, W ; l: lde ; f: scale
+      const int64_t n = (int64_t)i[0] * i[1] * i[2] * i[3];
+      cfg_denoised_kernel<<<ew_blocks(n), 256, 0, st>>>((const __half*)p[0], l[0], (const float*)p[1],
+                                                        (const float*)p[2], f[0], (float*)p[3], i[0], i[1], i[2] * i[3]);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
+    }
+    case LDX_OP_VAE_POST:
+      // p: dec, img ; l: ldc, npix
+      vae_post_kernel<<<ew_blocks(l[1] * 3), 256, 0, st>>>((const __half*)p[0], l[0], (float*)p[1], l[1]);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
+    case LDX_OP_SOFTMAX:
+      // p: s ; l: lds, rows ; i: n ; f: scale
+      softmax_rows_kernel<<<(unsigned)l[1], 256, 0, st>>>((__half*)p[0], l[0], i[0], f[0]);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
+    default:
+      set_error("unknown op kind %d", op->kind);
+      return LDX_E_INVALID;
+  }
+}
+
+}  // namespace ldx
+
+using namespace ldx;
+
+extern "C" int ldx_group_norm(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1, int B, int HW,
+                              float eps, const float* gamma, const float* beta, int silu, void* y, int64_t ldy,
+                              float* stats, ldx_stream_t stream) {
+  return group_norm_impl(x0, c0, ld0, x1, c1, ld1, B, HW, eps, gamma, beta, silu, y, ldy, stats, as_stream(stream));
+}
+
+extern "C" int ldx_layer_norm(const void* x, int64_t ldx_, int rows, int C, float eps, const float* gamma,
+                              const float* beta, void* y, int64_t ldy, ldx_stream_t stream) {
+  return layer_norm_impl(x, ldx_, rows, C, eps, gamma, beta, y, ldy, as_stream(stream));
+}
+
+static ldx_generic_op_t make_op(int kind) {
+  ldx_generic_op_t op;
+  memset(&op, 0, sizeof(op));
+  op.kind = kind;
+  return op;
+}
+
+extern "C" int ldx_nchw_to_nhwc_scaled(const float* x, const float* sigma, void* y, int B, int C, int H, int W, int Cpad,
+                                       ldx_stream_t stream) {
+  LDX_CHECK_ARG(x && y && Cpad >= C, "nchw_to_nhwc: bad args");
+  ldx_generic_op_t op = make_op(LDX_OP_NCHW_TO_NHWC);
+  op.p[0] = x; op.p[1] = sigma; op.p[2] = y;
+  op.i[0] = B; op.i[1] = C; op.i[2] = H; op.i[3] = W; op.i[4] = Cpad;
+  return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_timestep_embedding(const float* sigma, const float* log_sigmas, int n_sigmas, void* emb, int B,
+                                      int dim, ldx_stream_t stream) {
+  LDX_CHECK_ARG(sigma && log_sigmas && emb && dim % 2 == 0, "timestep_embedding: bad args");
+  ldx_generic_op_t op = make_op(LDX_OP_TIMESTEP_EMB);
+  op.p[0] = sigma; op.p[1] = log_sigmas; op.p[2] = emb;
+  op.i[0] = n_sigmas; op.i[1] = B; op.i[2] = dim;
+  return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_upsample_nearest2x(const void* x, void* y, int B, int H, int W, int C, ldx_stream_t stream) {
+  LDX_CHECK_ARG(x && y, "upsample: null");
+  ldx_generic_op_t op = make_op(LDX_OP_UPSAMPLE2X);
+  op.p[0] = x; op.p[1] = y;
+  op.i[0] = B; op.i[1] = H; op.i[2] = W; op.i[3] = C;
+  return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_eps_to_denoised(const void* eps, int64_t lde, const float* x, const float* sigma, float* den, int B,
+                                   int C, int H, int W, ldx_stream_t stream) {
+  LDX_CHECK_ARG(eps && x && sigma && den, "eps_to_denoised: null");
+  ldx_generic_op_t op = make_op(LDX_OP_EPS_TO_DENOISED);
+  op.p[0] = eps; op.p[1] = x; op.p[2] = sigma; op.p[3] = den;
+  op.i[0] = B; op.i[1] = C; op.i[2] = H; op.i[3] = W; op.l[0] = lde;
+  return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_cfg_denoised(const void* eps, int64_t lde, const float* x, const float* sigma, float scale,
+                                float* den, int b, int C, int H, int W, ldx_stream_t stream) {
+  LDX_CHECK_ARG(eps && x && sigma && den, "cfg_denoised: null");
+  ldx_generic_op_t op = make_op(LDX_OP_CFG_DENOISED);
+  op.p[0] = eps; op.p[1] = x; op.p[2] = sigma; op.p[3] = den;
+  op.i[0] = b; op.i[1] = C; op.i[2] = H; op.i[3] = W; op.l[0] = lde; op.f[0] = scale;
+  return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_cfg_combine(const float* cond, const float* uncond, float scale, float* out, int64_t n,
+                               ldx_stream_t stream) {
+  LDX_CHECK_ARG(cond && uncond && out, "cfg_combine: null");
+  cfg_combine_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(cond, uncond, scale, out, n);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
+}
+
+extern "C" int ldx_vae_postprocess(const void* dec, int64_t ldc, float* img, int64_t npix, ldx_stream_t stream) {
+  LDX_CHECK_ARG(dec && img, "vae_postprocess: null");
+  ldx_generic_op_t op = make_op(LDX_OP_VAE_POST);
+  op.p[0] = dec; op.p[1] = img; op.l[0] = ldc; op.l[1] = npix;
+  return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_softmax_rows(void* s, int64_t lds, int64_t rows, int n, float scale, ldx_stream_t stream) {
+  LDX_CHECK_ARG(s, "softmax: null");
+  ldx_generic_op_t op = make_op(LDX_OP_SOFTMAX);
+  op.p[0] = s; op.l[0] = lds; op.l[1] = rows; op.i[0] = n; op.f[0] = scale;
+  return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_dpmpp2m_step(float* x, const float* denoised, const float* old_denoised, float c_x, float c_d,
+                                float c_o, int64_t n, ldx_stream_t stream) {
+  LDX_CHECK_ARG(x && denoised, "dpmpp2m_step: null");
+  dpmpp2m_step_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(x, denoised, old_denoised, c_x, c_d, c_o, n);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
+}
+
+extern "C" int ldx_euler_ancestral_step(float* x, const float* denoised, const float* noise, float sigma,
+                                        float sigma_down, float noise_scale, int64_t n, ldx_stream_t stream) {
+  LDX_CHECK_ARG(x && denoised, "euler_ancestral_step: null");
+  euler_ancestral_step_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(x, denoised, noise, sigma,
+                                                                           sigma_down - sigma, noise_scale, n);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
+}

@@ -1,0 +1,70 @@
+// Host-side internals shared by the .cu translation units of libldx.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ldx.h"
+
+namespace ldx {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define LDX_CHECK_ARG(cond, ...)   \
+  do {                             \
+    if (!(cond)) {                 \
+      ldx::set_error(__VA_ARGS__); \
+      return LDX_E_INVALID;        \
+    }                              \
+  } while (0)
+
+#define LDX_CUDA(call)                                        \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return ldx::cuda_fail(e__, #call); \
+  } while (0)
+
+inline cudaStream_t as_stream(ldx_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+int num_sms();
+
+// ---- implicit GEMM: frozen kernel parameters (TMA descriptors encoded once)
+struct KSeg {
+  int32_t map, c0, dx, dy, nchunks;
+};
+
+struct alignas(64) GemmKParams {
+  CUtensorMap amap[LDX_MAX_SRC];
+  CUtensorMap bmap;
+  KSeg seg[LDX_MAX_SEG];
+  int32_t nseg, nk;
+  int32_t N, W, H, B;
+  int32_t bw, bh, bb;
+  int32_t tiles_x, tiles_y, tiles_b, n_tiles, num_tiles;
+  int32_t bn, stages;
+  uint32_t tmem_cols, acc_stride;
+  void* out;
+  int64_t o_sx, o_sy, o_sb, o_off;
+  const float* bias;
+  const float* rowadd;
+  int64_t ld_rowadd;
+  const void* res;
+  int64_t ldr;
+  int32_t flags;
+  int32_t vec_ok;   // 16-byte vector epilogue allowed
+};
+
+struct GemmLaunch {
+  GemmKParams p;
+  int grid;
+  int smem_bytes;
+};
+
+int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* out);
+int gemm_launch(const GemmLaunch* g, cudaStream_t stream);
+
+int run_generic_op(const ldx_generic_op_t* op, cudaStream_t stream);
+
+}  // namespace ldx

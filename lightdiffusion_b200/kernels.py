@@ -1,0 +1,287 @@
+"""Torch-tensor level wrappers over the libldx.so C ABI.
+
+Activations are fp16 CUDA tensors in channels-last logical layout: a 4-D tensor is indexed
+[B, H, W, C] with ``stride(-1) == 1`` (channel slices and strided spatial views are fine); a 2-D
+tensor is [rows, C].  Every function enqueues on the current torch CUDA stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def ceil64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+def _check_act(t: torch.Tensor):
+    if not (t.is_cuda and t.dtype == torch.float16 and t.stride(-1) == 1):
+        raise L.LdxError(f"expected a CUDA fp16 tensor with unit channel stride, got {t.dtype} {t.device} {t.stride()}")
+
+
+def make_src(t: torch.Tensor) -> L.Src:
+    _check_act(t)
+    s = L.Src()
+    s.ptr = t.data_ptr()
+    if t.dim() == 2:
+        m, k = t.shape
+        s.C, s.W, s.H, s.B = k, m, 1, 1
+        s.sw = t.stride(0)
+        s.sh = s.sb = t.stride(0) * max(m, 1)
+    else:
+        b, h, w, c = t.shape
+        s.C, s.W, s.H, s.B = c, w, h, b
+        s.sw, s.sh, s.sb = t.stride(2), t.stride(1), t.stride(0)
+    return s
+
+
+def _fill_out(d: L.GemmDesc, out: torch.Tensor, n_out: int):
+    if out.dim() == 2:
+        m = out.shape[0]
+        d.W, d.H, d.B = m, 1, 1
+        d.o_sx, d.o_sy, d.o_sb = out.stride(0), 0, 0
+    else:
+        b, h, w, _ = out.shape
+        d.W, d.H, d.B = w, h, b
+        d.o_sx, d.o_sy, d.o_sb = out.stride(2), out.stride(1), out.stride(0)
+    d.o_off = 0
+    d.out = out.data_ptr()
+    assert out.shape[-1] >= n_out and out.stride(-1) == 1
+
+
+def gemm_desc(srcs: Sequence[torch.Tensor], segs: Sequence[tuple], w: torch.Tensor, out: torch.Tensor, n: int,
+              bias: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None,
+              residual: Optional[torch.Tensor] = None, flags: int = 0, bn: int = 0) -> L.GemmDesc:
+    """segs: (src_index, c0, dx, dy, nchunks).  w: fp16 [N, K] (K = 64 * total chunks, row stride free)."""
+    d = L.GemmDesc()
+    d.nsrc = len(srcs)
+    for i, t in enumerate(srcs):
+        d.src[i] = make_src(t)
+    d.nseg = len(segs)
+    for i, (si, c0, dx, dy, nch) in enumerate(segs):
+        d.seg[i] = L.Seg(si, c0, dx, dy, nch)
+    assert w.dtype == torch.float16 and w.is_cuda and w.stride(1) == 1
+    d.w, d.ldw, d.N = w.data_ptr(), w.stride(0), n
+    n_out = n // 2 if flags & L.EPI_GEGLU else n
+    _fill_out(d, out, n_out)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+        d.bias = bias.data_ptr()
+    if rowadd is not None:
+        assert rowadd.dtype == torch.float32 and rowadd.stride(1) == 1
+        d.rowadd, d.ld_rowadd = rowadd.data_ptr(), rowadd.stride(0)
+    if residual is not None:
+        _check_act(residual)
+        r2 = residual if residual.dim() == 2 else residual
+        if residual.dim() == 4:
+            b, h, w_, c = residual.shape
+            assert residual.stride(1) == residual.stride(2) * w_ and residual.stride(0) == residual.stride(1) * h, \
+                "residual must be pixel-contiguous"
+            d.ldr = residual.stride(2)
+        else:
+            d.ldr = r2.stride(0)
+        d.residual = residual.data_ptr()
+    d.flags, d.bn = flags, bn
+    return d
+
+
+# ----------------------------------------------------------------------------- descriptor builders
+def linear_desc(a: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw) -> L.GemmDesc:
+    """out[M, N] = a[M, K] @ w[N, K]^T (+ epilogue).  K is taken from a; w may be K-padded to 64."""
+    k = a.shape[-1]
+    a2 = a if a.dim() == 2 else a.reshape(-1, k)
+    o2 = out if out.dim() == 2 else out.reshape(-1, out.shape[-1])
+    return gemm_desc([a2], [(0, 0, 0, 0, ceil64(k) // 64)], w, o2, w.shape[0], **kw)
+
+
+def linear2_desc(a0: torch.Tensor, a1: torch.Tensor, w: torch.Tensor, out: torch.Tensor, **kw) -> L.GemmDesc:
+    """1x1 conv over the channel concat [a0 | a1] without materialising it (two K segments)."""
+    k0, k1 = a0.shape[-1], a1.shape[-1]
+    assert k0 % 64 == 0, "first concat source must be a multiple of 64 channels"
+    f = lambda t: t if t.dim() == 2 else t.reshape(-1, t.shape[-1])
+    return gemm_desc([f(a0), f(a1)], [(0, 0, 0, 0, k0 // 64), (1, 0, 0, 0, ceil64(k1) // 64)], w, f(out),
+                     w.shape[0], **kw)
+
+
+def conv3x3_desc(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, **kw) -> L.GemmDesc:
+    """3x3 stride-1 pad-1 conv. x [B,H,W,Cin], wp packed [Cout, 9*ceil64(Cin)], out [B,H,W,Cout]."""
+    cin = x.shape[-1]
+    nch = ceil64(cin) // 64
+    segs = [(0, 0, kx - 1, ky - 1, nch) for ky in range(3) for kx in range(3)]
+    return gemm_desc([x], segs, wp, out, wp.shape[0], **kw)
+
+
+def conv3x3_s2_desc(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, **kw) -> L.GemmDesc:
+    """3x3 stride-2 pad-1 conv (Downsample1, LD.py:5173-5186) via four parity-strided views of x."""
+    b, h, w, cin = x.shape
+    assert h % 2 == 0 and w % 2 == 0
+    nch = ceil64(cin) // 64
+    views = [x[:, py::2, px::2, :] for py in range(2) for px in range(2)]
+    segs = []
+    for ky in range(3):
+        py, dy = ((1, -1), (0, 0), (1, 0))[ky]
+        for kx in range(3):
+            px, dx = ((1, -1), (0, 0), (1, 0))[kx]
+            segs.append((py * 2 + px, 0, dx, dy, nch))
+    return gemm_desc(views, segs, wp, out, wp.shape[0], **kw)
+
+
+def upconv3x3_descs(x: torch.Tensor, wp4: torch.Tensor, out: torch.Tensor, **kw) -> List[L.GemmDesc]:
+    """nearest-2x upsample + 3x3 conv as four 2x2 phase convs on the low-res input.
+    x [B,H,W,Cin], wp4 packed [4, Cout, 4*ceil64(Cin)], out [B,2H,2W,Cout]."""
+    cin = x.shape[-1]
+    nch = ceil64(cin) // 64
+    descs = []
+    for py in range(2):
+        for px in range(2):
+            segs = []
+            for a in range(2):
+                dy = a - 1 if py == 0 else a
+                for bb in range(2):
+                    dx = bb - 1 if px == 0 else bb
+                    segs.append((0, 0, dx, dy, nch))
+            descs.append(gemm_desc([x], segs, wp4[py * 2 + px], out[:, py::2, px::2, :], wp4.shape[1], **kw))
+    return descs
+
+
+def run_gemm(d: L.GemmDesc):
+    L.check(L.lib().ldx_gemm(C.byref(d), _stream()), "ldx_gemm")
+
+
+# ----------------------------------------------------------------------------- weight packing
+def pack_conv3x3(w_oihw: torch.Tensor) -> torch.Tensor:
+    cout, cin = w_oihw.shape[:2]
+    w16 = w_oihw.to(device="cuda", dtype=torch.float16).contiguous()
+    out = torch.empty(cout, 9 * ceil64(cin), dtype=torch.float16, device="cuda")
+    L.check(L.lib().ldx_pack_conv3x3(w16.data_ptr(), out.data_ptr(), cout, cin, _stream()), "ldx_pack_conv3x3")
+    return out
+
+
+def pack_upconv3x3(w_oihw: torch.Tensor) -> torch.Tensor:
+    cout, cin = w_oihw.shape[:2]
+    w16 = w_oihw.to(device="cuda", dtype=torch.float16).contiguous()
+    out = torch.empty(4, cout, 4 * ceil64(cin), dtype=torch.float16, device="cuda")
+    L.check(L.lib().ldx_pack_upconv3x3(w16.data_ptr(), out.data_ptr(), cout, cin, _stream()), "ldx_pack_upconv3x3")
+    return out
+
+
+def pack_linear(w: torch.Tensor) -> torch.Tensor:
+    """[N, K] (or 1x1 conv [N, K, 1, 1]) -> fp16 [N, ceil64(K)] (zero padded)."""
+    w2 = w.reshape(w.shape[0], -1).to(device="cuda", dtype=torch.float16)
+    n, k = w2.shape
+    if k % 64 == 0:
+        return w2.contiguous()
+    out = torch.zeros(n, ceil64(k), dtype=torch.float16, device="cuda")
+    out[:, :k] = w2
+    return out
+
+
+def pack_geglu(w: torch.Tensor, bias: torch.Tensor, half_bn: int = 128):
+    w16 = w.to(device="cuda", dtype=torch.float16).contiguous()
+    b32 = bias.to(device="cuda", dtype=torch.float32).contiguous()
+    two_f, k = w16.shape
+    assert k % 64 == 0
+    wo, bo = torch.empty_like(w16), torch.empty_like(b32)
+    L.check(L.lib().ldx_pack_geglu(w16.data_ptr(), b32.data_ptr(), wo.data_ptr(), bo.data_ptr(), two_f, k, half_bn,
+                                   _stream()), "ldx_pack_geglu")
+    return wo, bo
+
+
+# ----------------------------------------------------------------------------- generic ops
+def generic_op(kind: int, p=(), i=(), l=(), f=()) -> L.GenericOp:
+    op = L.GenericOp()
+    op.kind = kind
+    for k, v in enumerate(p):
+        op.p[k] = v
+    for k, v in enumerate(i):
+        op.i[k] = v
+    for k, v in enumerate(l):
+        op.l[k] = v
+    for k, v in enumerate(f):
+        op.f[k] = v
+    return op
+
+
+def group_norm_op(x0, x1, gamma, beta, y, stats, eps: float, silu: bool) -> L.GenericOp:
+    """x0 (and optional x1, channel-concatenated) [B,H,W,C*] -> y [B,H,W,C0+C1]."""
+    b, h, w, c0 = x0.shape
+    assert x0.stride(1) == x0.stride(2) * w and x0.stride(0) == x0.stride(1) * h
+    c1 = 0 if x1 is None else x1.shape[-1]
+    assert stats.numel() >= b * L.GN_STATS_FLOATS_PER_BATCH and stats.dtype == torch.float32
+    return generic_op(L.OP_GROUP_NORM, p=[x0.data_ptr(), _ptr(x1), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                          stats.data_ptr()],
+                      i=[c0, c1, b, h * w, int(silu)],
+                      l=[x0.stride(2), 0 if x1 is None else x1.stride(2), y.stride(2)], f=[eps])
+
+
+def layer_norm_op(x2, gamma, beta, y2, eps=1e-5) -> L.GenericOp:
+    rows, c = x2.shape
+    return generic_op(L.OP_LAYER_NORM, p=[x2.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y2.data_ptr()],
+                      i=[rows, c], l=[x2.stride(0), y2.stride(0)], f=[eps])
+
+
+def attention_op(q, k, v, o, heads: int) -> L.GenericOp:
+    """q [B,Nq,heads*d], k/v [B,Nk,heads*d] (row pitch free, batch stride = N * pitch), o like q."""
+    b, nq, c = q.shape
+    nk = k.shape[1]
+    for t, n in ((q, nq), (k, nk), (v, nk), (o, nq)):
+        _check_act(t)
+        assert t.stride(0) == t.stride(1) * n, "batch stride must equal N * row pitch"
+    return generic_op(L.OP_ATTENTION, p=[q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()],
+                      l=[q.stride(1), k.stride(1), v.stride(1), o.stride(1)], i=[b, nq, nk, heads, c // heads])
+
+
+def run_op(op: L.GenericOp):
+    """Execute one generic op immediately (through a one-op program)."""
+    prog = Program()
+    prog.add(op)
+    prog.run()
+
+
+class Program:
+    """Recorded list of kernel launches (ldx_program_*)."""
+
+    def __init__(self):
+        L.require_device()
+        self._h = L.lib().ldx_program_create()
+        self._keep = []          # tensors referenced by raw pointers
+
+    def add(self, op, keep=()):
+        if isinstance(op, L.GemmDesc):
+            L.check(L.lib().ldx_program_add_gemm(self._h, C.byref(op)), "ldx_program_add_gemm")
+        elif isinstance(op, (list, tuple)):
+            for o in op:
+                self.add(o)
+        else:
+            L.check(L.lib().ldx_program_add_op(self._h, C.byref(op)), "ldx_program_add_op")
+        self._keep.extend(keep)
+
+    def keep(self, *tensors):
+        self._keep.extend(tensors)
+
+    @property
+    def num_launches(self) -> int:
+        return L.lib().ldx_program_num_launches(self._h)
+
+    def run(self):
+        L.check(L.lib().ldx_program_run(self._h, _stream()), "ldx_program_run")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                L.lib().ldx_program_destroy(h)
+            except Exception:
+                pass

@@ -1,0 +1,288 @@
+"""Kernel-level parity: every libldx.so kernel against the torch op it replaces, computed in fp32
+from the same fp16 inputs (the oracle for a floating-point kernel).  All calls go through the C ABI.
+Tolerances: fp16 output rounding (rel 2^-11) plus fp32 accumulation-order noise -> 2e-3 rel-L2 bound
+per kernel is loose; observed values are ~3e-4."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from lightdiffusion_b200 import _lib as L
+    from lightdiffusion_b200 import kernels as K
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def h16(t):
+    return t.to(torch.float16)
+
+
+# ------------------------------------------------------------------------------- GEMM / linear
+@pytest.mark.parametrize("M,N,Kd", [(128, 128, 64), (256, 320, 320), (4096, 320, 320), (77 * 2, 640, 768),
+                                    (16, 1280, 320), (1000, 2560, 1280), (8192, 1280, 5120), (130, 72, 128)])
+def test_linear_plain(M, N, Kd):
+    a, w = h16(rnd(M, Kd, seed=1)), h16(rnd(N, Kd, seed=2, scale=Kd ** -0.5))
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.linear_desc(a, w, out))
+    ref = a.float() @ w.float().t()
+    assert rel(out, ref) < 1e-3, (M, N, Kd, rel(out, ref))
+
+
+@pytest.mark.parametrize("bn", [32, 64, 96, 128, 160, 192, 224, 256])
+def test_linear_all_tile_widths(bn):
+    M, N, Kd = 512, 640, 448
+    a, w = h16(rnd(M, Kd, seed=3)), h16(rnd(N, Kd, seed=4, scale=Kd ** -0.5))
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.linear_desc(a, w, out, bn=bn))
+    assert rel(out, a.float() @ w.float().t()) < 1e-3
+
+
+def test_linear_epilogues():
+    M, N, Kd = 1024, 320, 320
+    a, w = h16(rnd(M, Kd, seed=5)), h16(rnd(N, Kd, seed=6, scale=Kd ** -0.5))
+    bias = rnd(N, seed=7)
+    res = h16(rnd(M, N, seed=8))
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.linear_desc(a, w, out, bias=bias, residual=res))
+    ref = a.float() @ w.float().t() + bias + res.float()
+    assert rel(out, ref) < 1e-3
+    # SiLU + fp32 output
+    out32 = torch.empty(M, N, dtype=torch.float32, device=DEV)
+    K.run_gemm(K.linear_desc(a, w, out32, bias=bias, flags=L.EPI_SILU | L.EPI_OUT_F32))
+    assert rel(out32, F.silu(a.float() @ w.float().t() + bias)) < 1e-5
+    # strided output / input views (channel slices of wider buffers)
+    wide_in = h16(rnd(M, Kd + 64, seed=9))
+    wide_out = torch.zeros(M, N + 32, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.linear_desc(wide_in[:, 64:], w, wide_out[:, 32:]))
+    assert rel(wide_out[:, 32:], wide_in[:, 64:].float() @ w.float().t()) < 1e-3
+    assert float(wide_out[:, :32].abs().max()) == 0.0
+
+
+def test_linear_scalar_tail_n4():
+    M, N, Kd = 4096, 4, 320      # UNet out conv has N=4 -> scalar store path
+    a, w = h16(rnd(M, Kd, seed=10)), h16(rnd(N, Kd, seed=11, scale=Kd ** -0.5))
+    out = torch.zeros(M, 8, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.linear_desc(a, w, out[:, :4]))
+    assert rel(out[:, :4], a.float() @ w.float().t()) < 1e-3
+    assert float(out[:, 4:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,Kd,Fd,half_bn", [(512, 320, 1280, 128), (300, 640, 2560, 128), (256, 1280, 5120, 64)])
+def test_geglu(M, Kd, Fd, half_bn):
+    a = h16(rnd(M, Kd, seed=12))
+    w = h16(rnd(2 * Fd, Kd, seed=13, scale=Kd ** -0.5))
+    bias = rnd(2 * Fd, seed=14, scale=0.3)
+    wp, bp = K.pack_geglu(w, bias, half_bn)
+    out = torch.empty(M, Fd, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.linear_desc(a, wp, out, bias=bp, flags=L.EPI_GEGLU, bn=2 * half_bn))
+    y = a.float() @ w.float().t() + bias
+    ref = y[:, :Fd] * F.gelu(y[:, Fd:])
+    assert rel(out, ref) < 1e-3
+
+
+def test_rowadd_timestep_broadcast():
+    B, H, W, Cin, Cout = 3, 16, 16, 64, 96
+    x = h16(rnd(B, H, W, Cin, seed=15))
+    w = h16(rnd(Cout, Cin, 3, 3, seed=16, scale=(9 * Cin) ** -0.5))
+    bias, temb = rnd(Cout, seed=17), rnd(B, Cout + 5, seed=18)
+    out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.conv3x3_desc(x, K.pack_conv3x3(w), out, bias=bias, rowadd=temb[:, 5:]))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + temb[:, 5:, None, None]
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-3
+
+
+# ------------------------------------------------------------------------------- convolutions
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (2, 32, 32, 640, 640), (4, 16, 16, 1280, 1280),
+                                            (3, 8, 8, 1280, 1280), (1, 8, 8, 64, 64), (2, 64, 64, 8, 320),
+                                            (1, 24, 40, 128, 64), (2, 128, 128, 128, 128), (2, 64, 64, 320, 4)])
+def test_conv3x3(B, H, W, Cin, Cout):
+    x = h16(rnd(B, H, W, Cin, seed=20))
+    w = h16(rnd(Cout, Cin, 3, 3, seed=21, scale=(9 * Cin) ** -0.5))
+    bias = rnd(Cout, seed=22)
+    res = h16(rnd(B, H, W, Cout, seed=23))
+    out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.conv3x3_desc(x, K.pack_conv3x3(w), out, bias=bias, residual=res))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + res.float().permute(0, 3, 1, 2)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-3, rel(out.permute(0, 3, 1, 2), ref)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 64, 64, 320), (2, 32, 32, 640), (3, 16, 16, 1280)])
+def test_conv3x3_stride2(B, H, W, C):
+    x = h16(rnd(B, H, W, C, seed=24))
+    w = h16(rnd(C, C, 3, 3, seed=25, scale=(9 * C) ** -0.5))
+    bias = rnd(C, seed=26)
+    out = torch.empty(B, H // 2, W // 2, C, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.conv3x3_s2_desc(x, K.pack_conv3x3(w), out, bias=bias))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=2, padding=1)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-3
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 8, 8, 1280), (2, 16, 16, 1280), (2, 32, 32, 640), (1, 64, 64, 128)])
+def test_upsample_conv_folded(B, H, W, C):
+    x = h16(rnd(B, H, W, C, seed=27))
+    w = h16(rnd(C, C, 3, 3, seed=28, scale=(9 * C) ** -0.5))
+    bias = rnd(C, seed=29)
+    out = torch.empty(B, 2 * H, 2 * W, C, dtype=torch.float16, device=DEV)
+    for d in K.upconv3x3_descs(x, K.pack_upconv3x3(w), out, bias=bias):
+        K.run_gemm(d)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), bias, padding=1)
+    # folding sums up to 4 fp16 weights before rounding -> slightly different rounding than the reference
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1.5e-3
+    # explicit upsample kernel
+    y = torch.empty(B, 2 * H, 2 * W, C, dtype=torch.float16, device=DEV)
+    L.check(L.lib().ldx_upsample_nearest2x(x.data_ptr(), y.data_ptr(), B, H, W, C, 0))
+    torch.cuda.synchronize()
+    assert torch.equal(y.permute(0, 3, 1, 2).float(), up)
+
+
+def test_concat_1x1_skip():
+    B, H, W, C0, C1, Cout = 2, 16, 16, 1280, 640, 1280
+    a0, a1 = h16(rnd(B, H, W, C0, seed=30)), h16(rnd(B, H, W, C1, seed=31))
+    w = h16(rnd(Cout, C0 + C1, seed=32, scale=(C0 + C1) ** -0.5))
+    bias = rnd(Cout, seed=33)
+    out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.linear2_desc(a0, a1, w, out, bias=bias))
+    ref = torch.cat([a0, a1], -1).float() @ w.float().t() + bias
+    assert rel(out, ref) < 1e-3
+
+
+# ------------------------------------------------------------------------------- norms
+@pytest.mark.parametrize("B,HW,C0,C1,silu,eps", [(2, 4096, 320, 0, True, 1e-5), (2, 1024, 1280, 640, True, 1e-5),
+                                                 (3, 64, 1280, 1280, True, 1e-5), (2, 4096, 640, 320, True, 1e-5),
+                                                 (2, 256, 1280, 0, False, 1e-6), (1, 16384, 128, 0, True, 1e-6),
+                                                 (2, 4096, 512, 0, False, 1e-6)])
+def test_group_norm(B, HW, C0, C1, silu, eps):
+    h = int(math.isqrt(HW))
+    x0 = h16(rnd(B, h, HW // h, C0, seed=40) * 2 + 0.7)
+    x1 = h16(rnd(B, h, HW // h, C1, seed=41) * 0.5 - 0.3) if C1 else None
+    C = C0 + C1
+    gamma, beta = rnd(C, seed=42) * 0.2 + 1, rnd(C, seed=43) * 0.2
+    y = torch.empty(B, h, HW // h, C, dtype=torch.float16, device=DEV)
+    stats = torch.empty(B * L.GN_STATS_FLOATS_PER_BATCH, dtype=torch.float32, device=DEV)
+    K.run_op(K.group_norm_op(x0, x1, gamma, beta, y, stats, eps, silu))
+    xc = (x0 if x1 is None else torch.cat([x0, x1], -1)).float().permute(0, 3, 1, 2)
+    ref = F.group_norm(xc, 32, gamma, beta, eps)
+    ref = F.silu(ref) if silu else ref
+    assert rel(y.permute(0, 3, 1, 2), ref) < 6e-4
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 320), (1000, 640), (512, 1280), (77, 768)])
+def test_layer_norm(rows, C):
+    x = h16(rnd(rows, C, seed=44) * 3 + 1)
+    gamma, beta = rnd(C, seed=45) * 0.2 + 1, rnd(C, seed=46) * 0.2
+    y = torch.empty_like(x)
+    K.run_op(K.layer_norm_op(x, gamma, beta, y))
+    assert rel(y, F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)) < 6e-4
+
+
+# ------------------------------------------------------------------------------- attention
+@pytest.mark.parametrize("B,Nq,Nk,heads,d", [(2, 4096, 4096, 8, 40), (2, 1024, 1024, 8, 80), (2, 256, 256, 8, 160),
+                                             (3, 64, 64, 8, 160), (2, 4096, 77, 8, 40), (2, 1024, 77, 8, 80),
+                                             (2, 256, 77, 8, 160), (1, 200, 333, 4, 64), (1, 128, 64, 2, 128)])
+def test_attention(B, Nq, Nk, heads, d):
+    q = h16(rnd(B, Nq, heads * d, seed=50))
+    k = h16(rnd(B, Nk, heads * d, seed=51))
+    v = h16(rnd(B, Nk, heads * d, seed=52))
+    o = torch.empty_like(q)
+    K.run_op(K.attention_op(q, k, v, o, heads))
+    qf, kf, vf = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Nq, heads * d)
+    assert rel(o, ref) < 2e-3, rel(o, ref)
+
+
+def test_attention_peaked_scores_rescale_path():
+    # large-magnitude q/k make the running max jump by more than the lazy-rescale threshold
+    B, N, heads, d = 1, 512, 2, 40
+    q, k = h16(rnd(B, N, heads * d, seed=53) * 4), h16(rnd(B, N, heads * d, seed=54) * 4)
+    v = h16(rnd(B, N, heads * d, seed=55))
+    o = torch.empty_like(q)
+    K.run_op(K.attention_op(q, k, v, o, heads))
+    qf, kf, vf = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, N, heads * d)
+    assert rel(o, ref) < 2e-3
+
+
+# ------------------------------------------------------------------------------- small ops
+def test_input_output_transforms():
+    from oracle import ldm_oracle as O
+    B, H, W = 3, 16, 24
+    x, sigma = rnd(B, 4, H, W, seed=60) * 5, torch.tensor([14.6, 1.0, 0.03], device=DEV)
+    y = torch.empty(B, H, W, 8, dtype=torch.float16, device=DEV)
+    L.check(L.lib().ldx_nchw_to_nhwc_scaled(x.data_ptr(), sigma.data_ptr(), y.data_ptr(), B, 4, H, W, 8, 0))
+    ref = (x / (sigma.view(-1, 1, 1, 1) ** 2 + 1) ** 0.5).to(torch.float16).permute(0, 2, 3, 1)
+    assert torch.equal(y[..., :4], ref) and float(y[..., 4:].abs().max()) == 0
+    # timestep embedding incl. the nearest-sigma lookup
+    table = O.make_sigmas_table()
+    sig = torch.cat([O.calculate_sigmas("karras", 20)[:-1], torch.tensor([0.5, 7.7])]).to(DEV)
+    emb = torch.empty(len(sig), 320, dtype=torch.float16, device=DEV)
+    L.check(L.lib().ldx_timestep_embedding(sig.data_ptr(), table.log_sigmas.to(DEV).data_ptr(), 1000, emb.data_ptr(),
+                                           len(sig), 320, 0))
+    t = O.timestep_of_sigma(sig.cpu(), table.log_sigmas).float()
+    ref = O.timestep_embedding(t, 320).to(torch.float16).to(DEV)
+    assert float((emb.float() - ref.float()).abs().max()) < 2e-3
+    # eps -> denoised and the fused CFG variant
+    eps = h16(rnd(2 * B, H, W, 8, seed=61))
+    den = torch.empty(2 * B, 4, H, W, device=DEV)
+    x2, s2 = torch.cat([x, x]), torch.cat([sigma, sigma])
+    L.check(L.lib().ldx_eps_to_denoised(eps.data_ptr(), 8, x2.data_ptr(), s2.data_ptr(), den.data_ptr(), 2 * B, 4, H, W, 0))
+    ref = x2 - eps[..., :4].float().permute(0, 3, 1, 2) * s2.view(-1, 1, 1, 1)
+    assert torch.allclose(den, ref, rtol=1e-6, atol=1e-6)
+    out = torch.empty(B, 4, H, W, device=DEV)
+    L.check(L.lib().ldx_cfg_denoised(eps.data_ptr(), 8, x.data_ptr(), sigma.data_ptr(), 7.0, out.data_ptr(), B, 4, H, W, 0))
+    assert torch.allclose(out, O.cfg_combine(ref[B:], ref[:B], 7.0), rtol=1e-5, atol=1e-5)
+    out2 = torch.empty_like(out)
+    L.check(L.lib().ldx_cfg_combine(ref[B:].contiguous().data_ptr(), ref[:B].contiguous().data_ptr(), 7.0,
+                                    out2.data_ptr(), out2.numel(), 0))
+    assert torch.allclose(out2, O.cfg_combine(ref[B:], ref[:B], 7.0), rtol=1e-6, atol=1e-6)
+
+
+def test_vae_post_and_softmax():
+    dec = h16(rnd(2 * 32 * 32, 8, seed=62))
+    img = torch.empty(2 * 32 * 32, 3, device=DEV)
+    L.check(L.lib().ldx_vae_postprocess(dec.data_ptr(), 8, img.data_ptr(), dec.shape[0], 0))
+    assert torch.equal(img, torch.clamp((dec[:, :3].float() + 1.0) / 2.0, 0.0, 1.0))
+    s = h16(rnd(300, 4096, seed=63) * 20)
+    ref = torch.softmax(s.float() * 0.0442, -1)
+    L.check(L.lib().ldx_softmax_rows(s.data_ptr(), 4096, 300, 4096, 0.0442, 0))
+    assert rel(s, ref) < 1e-3
+
+
+def test_sampler_step_kernels():
+    n = 8 * 4 * 64 * 64
+    x, d, od, nz = (rnd(n, seed=70 + i) for i in range(4))
+    x1 = x.clone()
+    L.check(L.lib().ldx_dpmpp2m_step(x1.data_ptr(), d.data_ptr(), None, 0.8, 0.2, 0.0, n, 0))
+    assert torch.allclose(x1, 0.8 * x + 0.2 * d, rtol=1e-6, atol=1e-6)
+    x2 = x.clone()
+    L.check(L.lib().ldx_dpmpp2m_step(x2.data_ptr(), d.data_ptr(), od.data_ptr(), 0.8, 0.2, 0.05, n, 0))
+    assert torch.allclose(x2, 0.8 * x + 0.2 * d + 0.05 * (d - od), rtol=1e-6, atol=1e-6)
+    x3 = x.clone()
+    L.check(L.lib().ldx_euler_ancestral_step(x3.data_ptr(), d.data_ptr(), nz.data_ptr(), 2.0, 1.5, 0.7, n, 0))
+    assert torch.allclose(x3, x + (x - d) / 2.0 * (1.5 - 2.0) + nz * 0.7, rtol=1e-6, atol=1e-6)
+
+
+def test_errors_are_loud():
+    a = h16(rnd(64, 60, seed=80))          # K pitch 60 -> TMA stride not a multiple of 16 bytes
+    w, out = h16(rnd(32, 64, seed=81)), torch.empty(64, 32, dtype=torch.float16, device=DEV)
+    with pytest.raises(L.LdxError):
+        K.run_gemm(K.linear_desc(a, w, out))
+    q = h16(rnd(1, 64, 8 * 24, seed=82))   # head dim 24 unsupported
+    with pytest.raises(L.LdxError):
+        K.run_op(K.attention_op(q, q, q, torch.empty_like(q), 8))
