@@ -146,8 +146,10 @@ int ldx_cfg_combine(const float* cond, const float* uncond, float scale, float* 
 /* decoded fp16 NHWC [B,H,W,ldc] (first 3 channels) -> clamp((v+1)/2, 0, 1) fp32 NHWC [B,H,W,3]
  * (VAE.process_output + movedim, LD.py:6296-6298, 6377-6380). */
 int ldx_vae_postprocess(const void* dec, int64_t ldc, float* img, int64_t npix, ldx_stream_t stream);
-/* row softmax of fp16 [rows, n] scaled by `scale`, in place (VAE AttnBlock d=512 path, LD.py:3591-3602). */
-int ldx_softmax_rows(void* s, int64_t lds, int64_t rows, int n, float scale, ldx_stream_t stream);
+/* out[r, :] = softmax(scale * s[r, :]): fp32 scores in, fp16 probabilities out (the VAE AttnBlock's
+ * single-head d=512 attention runs as GEMM / softmax / GEMM, LD.py:3591-3602). */
+int ldx_softmax_rows(const float* s, int64_t lds, void* out, int64_t ldo, int64_t rows, int n, float scale,
+                     ldx_stream_t stream);
 
 /* ------------------------------------------------------------------ sampler updates (HBM bound)
  * One DPM++ 2M step (sample_dpmpp_2m_sde with eta=0, LD.py:1209-1236), in place on x:

@@ -80,7 +80,8 @@ _SIGS = {
                                    C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldx_cfg_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     "ldx_vae_postprocess": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
-    "ldx_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float, C.c_void_p]),
+    "ldx_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float,
+                                   C.c_void_p]),
     "ldx_dpmpp2m_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int64,
                                    C.c_void_p]),
     "ldx_euler_ancestral_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float,

@@ -121,7 +121,8 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
   a.HW = HW; a.C = C; a.cpg = C / 32; a.nvec = C / 8;
   a.P = a.nvec >= 256 ? 1 : 256 / a.nvec;
   if (a.P > HW) a.P = HW;
-  const int threads = ((a.nvec * a.P + 31) / 32) * 32;
+  int threads = ((a.nvec * a.P + 31) / 32) * 32;
+  if (threads < 64) threads = 64;   // the group reduction uses the first 64 threads
   LDX_CHECK_ARG(threads <= 1024, "group_norm: C too large for one block");
   // stats workspace holds [B][nslab][32][2]; nslab bounded so that it fits LDX_GN_MAX_SLABS
   const int sms = num_sms();
@@ -237,8 +238,6 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, const float* __
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / HW);
     const int pix = (int)(i % HW);
-    float scale = 1.f;
-    if (sigma) { const float s = sigma[b]; scale = 1.0f / sqrtf(s * s + 1.0f); }
     __half* o = y + i * Cpad;
     for (int c = 0; c < Cpad; ++c) {
       float v = 0.f;
@@ -248,7 +247,6 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, const float* __
       }
       o[c] = __float2half_rn(v);
     }
-    (void)scale;
   }
 }
 
@@ -346,12 +344,14 @@ __global__ void vae_post_kernel(const __half* __restrict__ dec, int64_t ldc, flo
   }
 }
 
-// in-place row softmax(scale * s), fp16 storage, fp32 math; one block per row
-__global__ void softmax_rows_kernel(__half* __restrict__ s, int64_t lds, int n, float scale) {
+// row softmax(scale * s): fp32 scores in, fp16 probabilities out; one block per row
+__global__ void softmax_rows_kernel(const float* __restrict__ s, int64_t lds, __half* __restrict__ out, int64_t ldo,
+                                    int n, float scale) {
   __shared__ float red[32];
-  __half* row = s + (int64_t)blockIdx.x * lds;
+  const float* row = s + (int64_t)blockIdx.x * lds;
+  __half* orow = out + (int64_t)blockIdx.x * ldo;
   float m = -3.4e38f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, __half2float(row[i]) * scale);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, row[i] * scale);
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -364,7 +364,7 @@ __global__ void softmax_rows_kernel(__half* __restrict__ s, int64_t lds, int n, 
   m = red[0];
   __syncthreads();
   float sum = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += expf(__half2float(row[i]) * scale - m);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += expf(row[i] * scale - m);
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
   __syncthreads();
@@ -375,8 +375,7 @@ __global__ void softmax_rows_kernel(__half* __restrict__ s, int64_t lds, int n, 
   }
   __syncthreads();
   const float inv = 1.0f / red[0];
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    row[i] = __float2half_rn(expf(__half2float(row[i]) * scale - m) * inv);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) orow[i] = __float2half_rn(expf(row[i] * scale - m) * inv);
 }
 
 // ----------------------------------------------------------------------------- sampler updates
@@ -467,8 +466,8 @@ int run_generic_op(const ldx_generic_op_t* op, cudaStream_t st) {
       LDX_CUDA(cudaGetLastError());
       return LDX_OK;
     case LDX_OP_SOFTMAX:
-      // p: s ; l: lds, rows ; i: n ; f: scale
-      softmax_rows_kernel<<<(unsigned)l[1], 256, 0, st>>>((__half*)p[0], l[0], i[0], f[0]);
+      // p: s (fp32), out (fp16) ; l: lds, ldo, rows ; i: n ; f: scale
+      softmax_rows_kernel<<<(unsigned)l[2], 256, 0, st>>>((const float*)p[0], l[0], (__half*)p[1], l[1], i[0], f[0]);
       LDX_CUDA(cudaGetLastError());
       return LDX_OK;
     default:
@@ -558,10 +557,11 @@ extern "C" int ldx_vae_postprocess(const void* dec, int64_t ldc, float* img, int
   return run_generic_op(&op, as_stream(stream));
 }
 
-extern "C" int ldx_softmax_rows(void* s, int64_t lds, int64_t rows, int n, float scale, ldx_stream_t stream) {
-  LDX_CHECK_ARG(s, "softmax: null");
+extern "C" int ldx_softmax_rows(const float* s, int64_t lds, void* out, int64_t ldo, int64_t rows, int n, float scale,
+                                ldx_stream_t stream) {
+  LDX_CHECK_ARG(s && out, "softmax: null");
   ldx_generic_op_t op = make_op(LDX_OP_SOFTMAX);
-  op.p[0] = s; op.l[0] = lds; op.l[1] = rows; op.i[0] = n; op.f[0] = scale;
+  op.p[0] = s; op.p[1] = out; op.l[0] = lds; op.l[1] = ldo; op.l[2] = rows; op.i[0] = n; op.f[0] = scale;
   return run_generic_op(&op, as_stream(stream));
 }
 

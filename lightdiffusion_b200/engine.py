@@ -1,0 +1,585 @@
+"""Whole-network execution plans for the SD1.5 UNet (UNetModel1.forward, LD.py:5688-5767, through
+BaseModel.apply_model, LD.py:5828-5860) and the VAE decoder (Decoder.forward LD.py:3857-3882 through
+VAE.decode LD.py:6357-6381), built from a reference-format state_dict.
+
+A plan is a static list of libldx.so kernel launches over pre-allocated NHWC fp16 buffers for one
+(batch, height, width); it is replayed through ldx_program_run and captured in a CUDA graph.
+Host code here only wires pointers: every FLOP runs in the hand-written kernels, and construction
+fails loudly when libldx.so or a sm_100 device is missing.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib as L
+from . import kernels as K
+from .sd15 import (SD15_UNET, SD15_VAE, AttnSpec, ConvSpec, ResSpec, UNetConfig, VAEConfig, unet_layout,
+                   vae_decoder_levels)
+
+F16, F32 = torch.float16, torch.float32
+
+
+def sigma_tables():
+    """The 1000 discrete sigmas / log-sigmas of ModelSamplingDiscrete (LD.py:1280-1326): scaled-linear
+    betas in float64; log taken in float64 then cast (bit-exact with the reference buffers)."""
+    betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float64) ** 2
+    acp = torch.cumprod(1.0 - betas, dim=0)
+    sig = ((1 - acp) / acp) ** 0.5
+    return sig.float(), sig.log().float()
+
+
+class _Pool:
+    """Size-keyed free list so that dead activations are reused (keeps the working set L2-friendly)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.free_lists: Dict[Tuple[int, torch.dtype], List[torch.Tensor]] = {}
+        self.all: List[torch.Tensor] = []       # owns every allocation for the life of the plan
+        self.total_bytes = 0
+
+    def alloc(self, *shape, dtype=F16) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        fl = self.free_lists.get((n, dtype))
+        if fl:
+            return fl.pop().view(*shape)
+        self.total_bytes += n * torch.empty((), dtype=dtype).element_size()
+        t = torch.empty(n, dtype=dtype, device=self.device)
+        self.all.append(t)
+        return t.view(*shape)
+
+    def free(self, t: torch.Tensor):
+        base = t.reshape(-1)
+        self.free_lists.setdefault((base.numel(), t.dtype), []).append(base)
+
+
+def _f32(sd, name, dev):
+    """fp16-rounded parameter as fp32 (the reference fp16 model stores every parameter in fp16)."""
+    return sd[name].to(device=dev, dtype=F16).float().contiguous()
+
+
+# =============================================================================== UNet
+class UNetEngine:
+    """SD1.x UNet with reference parameter names.  ``denoise`` has BaseModel.apply_model semantics."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], cfg: UNetConfig = SD15_UNET, device="cuda"):
+        L.require_device()
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.layout = unet_layout(cfg)
+        self.sigmas, log_sigmas = sigma_tables()
+        self.log_sigmas = log_sigmas.to(self.dev)
+        self.w: Dict[str, torch.Tensor] = {}
+        self._plans: Dict[tuple, "UNetPlan"] = {}
+        self._pack(state_dict)
+
+    # ---- one-time weight packing
+    def _pack(self, sd):
+        dev, w = self.dev, self.w
+        w["te0.w"], w["te0.b"] = K.pack_linear(sd["time_embed.0.weight"]), _f32(sd, "time_embed.0.bias", dev)
+        w["te2.w"], w["te2.b"] = K.pack_linear(sd["time_embed.2.weight"]), _f32(sd, "time_embed.2.bias", dev)
+        emb_w, emb_b, self.emb_off, off = [], [], {}, 0
+        kv_w, self.kv_off, kvo = [], {}, 0
+        blocks = self.layout.input_blocks + [self.layout.middle] + self.layout.output_blocks
+        for block in blocks:
+            for s in block:
+                if isinstance(s, ResSpec):
+                    self._pack_res(sd, s)
+                    emb_w.append(sd[s.name + ".emb_layers.1.weight"])
+                    emb_b.append(sd[s.name + ".emb_layers.1.bias"])
+                    self.emb_off[s.name] = off
+                    off += s.cout
+                elif isinstance(s, AttnSpec):
+                    self._pack_attn(sd, s)
+                    t = s.name + ".transformer_blocks.0.attn2"
+                    kv_w += [sd[t + ".to_k.weight"], sd[t + ".to_v.weight"]]
+                    self.kv_off[s.name] = kvo
+                    kvo += 2 * s.ch
+                elif s.kind == "up":
+                    w[s.name + ".w"] = K.pack_upconv3x3(sd[s.name + ".weight"])
+                    w[s.name + ".b"] = _f32(sd, s.name + ".bias", dev)
+                else:
+                    w[s.name + ".w"] = K.pack_conv3x3(self._pad_in(sd[s.name + ".weight"]))
+                    w[s.name + ".b"] = _f32(sd, s.name + ".bias", dev)
+        w["emb_all.w"] = K.pack_linear(torch.cat([t.to(dev) for t in emb_w], 0))
+        w["emb_all.b"] = torch.cat([t.to(device=dev, dtype=F16).float() for t in emb_b]).contiguous()
+        self.emb_total = off
+        w["kv_all.w"] = K.pack_linear(torch.cat([t.to(dev) for t in kv_w], 0))
+        self.kv_total = kvo
+        w["out.g"], w["out.beta"] = _f32(sd, "out.0.weight", dev), _f32(sd, "out.0.bias", dev)
+        w["out.w"], w["out.b"] = K.pack_conv3x3(sd["out.2.weight"]), _f32(sd, "out.2.bias", dev)
+        torch.cuda.synchronize()
+
+    @staticmethod
+    def _pad_in(wt):
+        """conv_in: pad Cin 4 -> 8 so that the NHWC pixel pitch is 16 bytes (TMA stride rule)."""
+        if wt.shape[1] % 8 == 0:
+            return wt
+        pad = 8 - wt.shape[1] % 8
+        return torch.cat([wt, wt.new_zeros(wt.shape[0], pad, 3, 3)], 1)
+
+    def _pack_res(self, sd, s: ResSpec):
+        dev, w, p = self.dev, self.w, s.name
+        w[p + ".gn1.g"], w[p + ".gn1.b"] = _f32(sd, p + ".in_layers.0.weight", dev), _f32(sd, p + ".in_layers.0.bias", dev)
+        w[p + ".conv1.w"] = K.pack_conv3x3(sd[p + ".in_layers.2.weight"])
+        w[p + ".conv1.b"] = _f32(sd, p + ".in_layers.2.bias", dev)
+        w[p + ".gn2.g"], w[p + ".gn2.b"] = _f32(sd, p + ".out_layers.0.weight", dev), _f32(sd, p + ".out_layers.0.bias", dev)
+        w2 = K.pack_conv3x3(sd[p + ".out_layers.3.weight"])
+        b2 = _f32(sd, p + ".out_layers.3.bias", dev)
+        if s.cin != s.cout:
+            # skip_connection (1x1 conv, LD.py:5267) rides along as extra K segments of the second 3x3 conv
+            w2 = torch.cat([w2, K.pack_linear(sd[p + ".skip_connection.weight"])], 1).contiguous()
+            b2 = b2 + _f32(sd, p + ".skip_connection.bias", dev)
+        w[p + ".conv2.w"], w[p + ".conv2.b"] = w2, b2
+
+    def _pack_attn(self, sd, s: AttnSpec):
+        dev, w, p = self.dev, self.w, s.name
+        t = p + ".transformer_blocks.0"
+        w[p + ".gn.g"], w[p + ".gn.b"] = _f32(sd, p + ".norm.weight", dev), _f32(sd, p + ".norm.bias", dev)
+        w[p + ".pin.w"], w[p + ".pin.b"] = K.pack_linear(sd[p + ".proj_in.weight"]), _f32(sd, p + ".proj_in.bias", dev)
+        w[p + ".pout.w"], w[p + ".pout.b"] = K.pack_linear(sd[p + ".proj_out.weight"]), _f32(sd, p + ".proj_out.bias", dev)
+        for n in ("norm1", "norm2", "norm3"):
+            w[f"{p}.{n}.g"], w[f"{p}.{n}.b"] = _f32(sd, f"{t}.{n}.weight", dev), _f32(sd, f"{t}.{n}.bias", dev)
+        w[p + ".qkv.w"] = K.pack_linear(torch.cat([sd[t + ".attn1.to_q.weight"], sd[t + ".attn1.to_k.weight"],
+                                                   sd[t + ".attn1.to_v.weight"]], 0))
+        w[p + ".o1.w"], w[p + ".o1.b"] = K.pack_linear(sd[t + ".attn1.to_out.0.weight"]), _f32(sd, t + ".attn1.to_out.0.bias", dev)
+        w[p + ".q2.w"] = K.pack_linear(sd[t + ".attn2.to_q.weight"])
+        w[p + ".o2.w"], w[p + ".o2.b"] = K.pack_linear(sd[t + ".attn2.to_out.0.weight"]), _f32(sd, t + ".attn2.to_out.0.bias", dev)
+        w[p + ".ff1.w"], w[p + ".ff1.b"] = K.pack_geglu(sd[t + ".ff.net.0.proj.weight"],
+                                                       sd[t + ".ff.net.0.proj.bias"].to(F16).float(), 128)
+        w[p + ".ff2.w"], w[p + ".ff2.b"] = K.pack_linear(sd[t + ".ff.net.2.weight"]), _f32(sd, t + ".ff.net.2.bias", dev)
+
+    # ---- plans
+    def plan(self, B: int, H: int, W: int, cfg_pairs: bool = False) -> "UNetPlan":
+        key = (B, H, W, cfg_pairs)
+        if key not in self._plans:
+            self._plans[key] = UNetPlan(self, B, H, W, cfg_pairs)
+        return self._plans[key]
+
+    @torch.no_grad()
+    def denoise(self, x: torch.Tensor, sigma: torch.Tensor, context: Optional[torch.Tensor]) -> torch.Tensor:
+        """apply_model: x fp32 [B,4,H,W], sigma [B], context [B,77,ctx] -> denoised fp32 [B,4,H,W]."""
+        B, _, H, W = x.shape
+        return self.plan(B, H, W).run(x, sigma, context).clone()
+
+    @torch.no_grad()
+    def eps(self, x, sigma, context) -> torch.Tensor:
+        """Raw UNet output (fp16 NHWC buffer converted to fp32 NCHW) for parity tests."""
+        B, _, H, W = x.shape
+        pl = self.plan(B, H, W)
+        pl.run(x, sigma, context)
+        return pl.eps_buf[..., :self.cfg.out_channels].float().permute(0, 3, 1, 2).contiguous()
+
+    @torch.no_grad()
+    def denoise_cfg(self, x, sigma, cond, uncond, scale: float, context_changed: bool = True) -> torch.Tensor:
+        """sampling_function (LD.py:2609): one 2b batch ordered [uncond, cond], then cfg_function."""
+        b, _, H, W = x.shape
+        pl = self.plan(2 * b, H, W, cfg_pairs=True)
+        ctx = torch.cat([uncond, cond]) if context_changed else None
+        return pl.run(x, sigma, ctx, cfg_scale=scale).clone()
+
+
+class UNetPlan:
+    def __init__(self, eng: UNetEngine, B: int, H: int, W: int, cfg_pairs: bool):
+        self.eng, self.B, self.H, self.W, self.cfg_pairs = eng, B, H, W, cfg_pairs
+        cfg, dev = eng.cfg, eng.dev
+        down = 2 ** (len(cfg.channel_mult) - 1)
+        if H % down or W % down:
+            raise L.LdxError(f"latent {H}x{W} must be a multiple of {down}")
+        self.pool = _Pool(dev)
+        nb = B // 2 if cfg_pairs else B          # number of distinct latents fed in
+        self.nb = nb
+        self.x_in = torch.zeros(nb, cfg.in_channels, H, W, dtype=F32, device=dev)
+        self.sigma_in = torch.ones(nb, dtype=F32, device=dev)
+        self.ctx = torch.zeros(B, 77, cfg.context_dim, dtype=F16, device=dev)
+        self.den = torch.zeros(nb, cfg.out_channels, H, W, dtype=F32, device=dev)
+        self.cfg_scale = torch.tensor([1.0])    # host copy; the CFG op is re-recorded when it changes
+        self.stats = torch.empty(B * L.GN_STATS_FLOATS_PER_BATCH, dtype=F32, device=dev)
+        self.kv_all = torch.empty(B * 77, eng.kv_total, dtype=F16, device=dev)
+        self.ctx_prog = K.Program()
+        self.ctx_prog.add(K.linear_desc(self.ctx.view(B * 77, -1), eng.w["kv_all.w"], self.kv_all))
+        self.prog = K.Program()
+        self._build()
+        self.tail_prog: Optional[K.Program] = None
+        self._tail_scale: Optional[float] = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.use_graph = True
+        self._ctx_len = 77
+
+    # ---- op helpers
+    def _gn(self, x0, x1, g, b, eps, silu):
+        Bn, h, w, c0 = x0.shape
+        c = c0 + (0 if x1 is None else x1.shape[-1])
+        y = self.pool.alloc(Bn, h, w, c)
+        self.prog.add(K.group_norm_op(x0, x1, g, b, y, self.stats, eps, silu))
+        return y
+
+    def _res(self, s: ResSpec, x0, x1):
+        eng, w, p = self.eng, self.eng.w, s.name
+        Bn, h, wd, _ = x0.shape
+        y = self._gn(x0, x1, w[p + ".gn1.g"], w[p + ".gn1.b"], 1e-5, True)
+        h1 = self.pool.alloc(Bn, h, wd, s.cout)
+        off = eng.emb_off[p]
+        self.prog.add(K.conv3x3_desc(y, w[p + ".conv1.w"], h1, bias=w[p + ".conv1.b"],
+                                     rowadd=self.emb_out[:, off:off + s.cout]))
+        self.pool.free(y)
+        y2 = self._gn(h1, None, w[p + ".gn2.g"], w[p + ".gn2.b"], 1e-5, True)
+        self.pool.free(h1)
+        out = self.pool.alloc(Bn, h, wd, s.cout)
+        nch = K.ceil64(s.cout) // 64
+        segs = [(0, 0, kx - 1, ky - 1, nch) for ky in range(3) for kx in range(3)]
+        if s.cin == s.cout:
+            assert x1 is None
+            d = K.gemm_desc([y2], segs, w[p + ".conv2.w"], out, s.cout, bias=w[p + ".conv2.b"], residual=x0)
+        else:
+            srcs = [y2, x0] + ([x1] if x1 is not None else [])
+            c0 = x0.shape[-1]
+            assert x1 is None or c0 % 64 == 0
+            segs.append((1, 0, 0, 0, K.ceil64(c0) // 64))
+            if x1 is not None:
+                segs.append((2, 0, 0, 0, K.ceil64(x1.shape[-1]) // 64))
+            d = K.gemm_desc(srcs, segs, w[p + ".conv2.w"], out, s.cout, bias=w[p + ".conv2.b"])
+        self.prog.add(d)
+        self.pool.free(y2)
+        return out
+
+    def _attn(self, s: AttnSpec, x):
+        eng, w, p, pool = self.eng, self.eng.w, s.name, self.pool
+        Bn, h, wd, c = x.shape
+        n, m = h * wd, Bn * h * wd
+        y = self._gn(x, None, w[p + ".gn.g"], w[p + ".gn.b"], 1e-6, False)
+        t = pool.alloc(m, c)
+        self.prog.add(K.linear_desc(y, w[p + ".pin.w"], t, bias=w[p + ".pin.b"]))
+        pool.free(y)
+        # attn1 (self)
+        nrm = pool.alloc(m, c)
+        self.prog.add(K.layer_norm_op(t, w[p + ".norm1.g"], w[p + ".norm1.b"], nrm))
+        qkv = pool.alloc(m, 3 * c)
+        self.prog.add(K.linear_desc(nrm, w[p + ".qkv.w"], qkv))
+        a = pool.alloc(m, c)
+        q3 = qkv.view(Bn, n, 3 * c)
+        self.prog.add(K.attention_op(q3[:, :, :c], q3[:, :, c:2 * c], q3[:, :, 2 * c:], a.view(Bn, n, c), s.heads))
+        pool.free(qkv)
+        t2 = pool.alloc(m, c)
+        self.prog.add(K.linear_desc(a, w[p + ".o1.w"], t2, bias=w[p + ".o1.b"], residual=t))
+        pool.free(t)
+        # attn2 (cross; K/V of the step-invariant context come from the kv_all GEMM)
+        self.prog.add(K.layer_norm_op(t2, w[p + ".norm2.g"], w[p + ".norm2.b"], nrm))
+        q2 = a
+        self.prog.add(K.linear_desc(nrm, w[p + ".q2.w"], q2))
+        kvo = eng.kv_off[p]
+        kv3 = self.kv_all.view(Bn, 77, eng.kv_total)
+        a2 = pool.alloc(m, c)
+        self.prog.add(K.attention_op(q2.view(Bn, n, c), kv3[:, :, kvo:kvo + c], kv3[:, :, kvo + c:kvo + 2 * c],
+                                     a2.view(Bn, n, c), s.heads))
+        t3 = pool.alloc(m, c)
+        self.prog.add(K.linear_desc(a2, w[p + ".o2.w"], t3, bias=w[p + ".o2.b"], residual=t2))
+        pool.free(a2); pool.free(t2); pool.free(q2)
+        # feed-forward (GEGLU gate fused in the first GEMM's epilogue)
+        self.prog.add(K.layer_norm_op(t3, w[p + ".norm3.g"], w[p + ".norm3.b"], nrm))
+        g = pool.alloc(m, 4 * c)
+        self.prog.add(K.linear_desc(nrm, w[p + ".ff1.w"], g, bias=w[p + ".ff1.b"], flags=L.EPI_GEGLU, bn=256))
+        pool.free(nrm)
+        t4 = pool.alloc(m, c)
+        self.prog.add(K.linear_desc(g, w[p + ".ff2.w"], t4, bias=w[p + ".ff2.b"], residual=t3))
+        pool.free(g); pool.free(t3)
+        out = pool.alloc(Bn, h, wd, c)
+        self.prog.add(K.linear_desc(t4, w[p + ".pout.w"], out, bias=w[p + ".pout.b"], residual=x))
+        pool.free(t4)
+        return out
+
+    def _block(self, layers, h, hskip=None):
+        """Runs one TimestepEmbedSequential (LD.py:5089-5111). Returns the new h (inputs are not freed)."""
+        pool = self.pool
+        cur, owned = h, False
+        for s in layers:
+            if isinstance(s, ResSpec):
+                nxt = self._res(s, cur, hskip)
+                hskip = None
+            elif isinstance(s, AttnSpec):
+                nxt = self._attn(s, cur)
+            elif s.kind == "conv_in":
+                Bn, hh, ww, _ = cur.shape
+                nxt = pool.alloc(Bn, hh, ww, s.cout)
+                self.prog.add(K.conv3x3_desc(cur, self.eng.w[s.name + ".w"], nxt, bias=self.eng.w[s.name + ".b"]))
+            elif s.kind == "down":
+                Bn, hh, ww, _ = cur.shape
+                nxt = pool.alloc(Bn, hh // 2, ww // 2, s.cout)
+                self.prog.add(K.conv3x3_s2_desc(cur, self.eng.w[s.name + ".w"], nxt, bias=self.eng.w[s.name + ".b"]))
+            else:  # up: nearest 2x + conv folded into four phase convs
+                Bn, hh, ww, _ = cur.shape
+                nxt = pool.alloc(Bn, hh * 2, ww * 2, s.cout)
+                self.prog.add(K.upconv3x3_descs(cur, self.eng.w[s.name + ".w"], nxt, bias=self.eng.w[s.name + ".b"]))
+            if owned:
+                pool.free(cur)
+            cur, owned = nxt, True
+        return cur
+
+    def _build(self):
+        eng, cfg, w, pool, B, H, W = self.eng, self.eng.cfg, self.eng.w, self.pool, self.B, self.H, self.W
+        prog = self.prog
+        cpad, nb = 8, self.nb
+        x0 = torch.zeros(B, H, W, cpad, dtype=F16, device=eng.dev)
+        temb = torch.empty(B, cfg.model_channels, dtype=F16, device=eng.dev)
+        # with CFG the same latents feed both halves of the [uncond, cond] batch
+        # (torch.cat([x] * 2), torch.cat([timestep] * 2) in calc_cond_batch, LD.py:2545-2551)
+        for half in range(B // nb):
+            prog.add(K.generic_op(L.OP_NCHW_TO_NHWC,
+                                  p=[self.x_in.data_ptr(), self.sigma_in.data_ptr(), x0[half * nb:].data_ptr()],
+                                  i=[nb, cfg.in_channels, H, W, cpad]))
+            prog.add(K.generic_op(L.OP_TIMESTEP_EMB,
+                                  p=[self.sigma_in.data_ptr(), eng.log_sigmas.data_ptr(), temb[half * nb:].data_ptr()],
+                                  i=[1000, nb, cfg.model_channels]))
+        e1 = torch.empty(B, cfg.time_embed_dim, dtype=F16, device=eng.dev)
+        semb = torch.empty(B, cfg.time_embed_dim, dtype=F16, device=eng.dev)
+        prog.add(K.linear_desc(temb, w["te0.w"], e1, bias=w["te0.b"], flags=L.EPI_SILU))
+        # emb is only ever consumed through SiLU (emb_layers = [SiLU, Linear], LD.py:5237-5248)
+        prog.add(K.linear_desc(e1, w["te2.w"], semb, bias=w["te2.b"], flags=L.EPI_SILU))
+        self.emb_out = torch.empty(B, eng.emb_total, dtype=F32, device=eng.dev)
+        prog.add(K.linear_desc(semb, w["emb_all.w"], self.emb_out, bias=w["emb_all.b"], flags=L.EPI_OUT_F32))
+        prog.keep(x0, temb, e1, semb)
+
+        hs = []
+        h = x0
+        for layers in eng.layout.input_blocks:
+            h = self._block(layers, h)
+            hs.append(h)
+        h = self._block(eng.layout.middle, h)
+        for layers in eng.layout.output_blocks:
+            hsp = hs.pop()
+            nh = self._block(layers, h, hsp)
+            if not any(h is t for t in hs):
+                pool.free(h)
+            pool.free(hsp)
+            h = nh
+        y = self._gn(h, None, w["out.g"], w["out.beta"], 1e-5, True)
+        self.eps_buf = torch.zeros(B, H, W, 8, dtype=F16, device=eng.dev)
+        prog.add(K.conv3x3_desc(y, w["out.w"], self.eps_buf[..., :cfg.out_channels], bias=w["out.b"]))
+        if not self.cfg_pairs:
+            prog.add(K.generic_op(L.OP_EPS_TO_DENOISED,
+                                  p=[self.eps_buf.data_ptr(), self.x_in.data_ptr(), self.sigma_in.data_ptr(),
+                                     self.den.data_ptr()],
+                                  i=[B, cfg.out_channels, H, W], l=[8]))
+        self.act_bytes = pool.total_bytes
+
+    def _tail(self, scale: float) -> K.Program:
+        if self.tail_prog is None or self._tail_scale != scale:
+            cfg = self.eng.cfg
+            tp = K.Program()
+            tp.add(K.generic_op(L.OP_CFG_DENOISED,
+                                p=[self.eps_buf.data_ptr(), self.x_in.data_ptr(), self.sigma_in.data_ptr(),
+                                   self.den.data_ptr()],
+                                i=[self.nb, cfg.out_channels, self.H, self.W], l=[8], f=[scale]))
+            self.tail_prog, self._tail_scale, self.graph = tp, scale, None
+        return self.tail_prog
+
+    @property
+    def num_launches(self) -> int:
+        return self.prog.num_launches + (1 if self.cfg_pairs else 0)
+
+    def _launch_all(self):
+        self.prog.run()
+        if self.cfg_pairs:
+            self.tail_prog.run()
+
+    def set_context(self, context: torch.Tensor):
+        """Copies the context in and recomputes the cross-attention K/V of all 16 blocks (step-invariant)."""
+        if context.shape[1] != 77 or context.shape[0] != self.B:
+            raise L.LdxError(f"context must be [{self.B}, 77, {self.eng.cfg.context_dim}], got {tuple(context.shape)}")
+        self.ctx.copy_(context.to(F16))
+        self.ctx_prog.run()
+
+    def run(self, x, sigma, context=None, cfg_scale: Optional[float] = None) -> torch.Tensor:
+        """Returns the plan's output buffer (denoised fp32 NCHW); valid until the next run."""
+        if context is not None:
+            self.set_context(context)
+        if x.data_ptr() != self.x_in.data_ptr():
+            self.x_in.copy_(x)
+        if sigma.data_ptr() != self.sigma_in.data_ptr():
+            self.sigma_in.copy_(sigma)
+        if self.cfg_pairs:
+            self._tail(1.0 if cfg_scale is None else float(cfg_scale))
+        if not self.use_graph:
+            self._launch_all()
+            return self.den
+        if self.graph is None:
+            self._launch_all()                      # warm-up (sets kernel attributes) outside capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_all()
+            self.graph = g
+        self.graph.replay()
+        return self.den
+
+
+# =============================================================================== VAE decoder
+class VAEDecoderEngine:
+    """AutoencoderKL decoder (post_quant_conv + Decoder) with reference parameter names."""
+
+    def __init__(self, state_dict, cfg: VAEConfig = SD15_VAE, device="cuda"):
+        L.require_device()
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.w: Dict[str, torch.Tensor] = {}
+        self._plans: Dict[tuple, "VAEPlan"] = {}
+        sd, dev, w = state_dict, self.dev, self.w
+        w["pq.w"], w["pq.b"] = K.pack_linear(sd["post_quant_conv.weight"]), _f32(sd, "post_quant_conv.bias", dev)
+        w["cin.w"] = K.pack_conv3x3(UNetEngine._pad_in(sd["decoder.conv_in.weight"]))
+        w["cin.b"] = _f32(sd, "decoder.conv_in.bias", dev)
+        self._pack_res(sd, "decoder.mid.block_1")
+        self._pack_res(sd, "decoder.mid.block_2")
+        a = "decoder.mid.attn_1"
+        w[a + ".gn.g"], w[a + ".gn.b"] = _f32(sd, a + ".norm.weight", dev), _f32(sd, a + ".norm.bias", dev)
+        w[a + ".qk.w"] = K.pack_linear(torch.cat([sd[a + ".q.weight"], sd[a + ".k.weight"]], 0))
+        w[a + ".qk.b"] = torch.cat([_f32(sd, a + ".q.bias", dev), _f32(sd, a + ".k.bias", dev)]).contiguous()
+        w[a + ".v.w"], w[a + ".v.b"] = K.pack_linear(sd[a + ".v.weight"]), _f32(sd, a + ".v.bias", dev)
+        w[a + ".o.w"], w[a + ".o.b"] = K.pack_linear(sd[a + ".proj_out.weight"]), _f32(sd, a + ".proj_out.bias", dev)
+        for i_level, blocks, has_up in vae_decoder_levels(cfg):
+            for j in range(len(blocks)):
+                self._pack_res(sd, f"decoder.up.{i_level}.block.{j}")
+            if has_up:
+                n = f"decoder.up.{i_level}.upsample.conv"
+                w[n + ".w"], w[n + ".b"] = K.pack_upconv3x3(sd[n + ".weight"]), _f32(sd, n + ".bias", dev)
+        w["nout.g"], w["nout.b"] = _f32(sd, "decoder.norm_out.weight", dev), _f32(sd, "decoder.norm_out.bias", dev)
+        w["cout.w"], w["cout.b"] = K.pack_conv3x3(sd["decoder.conv_out.weight"]), _f32(sd, "decoder.conv_out.bias", dev)
+        torch.cuda.synchronize()
+
+    def _pack_res(self, sd, p):
+        dev, w = self.dev, self.w
+        w[p + ".gn1.g"], w[p + ".gn1.b"] = _f32(sd, p + ".norm1.weight", dev), _f32(sd, p + ".norm1.bias", dev)
+        w[p + ".conv1.w"], w[p + ".conv1.b"] = K.pack_conv3x3(sd[p + ".conv1.weight"]), _f32(sd, p + ".conv1.bias", dev)
+        w[p + ".gn2.g"], w[p + ".gn2.b"] = _f32(sd, p + ".norm2.weight", dev), _f32(sd, p + ".norm2.bias", dev)
+        w2, b2 = K.pack_conv3x3(sd[p + ".conv2.weight"]), _f32(sd, p + ".conv2.bias", dev)
+        if (p + ".nin_shortcut.weight") in sd:
+            w2 = torch.cat([w2, K.pack_linear(sd[p + ".nin_shortcut.weight"])], 1).contiguous()
+            b2 = b2 + _f32(sd, p + ".nin_shortcut.bias", dev)
+        w[p + ".conv2.w"], w[p + ".conv2.b"] = w2, b2
+
+    def plan(self, B, H, W) -> "VAEPlan":
+        key = (B, H, W)
+        if key not in self._plans:
+            self._plans[key] = VAEPlan(self, B, H, W)
+        return self._plans[key]
+
+    @torch.no_grad()
+    def decode(self, z: torch.Tensor) -> torch.Tensor:
+        """VAE.decode: z fp32 [B,4,h,w] (already / 0.18215) -> image fp32 [B, 8h, 8w, 3] in [0,1]."""
+        B, _, H, W = z.shape
+        return self.plan(B, H, W).run(z).clone()
+
+    @torch.no_grad()
+    def decode_raw(self, z):
+        B, _, H, W = z.shape
+        pl = self.plan(B, H, W)
+        pl.run(z)
+        return pl.dec_buf[..., :3].float().permute(0, 3, 1, 2).contiguous()
+
+
+class VAEPlan:
+    def __init__(self, eng: VAEDecoderEngine, B, H, W):
+        self.eng, self.B, self.H, self.W = eng, B, H, W
+        dev, cfg, w = eng.dev, eng.cfg, eng.w
+        self.pool = pool = _Pool(dev)
+        self.prog = prog = K.Program()
+        self.z_in = torch.zeros(B, cfg.z_channels, H, W, dtype=F32, device=dev)
+        up = 2 ** (len(cfg.ch_mult) - 1)
+        self.img = torch.zeros(B, H * up, W * up, 3, dtype=F32, device=dev)
+        self.stats = torch.empty(B * L.GN_STATS_FLOATS_PER_BATCH, dtype=F32, device=dev)
+        z0 = torch.zeros(B, H, W, 8, dtype=F16, device=dev)
+        prog.add(K.generic_op(L.OP_NCHW_TO_NHWC, p=[self.z_in.data_ptr(), None, z0.data_ptr()],
+                              i=[B, cfg.z_channels, H, W, 8]))
+        z1 = torch.zeros(B, H, W, 8, dtype=F16, device=dev)       # channels 4..7 stay zero
+        prog.add(K.linear_desc(z0, w["pq.w"], z1[..., :cfg.z_channels], bias=w["pq.b"]))
+        top = cfg.ch * cfg.ch_mult[-1]
+        h = pool.alloc(B, H, W, top)
+        prog.add(K.conv3x3_desc(z1, w["cin.w"], h, bias=w["cin.b"]))
+        prog.keep(z0, z1)
+        h = self._res("decoder.mid.block_1", h, top, top)
+        h = self._attn("decoder.mid.attn_1", h)
+        h = self._res("decoder.mid.block_2", h, top, top)
+        for i_level, blocks, has_up in vae_decoder_levels(cfg):
+            for j, (cin, cout) in enumerate(blocks):
+                h = self._res(f"decoder.up.{i_level}.block.{j}", h, cin, cout)
+            if has_up:
+                n = f"decoder.up.{i_level}.upsample.conv"
+                Bn, hh, ww, c = h.shape
+                nh = pool.alloc(Bn, hh * 2, ww * 2, c)
+                prog.add(K.upconv3x3_descs(h, w[n + ".w"], nh, bias=w[n + ".b"]))
+                pool.free(h)
+                h = nh
+        Bn, hh, ww, c = h.shape
+        y = pool.alloc(Bn, hh, ww, c)
+        prog.add(K.group_norm_op(h, None, w["nout.g"], w["nout.b"], y, self.stats, 1e-6, True))
+        self.dec_buf = torch.zeros(Bn, hh, ww, 8, dtype=F16, device=dev)
+        prog.add(K.conv3x3_desc(y, w["cout.w"], self.dec_buf[..., :cfg.out_ch], bias=w["cout.b"]))
+        prog.add(K.generic_op(L.OP_VAE_POST, p=[self.dec_buf.data_ptr(), self.img.data_ptr()],
+                              l=[8, Bn * hh * ww]))
+        self.graph = None
+        self.use_graph = True
+
+    def _res(self, p, x, cin, cout):
+        w, pool, prog = self.eng.w, self.pool, self.prog
+        Bn, h, wd, _ = x.shape
+        y = pool.alloc(Bn, h, wd, cin)
+        prog.add(K.group_norm_op(x, None, w[p + ".gn1.g"], w[p + ".gn1.b"], y, self.stats, 1e-6, True))
+        h1 = pool.alloc(Bn, h, wd, cout)
+        prog.add(K.conv3x3_desc(y, w[p + ".conv1.w"], h1, bias=w[p + ".conv1.b"]))
+        pool.free(y)
+        y2 = pool.alloc(Bn, h, wd, cout)
+        prog.add(K.group_norm_op(h1, None, w[p + ".gn2.g"], w[p + ".gn2.b"], y2, self.stats, 1e-6, True))
+        pool.free(h1)
+        out = pool.alloc(Bn, h, wd, cout)
+        nch = K.ceil64(cout) // 64
+        segs = [(0, 0, kx - 1, ky - 1, nch) for ky in range(3) for kx in range(3)]
+        if cin == cout:
+            prog.add(K.gemm_desc([y2], segs, w[p + ".conv2.w"], out, cout, bias=w[p + ".conv2.b"], residual=x))
+        else:
+            segs.append((1, 0, 0, 0, K.ceil64(cin) // 64))
+            prog.add(K.gemm_desc([y2, x], segs, w[p + ".conv2.w"], out, cout, bias=w[p + ".conv2.b"]))
+        pool.free(y2); pool.free(x)
+        return out
+
+    def _attn(self, p, x):
+        """AttnBlock (LD.py:3631-3642): single head, d = C = 512 -> GEMM / row-softmax / GEMM per image.
+        The v bias is added after P@V (rows of P sum to 1), which lets V^T come straight out of a GEMM."""
+        w, pool, prog = self.eng.w, self.pool, self.prog
+        Bn, h, wd, c = x.shape
+        n = h * wd
+        y = pool.alloc(Bn, h, wd, c)
+        prog.add(K.group_norm_op(x, None, w[p + ".gn.g"], w[p + ".gn.b"], y, self.stats, 1e-6, False))
+        qk = pool.alloc(Bn * n, 2 * c)
+        prog.add(K.linear_desc(y, w[p + ".qk.w"], qk, bias=w[p + ".qk.b"]))
+        vt = pool.alloc(Bn, c, n)
+        s = pool.alloc(n, n, dtype=F32)
+        pm = pool.alloc(n, n)
+        o = pool.alloc(Bn * n, c)
+        y2, qk3, o3 = y.view(Bn, n, c), qk.view(Bn, n, 2 * c), o.view(Bn, n, c)
+        for b in range(Bn):
+            prog.add(K.linear_desc(w[p + ".v.w"], y2[b], vt[b]))                       # V^T = Wv @ hn^T
+            prog.add(K.linear_desc(qk3[b, :, :c], qk3[b, :, c:], s, flags=L.EPI_OUT_F32))  # S = Q K^T
+            prog.add(K.generic_op(L.OP_SOFTMAX, p=[s.data_ptr(), pm.data_ptr()], l=[n, n, n], i=[n],
+                                  f=[1.0 / math.sqrt(c)]))       # l: lds, ldo, rows
+            prog.add(K.linear_desc(pm, vt[b], o3[b], bias=w[p + ".v.b"]))             # O = P V + b_v
+        out = pool.alloc(Bn, h, wd, c)
+        prog.add(K.linear_desc(o, w[p + ".o.w"], out, bias=w[p + ".o.b"], residual=x))
+        for t in (y, qk, vt, s, pm, o, x):
+            pool.free(t)
+        return out
+
+    def run(self, z) -> torch.Tensor:
+        self.z_in.copy_(z)
+        if not self.use_graph:
+            self.prog.run()
+            return self.img
+        if self.graph is None:
+            self.prog.run()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.prog.run()
+            self.graph = g
+        self.graph.replay()
+        return self.img

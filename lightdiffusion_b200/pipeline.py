@@ -1,0 +1,137 @@
+"""txt2img hot path: noise -> 20-step sampler (CFG UNet step + fused update) -> VAE decode, and its
+data-parallel launcher (independent images sharded over ranks; one final gather of the images).
+
+Mirrors common_ksampler (LD.py:6657) -> CFGGuider.inner_sample (LD.py:2926-2965) -> KSAMPLER.sample
+(LD.py:2738-2773) -> sampler loop, then VAEDecode (LD.py:6581).  Everything on the device is a
+libldx.so kernel; the host only sequences launches.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from .engine import UNetEngine, VAEDecoderEngine, sigma_tables
+from .samplers import dpmpp2m_coefficients, get_ancestral_step, get_sigmas_karras
+
+LATENT_SCALE = 0.18215          # SD15 latent format (LD.py:137-139)
+
+
+def calculate_sigmas(scheduler: str, steps: int) -> torch.Tensor:
+    """calculate_sigmas (LD.py:3045-3054): 'karras' or 'normal' over the SD1.x discrete schedule."""
+    sig, log_sig = sigma_tables()
+    if scheduler == "karras":
+        return get_sigmas_karras(steps, float(sig[0]), float(sig[-1]))
+    if scheduler == "normal":           # normal_scheduler LD.py:2639-2651 with timestep()/sigma() of LD.py:1336-1351
+        def timestep(s):
+            return (s.log() - log_sig[:, None]).abs().argmin(dim=0).view(s.shape)
+        ts = torch.linspace(timestep(sig[-1]), timestep(sig[0]), steps)
+        out = []
+        for t in ts:
+            t = torch.clamp(t.float(), min=0, max=len(sig) - 1)
+            lo, hi, w = t.floor().long(), t.ceil().long(), t.frac()
+            out.append(float(((1 - w) * log_sig[lo] + w * log_sig[hi]).exp()))
+        return torch.FloatTensor(out + [0.0])
+    raise ValueError(f"unknown scheduler {scheduler!r}")
+
+
+def sigmas_for_denoise(scheduler: str, steps: int, denoise: Optional[float]) -> torch.Tensor:
+    """KSampler1.set_steps (LD.py:3097-3104)."""
+    if denoise is None or denoise > 0.9999:
+        return calculate_sigmas(scheduler, steps)
+    return calculate_sigmas(scheduler, int(steps / denoise))[-(steps + 1):]
+
+
+class Txt2ImgPipeline:
+    """Resident UNet + VAE decoder on one GPU.  ``sample`` returns the latent (already / 0.18215, like
+    the reference's sample()); ``generate`` also decodes to [b, 8h, 8w, 3] fp32 images in [0, 1]."""
+
+    def __init__(self, unet: UNetEngine, vae: Optional[VAEDecoderEngine]):
+        self.unet, self.vae = unet, vae
+        self.sigma_max = float(unet.sigmas[-1])
+        self.gpu_launches = 0            # kernels of ours launched by the last call
+
+    @torch.no_grad()
+    def sample(self, noise: torch.Tensor, cond: torch.Tensor, uncond: torch.Tensor, cfg_scale: float,
+               sigmas: torch.Tensor, sampler: str = "dpmpp_2m", latent: Optional[torch.Tensor] = None,
+               noise_sampler=None) -> torch.Tensor:
+        b, _, H, W = noise.shape
+        dev = self.unet.dev
+        plan = self.unet.plan(2 * b, H, W, cfg_pairs=True)
+        sig = torch.as_tensor(sigmas).detach().to("cpu", torch.float32)
+        lib, st = L.lib(), torch.cuda.current_stream().cuda_stream
+        launches = 0
+        # noise scaling (EPS.noise_scaling LD.py:1267-1274; max_denoise LD.py:2719-2722)
+        x = plan.x_in
+        noise = noise.to(dev, torch.float32)
+        max_denoise = math.isclose(self.sigma_max, float(sig[0]), rel_tol=1e-05) or float(sig[0]) > self.sigma_max
+        x.copy_(noise * torch.sqrt(1.0 + sig[0] ** 2.0) if max_denoise else noise * sig[0])
+        if latent is not None and torch.count_nonzero(latent) > 0:
+            x.add_(latent.to(dev, torch.float32) * LATENT_SCALE)      # process_latent_in (LD.py:2938-2941)
+        plan.set_context(torch.cat([uncond, cond]).to(dev))            # [uncond, cond] order, LD.py:2515
+        launches += 1
+        n = x.numel()
+        old = torch.empty_like(x)
+        have_old, h_last = False, None
+        for i in range(len(sig) - 1):
+            plan.sigma_in.fill_(float(sig[i]))
+            den = plan.run(x, plan.sigma_in, None, cfg_scale=cfg_scale)
+            launches += plan.num_launches
+            if sampler == "dpmpp_2m":
+                if sig[i + 1] == 0:
+                    x.copy_(den)
+                    h = None
+                else:
+                    c_x, c_d, c_o, h = dpmpp2m_coefficients(sig, i, h_last if have_old else None)
+                    L.check(lib.ldx_dpmpp2m_step(x.data_ptr(), den.data_ptr(), old.data_ptr() if have_old else None,
+                                                 c_x, c_d, 0.0 if c_o is None else c_o, n, st), "ldx_dpmpp2m_step")
+                    launches += 1
+                old.copy_(den)
+                have_old, h_last = True, h
+            elif sampler == "euler_ancestral":
+                sigma_down, sigma_up = get_ancestral_step(sig[i], sig[i + 1])
+                nz = None
+                if sig[i + 1] > 0:
+                    nz = (torch.randn_like(x) if noise_sampler is None else
+                          noise_sampler(sig[i], sig[i + 1]).to(dev, torch.float32).contiguous())
+                L.check(lib.ldx_euler_ancestral_step(x.data_ptr(), den.data_ptr(), None if nz is None else nz.data_ptr(),
+                                                     float(sig[i]), float(sigma_down), float(sigma_up), n, st),
+                        "ldx_euler_ancestral_step")
+                launches += 1
+            else:
+                raise ValueError(f"unknown sampler {sampler!r}")
+        self.gpu_launches = launches
+        return x / LATENT_SCALE                                      # process_latent_out (LD.py:2965)
+
+    @torch.no_grad()
+    def generate(self, noise, cond, uncond, cfg_scale, sigmas, sampler="dpmpp_2m", latent=None, noise_sampler=None):
+        z = self.sample(noise, cond, uncond, cfg_scale, sigmas, sampler, latent, noise_sampler)
+        img = self.vae.decode(z)
+        self.gpu_launches += self.vae.plan(*[z.shape[0], z.shape[2], z.shape[3]]).prog.num_launches
+        return z, img
+
+
+def shard_range(n_items: int, rank: int, world: int):
+    """Contiguous block of images for this rank (independent units; no collective on the step path)."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+def gather_images(local: torch.Tensor, n_total: int, group=None) -> Optional[torch.Tensor]:
+    """The one collective of the path: all ranks' decoded images -> rank 0 (all_gather over NCCL/NVLink
+    on GPUs, gloo in CPU tests).  ``local`` is this rank's [n_local, H, W, 3] block, padded to the
+    common shard size."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    pad = per - local.shape[0]
+    if pad:
+        local = torch.cat([local, local.new_zeros(pad, *local.shape[1:])])
+    out = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(out, local.contiguous(), group=group)
+    if dist.get_rank(group) != 0:
+        return None
+    return torch.cat(out)[:n_total]

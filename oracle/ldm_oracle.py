@@ -210,14 +210,15 @@ def unet_forward(sd: SD, cfg: UNetConfig, x, timesteps, context):
 def apply_model(sd: SD, cfg: UNetConfig, x, sigma, context, table=None, model_dtype=None):
     """BaseModel.apply_model + EPS, LD.py:5828-5860, 1259-1265. Returns denoised (fp32).
 
-    ``model_dtype`` mimics the reference's cast of xc/context to the UNet dtype.
+    ``model_dtype`` mimics the reference's cast of xc/context to the UNet dtype (values are rounded
+    to that dtype, arithmetic stays in the dtype of the weights).
     """
     table = make_sigmas_table() if table is None else table
     s = sigma.view(-1, 1, 1, 1)
     xc = x / (s ** 2 + 1.0) ** 0.5
     t = timestep_of_sigma(sigma, table.log_sigmas.to(sigma.device)).float()
     if model_dtype is not None:
-        xc, context = xc.to(model_dtype), context.to(model_dtype)
+        xc, context = xc.to(model_dtype).to(xc.dtype), context.to(model_dtype).to(context.dtype)
     eps = unet_forward(sd, cfg, xc, t, context).float()
     return x - eps * s
 
@@ -227,13 +228,13 @@ def cfg_combine(cond_pred, uncond_pred, scale: float):
     return uncond_pred + (cond_pred - uncond_pred) * scale
 
 
-def cfg_denoiser(sd: SD, cfg: UNetConfig, cond, uncond, scale: float, table=None) -> Callable:
+def cfg_denoiser(sd: SD, cfg: UNetConfig, cond, uncond, scale: float, table=None, model_dtype=None) -> Callable:
     """model(x, sigma) -> CFG-combined denoised; one batched call ordered [uncond, cond]
     (calc_cond_batch, LD.py:2515-2569; SURVEY gotcha 7)."""
     def model(x, sigma, **_):
         b = x.shape[0]
         den = apply_model(sd, cfg, torch.cat([x, x]), torch.cat([sigma, sigma]),
-                          torch.cat([uncond, cond]), table)
+                          torch.cat([uncond, cond]), table, model_dtype)
         return cfg_combine(den[b:], den[:b], scale)
     return model
 
