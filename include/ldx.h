@@ -183,7 +183,10 @@ ldx_program_t* ldx_program_create(void);
 int ldx_program_add_gemm(ldx_program_t* prog, const ldx_gemm_desc_t* d);
 int ldx_program_add_op(ldx_program_t* prog, const ldx_generic_op_t* op);
 int ldx_program_num_launches(const ldx_program_t* prog);
+int ldx_program_num_ops(const ldx_program_t* prog);
 int ldx_program_run(ldx_program_t* prog, ldx_stream_t stream);
+/* Replay with a CUDA event between ops; writes each op's device time (ms) to ms_out[n_ops]. Blocking. */
+int ldx_program_run_timed(ldx_program_t* prog, ldx_stream_t stream, float* ms_out, int n_ops);
 void ldx_program_destroy(ldx_program_t* prog);
 
 #ifdef __cplusplus

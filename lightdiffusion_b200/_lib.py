@@ -91,6 +91,8 @@ _SIGS = {
     "ldx_program_add_op": (C.c_int, [C.c_void_p, C.POINTER(GenericOp)]),
     "ldx_program_num_launches": (C.c_int, [C.c_void_p]),
     "ldx_program_run": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ldx_program_num_ops": (C.c_int, [C.c_void_p]),
+    "ldx_program_run_timed": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_float), C.c_int]),
     "ldx_program_destroy": (None, [C.c_void_p]),
 }
 

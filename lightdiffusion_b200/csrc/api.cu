@@ -138,6 +138,34 @@ extern "C" int ldx_program_run(ldx_program_t* prog, ldx_stream_t stream) {
   return LDX_OK;
 }
 
+extern "C" int ldx_program_num_ops(const ldx_program_t* prog) { return prog ? (int)prog->ops.size() : 0; }
+
+// Replays the program with a CUDA event between consecutive ops (on `stream`), synchronises, and
+// returns the device time of every op in milliseconds.  Used by bench.py for the per-kernel roofline.
+extern "C" int ldx_program_run_timed(ldx_program_t* prog, ldx_stream_t stream, float* ms_out, int n) {
+  LDX_CHECK_ARG(prog && ms_out && n == (int)prog->ops.size(), "program_run_timed: bad args");
+  cudaStream_t st = as_stream(stream);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (int i = 0; i <= n; ++i) LDX_CUDA(cudaEventCreate(&ev[i]));
+  LDX_CUDA(cudaEventRecord(ev[0], st));
+  int rc = LDX_OK;
+  for (int i = 0; i < n && rc == LDX_OK; ++i) {
+    const ProgOp& op = prog->ops[i];
+    if (op.kind == LDX_OP_GEMM) rc = gemm_launch(op.gemm, st);
+    else if (op.kind == LDX_OP_ATTENTION) rc = attention_run_handle(op.attn, st);
+    else rc = run_generic_op(&op.gen, st);
+    if (rc == LDX_OK && cudaEventRecord(ev[i + 1], st) != cudaSuccess) rc = LDX_E_CUDA;
+  }
+  if (rc == LDX_OK) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+  }
+  if (rc == LDX_OK)
+    for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  for (int i = 0; i <= n; ++i) cudaEventDestroy(ev[i]);
+  return rc;
+}
+
 extern "C" void ldx_program_destroy(ldx_program_t* prog) {
   if (!prog) return;
   for (ProgOp& op : prog->ops) {

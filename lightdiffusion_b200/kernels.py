@@ -257,15 +257,24 @@ class Program:
         L.require_device()
         self._h = L.lib().ldx_program_create()
         self._keep = []          # tensors referenced by raw pointers
+        self.meta = []           # per op: (kind, executed flops, tag) for profiling
 
     def add(self, op, keep=()):
         if isinstance(op, L.GemmDesc):
             L.check(L.lib().ldx_program_add_gemm(self._h, C.byref(op)), "ldx_program_add_gemm")
+            k = 64 * sum(op.seg[i].nchunks for i in range(op.nseg))
+            self.meta.append(("gemm", 2.0 * op.W * op.H * op.B * op.N * k, (op.W * op.H * op.B, op.N, k)))
         elif isinstance(op, (list, tuple)):
             for o in op:
                 self.add(o)
         else:
             L.check(L.lib().ldx_program_add_op(self._h, C.byref(op)), "ldx_program_add_op")
+            flops = 0.0
+            if op.kind == L.OP_ATTENTION:
+                b, nq, nk, heads, d = (op.i[j] for j in range(5))
+                flops = 4.0 * b * nq * nk * heads * d
+            self.meta.append(({L.OP_ATTENTION: "attention", L.OP_GROUP_NORM: "group_norm",
+                               L.OP_LAYER_NORM: "layer_norm"}.get(op.kind, "other"), flops, None))
         self._keep.extend(keep)
 
     def keep(self, *tensors):
@@ -277,6 +286,13 @@ class Program:
 
     def run(self):
         L.check(L.lib().ldx_program_run(self._h, _stream()), "ldx_program_run")
+
+    def run_timed(self):
+        """Blocking replay with per-op device times; returns [(kind, flops, tag, ms)]."""
+        n = L.lib().ldx_program_num_ops(self._h)
+        ms = (C.c_float * n)()
+        L.check(L.lib().ldx_program_run_timed(self._h, _stream(), ms, n), "ldx_program_run_timed")
+        return [(m[0], m[1], m[2], ms[i]) for i, m in enumerate(self.meta)]
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
