@@ -31,6 +31,7 @@ int num_sms() {
   return n;
 }
 
+int group_norm_num_launches(int C, int HW);
 int attention_prepare_op(const ldx_generic_op_t* op, void** handle);
 int attention_run_handle(void* handle, cudaStream_t st);
 void attention_free_handle(void* handle);
@@ -108,7 +109,7 @@ extern "C" int ldx_program_add_op(ldx_program_t* prog, const ldx_generic_op_t* g
     int rc = attention_prepare_op(gop, &op.attn);
     if (rc) return rc;
   } else if (gop->kind == LDX_OP_GROUP_NORM) {
-    op.launches = 2;
+    op.launches = group_norm_num_launches(gop->i[0] + gop->i[1], gop->i[3]);
   } else if (gop->kind == LDX_OP_GEMM) {
     set_error("use ldx_program_add_gemm for GEMM ops");
     return LDX_E_INVALID;

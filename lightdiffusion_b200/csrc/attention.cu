@@ -99,31 +99,40 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
   const uint32_t tO = tmem_base + 64;     // DN fp32 columns
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---- TMA producer: warp-uniform loop, one elected lane issues
+    if (elect_one()) {
       mbar_arrive_expect_tx(&bars->q_full, C::Q_BYTES);
       for (int c = 0; c < C::DCH; ++c) tma_load_4d(sQ + c * (BQ * 128), &p.qmap, &bars->q_full, c * 64, h, q0, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int ks = j % C::KST, vs = j % C::VST;
-        mbar_wait(&bars->k_empty[ks], ((j / C::KST) & 1) ^ 1);
+    }
+    __syncwarp();
+    for (int j = 0; j < nkv; ++j) {
+      const int ks = j % C::KST, vs = j % C::VST;
+      mbar_wait(&bars->k_empty[ks], ((j / C::KST) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars->k_full[ks], C::KV_BYTES);
         for (int c = 0; c < C::DCH; ++c)
           tma_load_4d(sK + ks * C::KV_BYTES + c * (BKV * 128), &p.kmap, &bars->k_full[ks], c * 64, h, j * BKV, b);
-        mbar_wait(&bars->v_empty[vs], ((j / C::VST) & 1) ^ 1);
+      }
+      __syncwarp();
+      mbar_wait(&bars->v_empty[vs], ((j / C::VST) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars->v_full[vs], C::KV_BYTES);
         for (int c = 0; c < C::DCH; ++c)
           tma_load_4d(sV + vs * C::KV_BYTES + c * (BKV * 128), &p.vmap, &bars->v_full[vs], c * 64, h, j * BKV, b);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_f16(BQ, BKV, 0, 0);
-      const uint32_t idesc_o = umma_idesc_f16(BQ, C::DN, 0, 1);       // B = V is MN-major
-      const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-      auto mma_s = [&](int j) {
-        const int ks = j % C::KST;
-        mbar_wait(&bars->k_full[ks], (j / C::KST) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + ks * C::KV_BYTES);
+    // ---- MMA issuer: warp-uniform control flow, one elected lane issues tcgen05.mma / commit
+    const uint32_t idesc_s = umma_idesc_f16(BQ, BKV, 0, 0);
+    const uint32_t idesc_o = umma_idesc_f16(BQ, C::DN, 0, 1);       // B = V is MN-major
+    const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
+    auto mma_s = [&](int j) {
+      const int ks = j % C::KST;
+      mbar_wait(&bars->k_full[ks], (j / C::KST) & 1);
+      tc_fence_after();
+      const uint32_t k_addr = smem_u32(sK + ks * C::KV_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < C::DK; ++s) {
           const uint32_t qa = q_addr + (s / 4) * (BQ * 128) + (s % 4) * 32;
@@ -132,20 +141,23 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
         }
         umma_commit(&bars->k_empty[ks]);
         umma_commit(&bars->s_full);
-      };
-      mbar_wait(&bars->q_full, 0);
-      mma_s(0);
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {
-          mbar_wait(&bars->s_free, j & 1);
-          tc_fence_after();
-          mma_s(j + 1);
-        }
-        const int vs = j % C::VST;
-        mbar_wait(&bars->p_full, j & 1);
-        mbar_wait(&bars->v_full[vs], (j / C::VST) & 1);
+      }
+      __syncwarp();
+    };
+    mbar_wait(&bars->q_full, 0);
+    mma_s(0);
+    for (int j = 0; j < nkv; ++j) {
+      if (j + 1 < nkv) {
+        mbar_wait(&bars->s_free, j & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + vs * C::KV_BYTES);
+        mma_s(j + 1);
+      }
+      const int vs = j % C::VST;
+      mbar_wait(&bars->p_full, j & 1);
+      mbar_wait(&bars->v_full[vs], (j / C::VST) & 1);
+      tc_fence_after();
+      const uint32_t v_addr = smem_u32(sV + vs * C::KV_BYTES);
+      if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < BKV / 16; ++s) {
           umma_f16_ss(tO, umma_desc_kmajor_sw128(p_addr + s * 32),
@@ -154,6 +166,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
         umma_commit(&bars->v_empty[vs]);
         umma_commit(&bars->o_done);
       }
+      __syncwarp();
     }
   } else {
     // ------------------------------------------------------------------ softmax warps
@@ -168,15 +181,21 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
       mbar_wait(&bars->s_full, j & 1);
       tc_fence_after();
       const int kv_left = p.Nk - j * BKV;   // valid keys in this tile (>= 1)
+      const bool full_tile = kv_left >= BKV;   // only the last tile of a ragged Nk needs key masking
       uint32_t r[32];
       float m_tile = -INFINITY;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         tmem_ld32(tS + lane_off + hf * 32, r);
         tmem_ld_wait();
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (hf * 32 + i < kv_left) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (hf * 32 + i < kv_left) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
+        }
       }
       if (j > 0) {
         mbar_wait(&bars->o_done, (j - 1) & 1);   // P buffer and O are free again
@@ -188,7 +207,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
         m_used = m_tile;
       } else if (__any_sync(0xffffffffu, grow)) {
         const float m_new = fmaxf(m_used, m_tile);
-        const float alpha = exp2f((m_used - m_new) * c);
+        const float alpha = ex2_approx((m_used - m_new) * c);
         m_used = m_new;
         l *= alpha;
 #pragma unroll
@@ -208,6 +227,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
         tmem_st_wait();
       }
       const float mc = m_used * c;
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         tmem_ld32(tS + lane_off + hf * 32, r);
@@ -218,14 +238,26 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
           if (lane == 0) mbar_arrive(&bars->s_free);   // S may be overwritten by the next Q K^T
         }
         uint32_t pk[16];
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = exp2f(__uint_as_float(r[2 * i]) * c - mc);
-          float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * c - mc);
-          if (hf * 32 + 2 * i >= kv_left) p0 = 0.f;
-          if (hf * 32 + 2 * i + 1 >= kv_left) p1 = 0.f;
-          l += p0 + p1;
-          pk[i] = pack_h2(p0, p1);
+          for (int i = 0; i < 16; ++i) {
+            const float p0 = ex2_approx(__uint_as_float(r[2 * i]) * c - mc);
+            const float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) * c - mc);
+            l0 += p0;
+            l1 += p1;
+            pk[i] = pack_h2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float p0 = ex2_approx(__uint_as_float(r[2 * i]) * c - mc);
+            float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) * c - mc);
+            if (hf * 32 + 2 * i >= kv_left) p0 = 0.f;
+            if (hf * 32 + 2 * i + 1 >= kv_left) p1 = 0.f;
+            l0 += p0;
+            l1 += p1;
+            pk[i] = pack_h2(p0, p1);
+          }
         }
         // 32 keys = 4 16-byte chunks; chunk index XOR (row % 8) is the SWIZZLE_128B pattern
 #pragma unroll
@@ -235,6 +267,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
               make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
         }
       }
+      l += l0 + l1;
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();

@@ -39,7 +39,20 @@ __global__ void gn_stats_kernel(const GnArgs a) {
   const int p_begin = slab * a.pix_per_slab;
   const int p_end = min(a.HW, p_begin + a.pix_per_slab);
   if (pl < a.P) {
-    for (int pix = p_begin + pl; pix < p_end; pix += a.P) {
+    int pix = p_begin + pl;
+    for (; pix + 3 * a.P < p_end; pix += 4 * a.P) {     // 4 independent 16-byte loads in flight
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = gn_load(a, b, pix + u * a.P, vec);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f0 = unpack_h2(v[u].x), f1 = unpack_h2(v[u].y), f2 = unpack_h2(v[u].z), f3 = unpack_h2(v[u].w);
+        const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
+      }
+    }
+    for (; pix < p_end; pix += a.P) {
       const uint4 v = gn_load(a, b, pix, vec);
       const float2 f0 = unpack_h2(v.x), f1 = unpack_h2(v.y), f2 = unpack_h2(v.z), f3 = unpack_h2(v.w);
       const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
@@ -65,18 +78,29 @@ __global__ void gn_stats_kernel(const GnArgs a) {
 __global__ void gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_slab_apply) {
   __shared__ float s_mean[32], s_rstd[32];
   const int b = blockIdx.x, slab = blockIdx.y;
-  if (threadIdx.x < 32) {
+  {
+    // 8 threads per group sum the slab partials in a fixed order (bit-reproducible), in double
+    const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
     double s = 0.0, ss = 0.0;
-    for (int k = 0; k < a.nslab; ++k) {
-      s += (double)a.partial[(((size_t)b * a.nslab + k) * 32 + threadIdx.x) * 2 + 0];
-      ss += (double)a.partial[(((size_t)b * a.nslab + k) * 32 + threadIdx.x) * 2 + 1];
+    if (g < 32) {
+      for (int k = sub; k < a.nslab; k += 8) {
+        s += (double)a.partial[(((size_t)b * a.nslab + k) * 32 + g) * 2 + 0];
+        ss += (double)a.partial[(((size_t)b * a.nslab + k) * 32 + g) * 2 + 1];
+      }
     }
-    const double n = (double)a.HW * a.cpg;
-    const double mean = s / n;
-    double var = ss / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = (float)mean;
-    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)a.eps));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (g < 32 && sub == 0) {
+      const double n = (double)a.HW * a.cpg;
+      const double mean = s / n;
+      double var = ss / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = (float)(1.0 / sqrt(var + (double)a.eps));
+    }
   }
   __syncthreads();
   const int vec = threadIdx.x % a.nvec, pl = threadIdx.x / a.nvec;
@@ -92,8 +116,7 @@ __global__ void gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_sla
   }
   const int p_begin = slab * pix_per_slab_apply;
   const int p_end = min(a.HW, p_begin + pix_per_slab_apply);
-  for (int pix = p_begin + pl; pix < p_end; pix += a.P) {
-    const uint4 v = gn_load(a, b, pix, vec);
+  auto apply_store = [&](const uint4& v, int pix) {
     const float2 f0 = unpack_h2(v.x), f1 = unpack_h2(v.y), f2 = unpack_h2(v.z), f3 = unpack_h2(v.w);
     float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
@@ -104,7 +127,86 @@ __global__ void gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_sla
     uint4 o;
     o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
     *reinterpret_cast<uint4*>(a.y + ((int64_t)b * a.HW + pix) * a.ldy + vec * 8) = o;
+  };
+  int pix = p_begin + pl;
+  for (; pix + 3 * a.P < p_end; pix += 4 * a.P) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = gn_load(a, b, pix + u * a.P, vec);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) apply_store(v[u], pix + u * a.P);
   }
+  for (; pix < p_end; pix += a.P) apply_store(gn_load(a, b, pix, vec), pix);
+}
+
+// Small maps (8x8 / 16x16 levels): one CTA per (batch, group) keeps its HW x cpg slice in registers and
+// does stats + apply in a single launch.  Requires cpg % 8 == 0 and HW*cpg/8 <= 256*GN_SMALL_VPT vectors.
+static constexpr int GN_SMALL_VPT = 8;
+__global__ void __launch_bounds__(256) gn_small_kernel(const GnArgs a) {
+  __shared__ float red[2][8];
+  __shared__ float s_stat[2];
+  const int b = blockIdx.x >> 5, g = blockIdx.x & 31;
+  const int vpg = a.cpg >> 3;                 // 16-byte vectors per group per pixel
+  const int nv = a.HW * vpg;
+  uint4 v[GN_SMALL_VPT];
+  float s = 0.f, ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < GN_SMALL_VPT; ++u) {
+    const int idx = threadIdx.x + u * 256;
+    if (idx < nv) {
+      v[u] = gn_load(a, b, idx / vpg, g * vpg + idx % vpg);
+      const float2 f0 = unpack_h2(v[u].x), f1 = unpack_h2(v[u].y), f2 = unpack_h2(v[u].z), f3 = unpack_h2(v[u].w);
+      s += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+      ss += ((f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y)) +
+            ((f2.x * f2.x + f2.y * f2.y) + (f3.x * f3.x + f3.y * f3.y));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tss = 0.0;
+    for (int w = 0; w < 8; ++w) { ts += (double)red[0][w]; tss += (double)red[1][w]; }
+    const double n = (double)a.HW * a.cpg;
+    const double mean = ts / n;
+    double var = tss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_stat[0] = (float)mean;
+    s_stat[1] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  __syncthreads();
+  const float mean = s_stat[0], rstd = s_stat[1];
+#pragma unroll
+  for (int u = 0; u < GN_SMALL_VPT; ++u) {
+    const int idx = threadIdx.x + u * 256;
+    if (idx < nv) {
+      const int pix = idx / vpg, vec = g * vpg + idx % vpg;
+      const float2 f0 = unpack_h2(v[u].x), f1 = unpack_h2(v[u].y), f2 = unpack_h2(v[u].z), f3 = unpack_h2(v[u].w);
+      float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(a.gamma + vec * 8)), g1 = __ldg(reinterpret_cast<const float4*>(a.gamma + vec * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(a.beta + vec * 8)), b1 = __ldg(reinterpret_cast<const float4*>(a.beta + vec * 8) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float w = gg[j] * rstd;
+        f[j] = f[j] * w + (bb[j] - mean * w);
+        if (a.silu) f[j] = silu_f(f[j]);
+      }
+      uint4 o;
+      o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(a.y + ((int64_t)b * a.HW + pix) * a.ldy + vec * 8) = o;
+    }
+  }
+}
+
+int group_norm_num_launches(int C, int HW) {
+  const int cpg = C / 32;
+  return (cpg % 8 == 0 && (int64_t)HW * (cpg / 8) <= 256 * GN_SMALL_VPT) ? 1 : 2;
 }
 
 static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1, int B, int HW,
@@ -119,10 +221,19 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
   a.x0 = (const __half*)x0; a.x1 = (const __half*)x1;
   a.c0 = c0; a.c1 = c1; a.ld0 = ld0; a.ld1 = ld1;
   a.HW = HW; a.C = C; a.cpg = C / 32; a.nvec = C / 8;
+  if (a.cpg % 8 == 0 && (int64_t)HW * (a.cpg / 8) <= 256 * GN_SMALL_VPT &&
+      reinterpret_cast<uintptr_t>(gamma) % 16 == 0 && reinterpret_cast<uintptr_t>(beta) % 16 == 0) {
+    a.P = 1; a.pix_per_slab = HW; a.nslab = 1;
+    a.eps = eps; a.silu = silu; a.gamma = gamma; a.beta = beta;
+    a.y = (__half*)y; a.ldy = ldy; a.partial = stats;
+    gn_small_kernel<<<B * 32, 256, 0, stream>>>(a);
+    LDX_CUDA(cudaGetLastError());
+    return LDX_OK;
+  }
   a.P = a.nvec >= 256 ? 1 : 256 / a.nvec;
   if (a.P > HW) a.P = HW;
   int threads = ((a.nvec * a.P + 31) / 32) * 32;
-  if (threads < 64) threads = 64;   // the group reduction uses the first 64 threads
+  if (threads < 256) threads = 256;   // the reductions use the first 64 (stats) / 256 (apply) threads
   LDX_CHECK_ARG(threads <= 1024, "group_norm: C too large for one block");
   // stats workspace holds [B][nslab][32][2]; nslab bounded so that it fits LDX_GN_MAX_SLABS
   const int sms = num_sms();
@@ -159,58 +270,83 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
 }
 
 // ----------------------------------------------------------------------------- LayerNorm
-// One warp per row, row held in registers (two-pass variance). bytes: read + write rows*C*2.
+// One warp per row at a time (grid-stride over rows), row held in registers (two-pass variance); the
+// affine parameters of a lane's columns are loaded once and reused for every row. bytes: r+w rows*C*2.
 template <int VPL>
-__global__ void layer_norm_kernel(const __half* __restrict__ x, int64_t ldx_, int rows, int C, float eps,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  __half* __restrict__ y, int64_t ldy) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+__global__ void __launch_bounds__(256) layer_norm_kernel(const __half* __restrict__ x, int64_t ldx_, int rows, int C,
+                                                         float eps, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, __half* __restrict__ y,
+                                                         int64_t ldy) {
   const int lane = threadIdx.x & 31;
-  if (warp >= rows) return;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int nvec = C >> 3;
-  const __half* xr = x + (int64_t)warp * ldx_;
-  float f[VPL][8];
-  float sum = 0.f;
+  constexpr bool kParamsInRegs = VPL <= 2;   // wider rows re-read the (L1-resident) parameters as float4
+  constexpr int PV = kParamsInRegs ? VPL : 1;
+  float g[PV][8], bt[PV][8];
+  if constexpr (kParamsInRegs) {
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      const uint4 u = __ldg(reinterpret_cast<const uint4*>(xr + v * 8));
-      const float2 a = unpack_h2(u.x), b = unpack_h2(u.y), c = unpack_h2(u.z), d = unpack_h2(u.w);
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        g[i][j] = v < nvec ? __ldg(gamma + v * 8 + j) : 0.f;
+        bt[i][j] = v < nvec ? __ldg(beta + v * 8 + j) : 0.f;
+      }
+    }
+  }
+  const float inv_c = 1.0f / (float)C;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_total) {
+    const __half* xr = x + (int64_t)r * ldx_;
+    uint4 u[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      u[i] = v < nvec ? __ldg(reinterpret_cast<const uint4*>(xr + v * 8)) : make_uint4(0, 0, 0, 0);
+    }
+    float f[VPL][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float2 a = unpack_h2(u[i].x), b = unpack_h2(u[i].y), c = unpack_h2(u[i].z), d = unpack_h2(u[i].w);
       f[i][0] = a.x; f[i][1] = a.y; f[i][2] = b.x; f[i][3] = b.y; f[i][4] = c.x; f[i][5] = c.y; f[i][6] = d.x; f[i][7] = d.y;
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum += f[i][j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[i][j] = 0.f;
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / C;
-  float var = 0.f;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float var = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + i * 32 < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var += d * d; }
+        for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; var += d * d; }
+      }
     }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  const float rstd = rsqrtf(var / C + eps);
-  __half* yr = y + (int64_t)warp * ldy;
+    for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = rsqrtf(var * inv_c + eps);
+    __half* yr = y + (int64_t)r * ldy;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      float o[8];
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float o[8];
+        if constexpr (kParamsInRegs) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * __ldg(gamma + v * 8 + j) + __ldg(beta + v * 8 + j);
-      uint4 u;
-      u.x = pack_h2(o[0], o[1]); u.y = pack_h2(o[2], o[3]); u.z = pack_h2(o[4], o[5]); u.w = pack_h2(o[6], o[7]);
-      *reinterpret_cast<uint4*>(yr + v * 8) = u;
+          for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * g[i][j] + bt[i][j];
+        } else {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8) + 1);
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8) + 1);
+          const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = (f[i][j] - mean) * rstd * gg[j] + bb[j];
+        }
+        uint4 w;
+        w.x = pack_h2(o[0], o[1]); w.y = pack_h2(o[2], o[3]); w.z = pack_h2(o[4], o[5]); w.w = pack_h2(o[6], o[7]);
+        *reinterpret_cast<uint4*>(yr + v * 8) = w;
+      }
     }
   }
 }
@@ -219,8 +355,12 @@ static int layer_norm_impl(const void* x, int64_t ldx_, int rows, int C, float e
                            const float* beta, void* y, int64_t ldy, cudaStream_t stream) {
   LDX_CHECK_ARG(x && y && gamma && beta, "layer_norm: null pointer");
   LDX_CHECK_ARG(C % 8 == 0 && C <= 2048 && ldx_ % 8 == 0 && ldy % 8 == 0, "layer_norm: C=%d unsupported", C);
+  LDX_CHECK_ARG(reinterpret_cast<uintptr_t>(gamma) % 16 == 0 && reinterpret_cast<uintptr_t>(beta) % 16 == 0,
+                "layer_norm: gamma/beta must be 16-byte aligned");
   const int threads = 256;
-  const int blocks = (rows * 32 + threads - 1) / threads;
+  int blocks = (rows * 32 + threads - 1) / threads;
+  const int cap = num_sms() * 8;          // persistent: every warp walks several rows
+  if (blocks > cap) blocks = cap;
   const int vpl = (C / 8 + 31) / 32;
   const __half* xx = (const __half*)x;
   __half* yy = (__half*)y;

@@ -17,6 +17,8 @@
 //   (tcgen05.ld -> bias / timestep-embedding row add / residual / SiLU / GEGLU -> fp16 stores).
 //
 // Roofline: tensor-pipe bound; algorithmic FLOPs = 2 * M * N * K.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -25,14 +27,22 @@ namespace ldx {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
-static constexpr int GEMM_THREADS = 192;
-static constexpr int MAX_STAGES = 8;
+static constexpr int EPI_GROUPS = 2;                          // epilogue warpgroups (4 warps = 128 TMEM lanes each)
+static constexpr int GEMM_THREADS = 64 + EPI_GROUPS * 128;   // warp 0 TMA, warp 1 MMA, then the epilogue groups
+static constexpr int MAX_STAGES = 6;
+
+static constexpr int EPI_CHUNK = 32;                         // output columns per staged chunk
+static constexpr int EPI_BUF_BYTES = BM * EPI_CHUNK * 2;     // 8 KiB, SWIZZLE_64B rows of 64 bytes
+static constexpr int EPI_NBUF = 4;                           // staging buffers per epilogue group
+static constexpr int EPI_THREADS = 128;
+static constexpr int EPI_SMEM = EPI_GROUPS * EPI_NBUF * EPI_BUF_BYTES;
 
 struct __align__(8) GemmBarriers {
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
+  uint64_t res_full[EPI_GROUPS * EPI_NBUF];
   uint32_t tmem_base;
 };
 
@@ -56,7 +66,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, uint32_t tm
         a += __ldg(p.bias + n_packed + j);
         gt += __ldg(p.bias + n_packed + p.bn / 2 + j);
       }
-      v[j] = a * gelu_erf_f(gt);
+      v[j] = a * gelu_erf_fast(gt);
     }
   } else {
     tmem_ld_wait();
@@ -117,6 +127,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, uint32_t tm
   }
 }
 
+// kCtas = 1: one CTA per 128 x bn tile.  kCtas = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per
+// 256 x bn tile: each CTA loads its own 128 A rows and HALF of the B tile, so the L2->smem operand
+// traffic per FLOP drops by a third and the MMA reads B from both CTAs' shared memory.
+template <int kCtas>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -125,10 +139,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int stages = p.stages;
-  const uint32_t b_stage_bytes = (uint32_t)p.bn * BK * 2;
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const int worker = (int)blockIdx.x / kCtas, nworkers = (int)gridDim.x / kCtas;
+  const int bn_cta = p.bn / kCtas;                           // B rows this CTA loads
+  const uint32_t b_stage_bytes = (uint32_t)bn_cta * BK * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)stages * A_STAGE_BYTES;
-  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sB + (size_t)stages * b_stage_bytes);
+  uint8_t* sC = sB + (size_t)stages * b_stage_bytes;          // EPI_NBUF staging buffers (1024-aligned)
+  GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sC + EPI_SMEM);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < LDX_MAX_SRC; ++i) tma_prefetch_desc(&p.amap[i]);
@@ -139,37 +157,59 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&bars->tmem_full[a], 1);
-      mbar_init(&bars->tmem_empty[a], 4);
+      mbar_init(&bars->tmem_empty[a], 4 * EPI_GROUPS * kCtas);
     }
+    for (int a = 0; a < EPI_GROUPS * EPI_NBUF; ++a) mbar_init(&bars->res_full[a], 1);
+    tma_prefetch_desc(&p.omap);
+    tma_prefetch_desc(&p.rmap);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(&bars->tmem_base, p.tmem_cols);
-    tmem_relinquish();
+    if constexpr (kCtas == 2) {
+      tmem_alloc_pair(&bars->tmem_base, p.tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(&bars->tmem_base, p.tmem_cols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
+        const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * kCtas + (int)cta_rank;
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
-        const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * p.bn;
+        const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * p.bn + (int)cta_rank * bn_cta;
         int kcol = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const KSeg sg = p.seg[s];
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             mbar_wait(&bars->empty[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&bars->full[stage], A_STAGE_BYTES + b_stage_bytes);
-            tma_load_4d(sA + (size_t)stage * A_STAGE_BYTES, &p.amap[sg.map], &bars->full[stage], sg.c0 + ch * BK,
-                        x0 + sg.dx, y0 + sg.dy, b0);
-            tma_load_2d(sB + (size_t)stage * b_stage_bytes, &p.bmap, &bars->full[stage], kcol, n0);
+            uint8_t* dA = sA + (size_t)stage * A_STAGE_BYTES;
+            uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
+            if constexpr (kCtas == 2) {
+              // both CTAs' loads complete on the leader's barrier, which the leader arms for the pair
+              const uint32_t lbar = mapa_shared(smem_u32(&bars->full[stage]), 0);
+              if (elect_one()) {
+                if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2 * (A_STAGE_BYTES + b_stage_bytes));
+                tma_load_4d_pair(dA, &p.amap[sg.map], lbar, sg.c0 + ch * BK, x0 + sg.dx, y0 + sg.dy, b0);
+                tma_load_2d_pair(dB, &p.bmap, lbar, kcol, n0);
+              }
+            } else {
+              if (elect_one()) {
+                mbar_arrive_expect_tx(&bars->full[stage], A_STAGE_BYTES + b_stage_bytes);
+                tma_load_4d(dA, &p.amap[sg.map], &bars->full[stage], sg.c0 + ch * BK, x0 + sg.dx, y0 + sg.dy, b0);
+                tma_load_2d(dB, &p.bmap, &bars->full[stage], kcol, n0);
+              }
+            }
+            __syncwarp();
             kcol += BK;
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
@@ -177,13 +217,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (single thread)
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(BM, p.bn);
+    // ------------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform
+    // loop, one elected lane issues)
+    if (cta_rank == 0) {
+      const uint32_t idesc = umma_idesc_f16(BM * kCtas, p.bn);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = worker; tile < p.num_tiles; tile += nworkers, ++it) {
         const int as = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
@@ -194,47 +235,208 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_f16_ss(d_tmem, umma_desc_kmajor_sw128(a_addr + k * 32), umma_desc_kmajor_sw128(b_addr + k * 32),
-                        idesc, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < BK / 16; ++k) {
+              const uint64_t ad = umma_desc_kmajor_sw128(a_addr + k * 32), bd = umma_desc_kmajor_sw128(b_addr + k * 32);
+              if constexpr (kCtas == 2) umma_f16_ss_pair(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+              else umma_f16_ss(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+            }
+            // frees the smem stage (in both CTAs) once these MMAs have read it
+            if constexpr (kCtas == 2) umma_commit_pair(&bars->empty[stage], 3); else umma_commit(&bars->empty[stage]);
+            // accumulator complete -> epilogue (of both CTAs)
+            if (kb == p.nk - 1) {
+              if constexpr (kCtas == 2) umma_commit_pair(&bars->tmem_full[as], 3); else umma_commit(&bars->tmem_full[as]);
+            }
           }
-          umma_commit(&bars->empty[stage]);     // frees the smem stage once these MMAs have read it
+          __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bars->tmem_full[as]);      // accumulator complete -> epilogue
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue: EPI_GROUPS warpgroups.
+    // Group g owns the 32-column chunks c = g, g + EPI_GROUPS, ... of every tile; a thread owns one row.
+    // Per chunk: TMEM -> regs -> (+bias, +rowadd, +residual tile that TMA prefetched into the staging
+    // buffer, activation) -> fp16 into the SWIZZLE_64B staging tile -> TMA store (coalesced, clipped).
+    const int grp = (warp - 2) >> 2;
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const bool geglu = (p.flags & LDX_EPI_GEGLU) != 0;
     const bool f32 = (p.flags & LDX_EPI_OUT_F32) != 0;
     const int n_out_tile = geglu ? p.bn / 2 : p.bn;
+    const int n_out_total = geglu ? p.N / 2 : p.N;
     const int osz = f32 ? 4 : 2;
+    const bool elected = ((threadIdx.x - 64) & 127) == 0;   // first thread of the group issues its TMA traffic
+    uint8_t* sCg = sC + grp * (EPI_NBUF * EPI_BUF_BYTES);
+    uint64_t* res_full = &bars->res_full[grp * EPI_NBUF];
+    const uint32_t leader_empty0 = kCtas == 2 ? mapa_shared(smem_u32(&bars->tmem_empty[0]), 0) : 0u;
+    const uint32_t leader_empty1 = kCtas == 2 ? mapa_shared(smem_u32(&bars->tmem_empty[1]), 0) : 0u;
+    auto release_tmem = [&](int as) {
+      if constexpr (kCtas == 2) mbar_arrive_cluster(as ? leader_empty1 : leader_empty0);
+      else mbar_arrive(&bars->tmem_empty[as]);
+    };
+    auto tile_nchunk = [&](int tile) {
+      const int n_out0 = (tile % p.n_tiles) * n_out_tile;
+      return (min(n_out_tile, n_out_total - n_out0) + EPI_CHUNK - 1) / EPI_CHUNK;
+    };
+    // residual prefetch cursor: runs EPI_RES_AHEAD items ahead of the consume cursor over the same sequence
+    constexpr int EPI_RES_AHEAD = 2;
+    int pf_tile = worker, pf_chunk = grp;
+    uint32_t pf_idx = 0;
+    auto pf_normalise = [&]() {
+      while (pf_tile < p.num_tiles && pf_chunk >= tile_nchunk(pf_tile)) { pf_tile += nworkers; pf_chunk = grp; }
+    };
+    auto pf_issue = [&]() {                     // elected thread only
+      pf_normalise();
+      if (pf_tile >= p.num_tiles) return;
+      const int nt = pf_tile % p.n_tiles, mt = (pf_tile / p.n_tiles) * kCtas + (int)cta_rank;
+      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+      const uint32_t buf = pf_idx % EPI_NBUF;
+      mbar_arrive_expect_tx(&res_full[buf], EPI_BUF_BYTES);
+      tma_load_4d(sCg + buf * EPI_BUF_BYTES, &p.rmap, &res_full[buf], nt * n_out_tile + pf_chunk * EPI_CHUNK,
+                  tx * p.bw, ty * p.bh, tb * p.bb);
+      pf_chunk += EPI_GROUPS;
+      ++pf_idx;
+    };
+    const bool use_res = p.tma_epi && p.res != nullptr;
+    if (use_res && elected) {
+      for (int i = 0; i < EPI_RES_AHEAD; ++i) pf_issue();
+    }
+    uint32_t cidx = 0;                          // this group's running chunk counter (staging buffer ring)
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < p.num_tiles; tile += nworkers, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * kCtas + (int)cta_rank;
       const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
-      const int x = tx * p.bw + row % p.bw;
-      const int y = ty * p.bh + (row / p.bw) % p.bh;
-      const int b = tb * p.bb + row / (p.bw * p.bh);
+      const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+      const int x = x0 + row % p.bw;
+      const int y = y0 + (row / p.bw) % p.bh;
+      const int b = b0 + row / (p.bw * p.bh);
       const bool valid = (x < p.W) && (y < p.H) && (b < p.B);
+      const float* rowadd_row = (p.rowadd && valid) ? p.rowadd + (int64_t)b * p.ld_rowadd : nullptr;
+      const int n_out0 = nt * n_out_tile;
+      const uint32_t trow = tmem_base + as * p.acc_stride + ((uint32_t)(q * 32) << 16);
+      const int nchunk = tile_nchunk(tile);
+
+      mbar_wait(&bars->tmem_full[as], aphase);
+      tc_fence_after();
+
+      if (p.flags & (1 << 17)) {               // debug: epilogue only drains the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release_tmem(as);
+        continue;
+      }
+      if (p.tma_epi) {
+        int last_c = grp;                       // this group's last chunk of the tile
+        while (last_c + EPI_GROUPS < nchunk) last_c += EPI_GROUPS;
+        if (grp >= nchunk) {                    // nothing to do for this group in a narrow tile
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_tmem(as);
+          continue;
+        }
+        for (int c = grp; c < nchunk; c += EPI_GROUPS, ++cidx) {
+          const uint32_t buf = cidx % EPI_NBUF;
+          uint8_t* cbuf = sCg + buf * EPI_BUF_BYTES;
+          const int n_glob = n_out0 + c * EPI_CHUNK;
+          if (elected) {
+            tma_store_wait_read<1>();           // stores older than the previous chunk have drained their buffers
+            if (use_res) pf_issue();            // residual tile EPI_RES_AHEAD chunks ahead (buffer of chunk cidx-2)
+          }
+          uint32_t r[32];
+          float v[32];
+          tmem_ld32(trow + c * EPI_CHUNK, r);
+          if (geglu) {
+            uint32_t g[32];
+            tmem_ld32(trow + c * EPI_CHUNK + p.bn / 2, g);
+            tmem_ld_wait();
+            const int n_packed = nt * p.bn + c * EPI_CHUNK;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+              if (p.bias) {
+                ba = __ldg(reinterpret_cast<const float4*>(p.bias + n_packed) + j4);
+                bg = __ldg(reinterpret_cast<const float4*>(p.bias + n_packed + p.bn / 2) + j4);
+              }
+              v[j4 * 4 + 0] = (__uint_as_float(r[j4 * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 0]) + bg.x);
+              v[j4 * 4 + 1] = (__uint_as_float(r[j4 * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 1]) + bg.y);
+              v[j4 * 4 + 2] = (__uint_as_float(r[j4 * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 2]) + bg.z);
+              v[j4 * 4 + 3] = (__uint_as_float(r[j4 * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 3]) + bg.w);
+            }
+          } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias) {
+              if (n_glob + EPI_CHUNK <= p.N) {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 bb4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_glob) + j4);
+                  v[j4 * 4 + 0] += bb4.x; v[j4 * 4 + 1] += bb4.y; v[j4 * 4 + 2] += bb4.z; v[j4 * 4 + 3] += bb4.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n_glob + j < p.N) v[j] += __ldg(p.bias + n_glob + j);
+              }
+            }
+            if (rowadd_row) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n_glob + j < p.N) v[j] += __ldg(rowadd_row + n_glob + j);
+            }
+          }
+          if (c == last_c) {                    // this group has read all its accumulator columns
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) release_tmem(as);
+          }
+          // SWIZZLE_64B tile: row r at r*64 bytes, 16-byte chunk index XOR ((r >> 1) & 3)
+          uint8_t* srow = cbuf + row * 64;
+          const int sw = (row >> 1) & 3;
+          if (use_res) {
+            mbar_wait(&res_full[buf], (cidx / EPI_NBUF) & 1);
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+              const uint4 rr = *reinterpret_cast<const uint4*>(srow + ((ch ^ sw) << 4));
+              const float2 a0 = unpack_h2(rr.x), a1 = unpack_h2(rr.y), a2 = unpack_h2(rr.z), a3 = unpack_h2(rr.w);
+              v[ch * 8 + 0] += a0.x; v[ch * 8 + 1] += a0.y; v[ch * 8 + 2] += a1.x; v[ch * 8 + 3] += a1.y;
+              v[ch * 8 + 4] += a2.x; v[ch * 8 + 5] += a2.y; v[ch * 8 + 6] += a3.x; v[ch * 8 + 7] += a3.y;
+            }
+          }
+          if (p.flags & LDX_EPI_SILU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+          }
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 o;
+            o.x = pack_h2(v[ch * 8 + 0], v[ch * 8 + 1]);
+            o.y = pack_h2(v[ch * 8 + 2], v[ch * 8 + 3]);
+            o.z = pack_h2(v[ch * 8 + 4], v[ch * 8 + 5]);
+            o.w = pack_h2(v[ch * 8 + 6], v[ch * 8 + 7]);
+            *reinterpret_cast<uint4*>(srow + ((ch ^ sw) << 4)) = o;
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + grp, EPI_THREADS);
+          if (elected && !(p.flags & (1 << 16))) {   // (bit 16: debug, skip the store)
+            tma_store_4d(&p.omap, cbuf, n_glob, x0, y0, b0);
+            tma_store_commit();
+          }
+        }
+        continue;
+      }
+
+      // ---- direct path (fp32 outputs / unaligned outputs)
       const int64_t opix = p.o_off + (int64_t)b * p.o_sb + (int64_t)y * p.o_sy + (int64_t)x * p.o_sx;
       char* out_row = reinterpret_cast<char*>(p.out) + opix * osz;
       const __half* res_row =
           (p.res && valid) ? reinterpret_cast<const __half*>(p.res) + (((int64_t)b * p.H + y) * p.W + x) * p.ldr
                            : nullptr;
-      const float* rowadd_row = (p.rowadd && valid) ? p.rowadd + (int64_t)b * p.ld_rowadd : nullptr;
-      const int n_out0 = nt * n_out_tile;
-
-      mbar_wait(&bars->tmem_full[as], aphase);
-      tc_fence_after();
-      const uint32_t trow = tmem_base + as * p.acc_stride + ((uint32_t)(q * 32) << 16);
-      for (int c = 0; c < n_out_tile; c += 32) {
+      for (int c = grp * 32; c < n_out_tile; c += 32 * EPI_GROUPS) {
         if (geglu) {
           if (f32) epilogue_chunk<true, true>(p, trow, c, n_out0 + c, valid, out_row, res_row, rowadd_row);
           else epilogue_chunk<true, false>(p, trow, c, n_out0 + c, valid, out_row, res_row, rowadd_row);
@@ -245,13 +447,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->tmem_empty[as]);
+      if (lane == 0) release_tmem(as);
     }
+    if (p.tma_epi && elected) tma_store_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  if constexpr (kCtas == 2) {
+    cluster_sync_all();       // the peer's smem / TMEM stay alive until the leader's last MMA has retired
+    if (warp == 1) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  }
 }
 
 // ================================================================================ host side
@@ -272,8 +480,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // fp16 tensor map: up to 4 dims, dim0 contiguous, SWIZZLE_128B, zero OOB fill.
-int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+int encode_map_f16_sw(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -298,7 +506,7 @@ int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* 
       return LDX_E_INVALID;
     }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gdim, gstr, bx, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u]", (int)r, rank,
@@ -308,6 +516,11 @@ int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* 
     return LDX_E_CUDA;
   }
   return LDX_OK;
+}
+
+int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  return encode_map_f16_sw(map, ptr, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 static int pow2_floor(int v) {
@@ -321,23 +534,33 @@ static int pow2_ceil(int v) {
   return p;
 }
 
-static int choose_bn(int N, int m_tiles, int flags, int sms) {
+// Tile configuration: N tile width and 1-CTA vs CTA-pair kernel.  Cost model per 16-wide K step and per
+// SM: tensor pipe bn/2 cycles vs operand fetch (L2 -> smem) of (128 + bn/ctas) rows x 32 bytes at an
+// effective ~61 B/clk/SM (calibrated on B200: the 1-CTA 128x256 tile runs at ~0.64 of the MMA rate).
+static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas, int* bn_out, int* ctas_out) {
   const bool geglu = (flags & LDX_EPI_GEGLU) != 0;
-  int best = 0;
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 32; bn -= 32) {
-    if (geglu && bn % 64) continue;
-    const int n_tiles = (N + bn - 1) / bn;
-    const double waves = (double)(((long long)m_tiles * n_tiles + sms - 1) / sms);
-    // cycles per 16-wide K step: tensor pipe bn/2, smem operand reads (128 + bn) * 32 B at 128 B/clk
-    const double per_k = (bn / 2.0 > (128 + bn) / 4.0) ? bn / 2.0 : (128 + bn) / 4.0;
-    const double cost = waves * (per_k + 6.0);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = bn;
+  *bn_out = 128;
+  *ctas_out = 1;
+  for (int ctas = 1; ctas <= 2; ++ctas) {
+    if (force_ctas && ctas != force_ctas) continue;
+    for (int bn = 256; bn >= 32; bn -= 32) {
+      if (geglu && bn % 64) continue;
+      if (ctas == 2 && bn < 64) continue;
+      const long long n_tiles = (N + bn - 1) / bn;
+      const long long tiles = ((m_tiles + ctas - 1) / ctas) * n_tiles;
+      const long long workers = sms / ctas;
+      const double waves = (double)((tiles + workers - 1) / workers);
+      const double mma = bn / 2.0, fetch = (128 + bn / (double)ctas) * 0.52;
+      const double per_k = mma > fetch ? mma : fetch;
+      const double cost = waves * (per_k + 6.0);
+      if (cost < best_cost - 1e-9) {
+        best_cost = cost;
+        *bn_out = bn;
+        *ctas_out = ctas;
+      }
     }
   }
-  return best;
 }
 
 int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
@@ -369,7 +592,20 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
 
   const int sms = num_sms();
-  int bn = d->bn ? d->bn : choose_bn(d->N, m_tiles, d->flags, sms);
+  static int force_ctas = -1;
+  if (force_ctas < 0) {
+    const char* e = getenv("LDX_GEMM_CTAS");
+    force_ctas = e ? atoi(e) : 0;
+  }
+  int bn = d->bn, ctas = 1;
+  if (bn == 0) {
+    choose_config(d->N, m_tiles, d->flags, sms, force_ctas, &bn, &ctas);
+  } else {
+    int bn_unused;
+    choose_config(d->N, m_tiles, d->flags, sms, force_ctas, &bn_unused, &ctas);
+    if (ctas == 2 && bn < 64) ctas = 1;
+  }
+  g->ctas = ctas;
   LDX_CHECK_ARG(bn >= 32 && bn <= 256 && bn % 32 == 0, "bn %d must be a multiple of 32 in [32,256]", bn);
   if (d->flags & LDX_EPI_GEGLU) {
     LDX_CHECK_ARG(bn % 64 == 0 && d->N % bn == 0, "GEGLU needs bn %% 64 == 0 and N %% bn == 0 (N=%d bn=%d)", d->N, bn);
@@ -377,7 +613,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   }
   p.bn = bn;
   p.n_tiles = (d->N + bn - 1) / bn;
-  p.num_tiles = m_tiles * p.n_tiles;
+  p.num_tiles = ((m_tiles + ctas - 1) / ctas) * p.n_tiles;   // (pair-)tiles
   p.acc_stride = (uint32_t)pow2_ceil(bn < 32 ? 32 : bn);
   p.tmem_cols = 2 * p.acc_stride;
 
@@ -393,14 +629,22 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.nk = nk;
   LDX_CHECK_ARG(d->ldw >= (int64_t)nk * BK, "weight pitch %lld < K %d", (long long)d->ldw, nk * BK);
 
-  const uint32_t b_stage = (uint32_t)bn * BK * 2;
-  int stages = (int)((200 * 1024) / (A_STAGE_BYTES + b_stage));
+  const uint32_t b_stage = (uint32_t)(bn / ctas) * BK * 2;
+  int stages = (int)((224 * 1024 - EPI_SMEM - 2048) / (A_STAGE_BYTES + b_stage));
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  {
+    static int st_env = -1;
+    if (st_env < 0) { const char* e = getenv("LDX_GEMM_STAGES"); st_env = e ? atoi(e) : 0; }
+    if (st_env > 0 && st_env < stages) stages = st_env;
+  }
   if (stages > nk + 1) stages = nk + 1 > 2 ? nk + 1 : 2;
   p.stages = stages;
-  g->smem_bytes = stages * (A_STAGE_BYTES + (int)b_stage) + (int)sizeof(GemmBarriers) + 1024;
+  g->smem_bytes = stages * (A_STAGE_BYTES + (int)b_stage) + EPI_SMEM + (int)sizeof(GemmBarriers) + 1024;
   if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;   // keep one CTA per SM: it owns up to all of TMEM
-  g->grid = p.num_tiles < sms ? p.num_tiles : sms;
+  {
+    const int workers = sms / ctas;
+    g->grid = ctas * (p.num_tiles < workers ? p.num_tiles : workers);
+  }
 
   for (int i = 0; i < d->nsrc; ++i) {
     const ldx_src_t& s = d->src[i];
@@ -415,7 +659,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   {
     const uint64_t dims[2] = {(uint64_t)nk * BK, (uint64_t)d->N};
     const uint64_t str[1] = {(uint64_t)d->ldw * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)bn};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(bn / ctas)};
     int rc = encode_map_f16(&p.bmap, d->w, 2, dims, str, box);
     if (rc) return rc;
   }
@@ -428,22 +672,73 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.res = d->residual;
   p.ldr = d->ldr;
   p.flags = d->flags;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("LDX_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (dbg == 1) p.flags |= (1 << 16);
+    if (dbg == 2) p.flags |= (1 << 17);
+  }
   const int osz = (d->flags & LDX_EPI_OUT_F32) ? 4 : 2;
   const int n_out = (d->flags & LDX_EPI_GEGLU) ? d->N / 2 : d->N;
   bool vec = (n_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->out) + (uint64_t)d->o_off * osz) % 16 == 0) &&
              ((d->o_sx * osz) % 16 == 0) && ((d->o_sy * osz) % 16 == 0) && ((d->o_sb * osz) % 16 == 0);
   if (d->residual) vec = vec && (reinterpret_cast<uintptr_t>(d->residual) % 16 == 0) && ((d->ldr * 2) % 16 == 0);
   p.vec_ok = vec ? 1 : 0;
+
+  // TMA-store epilogue (fp16 outputs whose strides satisfy the TMA rules); otherwise direct stores
+  auto fix = [](int64_t s, int64_t fallback) { return (uint64_t)(s > 0 ? s : fallback) * 2; };
+  bool tma_ok = osz == 2 && ((reinterpret_cast<uintptr_t>(d->out) + (uint64_t)d->o_off * 2) % 16 == 0) &&
+                (d->o_sx * 2) % 16 == 0 && (d->o_sy * 2) % 16 == 0 && (d->o_sb * 2) % 16 == 0 && d->o_sx > 0;
+  if (d->residual) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(d->residual) % 16 == 0) && ((d->ldr * 2) % 16 == 0);
+  p.tma_epi = 0;
+  p.omap = p.bmap;
+  p.rmap = p.bmap;
+  if (tma_ok) {
+    const uint32_t box[4] = {(uint32_t)EPI_CHUNK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    const uint64_t odims[4] = {(uint64_t)n_out, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    const uint64_t sx = (uint64_t)d->o_sx * 2;
+    const uint64_t sy = fix(d->o_sy, d->o_sx * d->W);
+    const uint64_t sb = fix(d->o_sb, (d->o_sy > 0 ? d->o_sy : d->o_sx * d->W) * d->H);
+    const uint64_t ostr[3] = {sx, sy, sb};
+    int rc = encode_map_f16_sw(&p.omap, reinterpret_cast<const char*>(d->out) + d->o_off * 2, 4, odims, ostr, box,
+                               CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+    if (d->residual) {
+      const uint64_t rdims[4] = {(uint64_t)d->N, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+      const uint64_t rstr[3] = {(uint64_t)d->ldr * 2, (uint64_t)d->ldr * 2 * d->W, (uint64_t)d->ldr * 2 * d->W * d->H};
+      rc = encode_map_f16_sw(&p.rmap, d->residual, 4, rdims, rstr, box, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
+    p.tma_epi = 1;
+    if (p.bias && (reinterpret_cast<uintptr_t>(p.bias) % 16 != 0)) p.tma_epi = 0;   // float4 bias loads
+  }
   return LDX_OK;
 }
 
 int gemm_launch(const GemmLaunch* g, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    LDX_CUDA(cudaFuncSetAttribute(ldx_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDX_CUDA(cudaFuncSetAttribute(ldx_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDX_CUDA(cudaFuncSetAttribute(ldx_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  ldx_gemm_kernel<<<g->grid, GEMM_THREADS, g->smem_bytes, stream>>>(g->p);
+  if (g->ctas == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(g->grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = g->smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LDX_CUDA(cudaLaunchKernelEx(&cfg, ldx_gemm_kernel<2>, g->p));
+  } else {
+    ldx_gemm_kernel<1><<<g->grid, GEMM_THREADS, g->smem_bytes, stream>>>(g->p);
+  }
   LDX_CUDA(cudaGetLastError());
   return LDX_OK;
 }

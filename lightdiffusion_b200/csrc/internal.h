@@ -38,6 +38,8 @@ struct KSeg {
 struct alignas(64) GemmKParams {
   CUtensorMap amap[LDX_MAX_SRC];
   CUtensorMap bmap;
+  CUtensorMap omap;   // output, box (32, bw, bh, bb), SWIZZLE_64B (TMA-store epilogue)
+  CUtensorMap rmap;   // residual, same box
   KSeg seg[LDX_MAX_SEG];
   int32_t nseg, nk;
   int32_t N, W, H, B;
@@ -53,13 +55,15 @@ struct alignas(64) GemmKParams {
   const void* res;
   int64_t ldr;
   int32_t flags;
-  int32_t vec_ok;   // 16-byte vector epilogue allowed
+  int32_t vec_ok;   // 16-byte vector epilogue allowed (direct-store path)
+  int32_t tma_epi;  // 1: stage 32-column chunks in smem and TMA-store them (fp16 outputs)
 };
 
 struct GemmLaunch {
   GemmKParams p;
   int grid;
   int smem_bytes;
+  int ctas;      // 1, or 2 = CTA-pair kernel (cluster of 2, tcgen05 cta_group::2)
 };
 
 int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* out);

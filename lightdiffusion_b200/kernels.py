@@ -269,12 +269,16 @@ class Program:
                 self.add(o)
         else:
             L.check(L.lib().ldx_program_add_op(self._h, C.byref(op)), "ldx_program_add_op")
-            flops = 0.0
+            flops, tag = 0.0, None
             if op.kind == L.OP_ATTENTION:
                 b, nq, nk, heads, d = (op.i[j] for j in range(5))
-                flops = 4.0 * b * nq * nk * heads * d
+                flops, tag = 4.0 * b * nq * nk * heads * d, (b, nq, nk, heads, d)
+            elif op.kind == L.OP_GROUP_NORM:
+                tag = (op.i[2], op.i[3], op.i[0] + op.i[1])         # B, HW, C
+            elif op.kind == L.OP_LAYER_NORM:
+                tag = (op.i[0], op.i[1])                            # rows, C
             self.meta.append(({L.OP_ATTENTION: "attention", L.OP_GROUP_NORM: "group_norm",
-                               L.OP_LAYER_NORM: "layer_norm"}.get(op.kind, "other"), flops, None))
+                               L.OP_LAYER_NORM: "layer_norm"}.get(op.kind, "other"), flops, tag))
         self._keep.extend(keep)
 
     def keep(self, *tensors):
