@@ -673,6 +673,13 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.ldr = d->ldr;
   p.flags = d->flags;
   {
+    static int verbose = -1;
+    if (verbose < 0) { const char* e = getenv("LDX_GEMM_VERBOSE"); verbose = e ? atoi(e) : 0; }
+    if (verbose)
+      fprintf(stderr, "[ldx_gemm] M=%d(%dx%dx%d) N=%d K=%d -> ctas=%d bn=%d stages=%d tiles=%d grid=%d tma_epi=%d\n",
+              d->W * d->H * d->B, d->B, d->H, d->W, d->N, nk * BK, ctas, bn, stages, p.num_tiles, g->grid, p.tma_epi);
+  }
+  {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("LDX_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
     if (dbg == 1) p.flags |= (1 << 16);

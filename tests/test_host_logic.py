@@ -1,0 +1,97 @@
+"""Host-side logic that needs no GPU: architecture schema, schedules, sampler coefficients, sharding and
+the N>1 gather over gloo (world_size 2)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from lightdiffusion_b200 import sd15
+from lightdiffusion_b200.pipeline import calculate_sigmas, shard_range, sigmas_for_denoise
+from lightdiffusion_b200.samplers import dpmpp2m_coefficients, get_ancestral_step
+
+
+def test_schema_counts():
+    assert sd15.count_params(sd15.unet_param_shapes()) == 859520964
+    lay = sd15.unet_layout(sd15.SD15_UNET)
+    assert len(lay.input_blocks) == 12 and len(lay.output_blocks) == 12 and len(lay.middle) == 3
+    n_res = sum(isinstance(s, sd15.ResSpec) for b in lay.input_blocks + [lay.middle] + lay.output_blocks for s in b)
+    n_att = sum(isinstance(s, sd15.AttnSpec) for b in lay.input_blocks + [lay.middle] + lay.output_blocks for s in b)
+    assert (n_res, n_att) == (22, 16)                      # SURVEY.md App. A module census
+    dec = sd15.vae_decoder_param_shapes()
+    assert sum(torch.Size(s).numel() for k, s in dec.items() if k.startswith("decoder.")) == 49490179
+
+
+def test_seeded_weights_are_reproducible():
+    shapes = sd15.unet_param_shapes(sd15.tiny_unet_config())
+    a, b = sd15.seeded_state_dict(shapes, 5), sd15.seeded_state_dict(shapes, 5)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    c = sd15.seeded_state_dict(shapes, 6)
+    assert not torch.equal(a["time_embed.0.weight"], c["time_embed.0.weight"])
+
+
+def test_schedules_match_reference_golden(golden):
+    g = golden("schedules.pt")
+    assert torch.equal(calculate_sigmas("karras", 20), g["karras20"])
+    assert torch.equal(calculate_sigmas("karras", 8), g["karras8"])
+    assert torch.equal(calculate_sigmas("normal", 10), g["normal10"])
+    assert torch.equal(calculate_sigmas("normal", 22), g["normal22"])
+    assert torch.equal(sigmas_for_denoise("normal", 4, 0.45), golden("samplers_tiny.pt")["sigmas2"])
+
+
+def test_dpmpp2m_coefficients_reproduce_reference_trajectory(golden):
+    """x <- c_x x + c_d D + c_o (D - D_old) with our host coefficients == the real reference's
+    sample_dpmpp_2m_sde(eta=0) trajectory (golden) on the closed-form denoiser."""
+    g = golden("samplers_toy.pt")
+    sig, x = g["sigmas"], g["x0"].clone()
+    old, h_last = None, None
+    for i in range(len(sig) - 1):
+        d = x / (1.0 + sig[i] ** 2)
+        if sig[i + 1] == 0:
+            x, h = d, None
+        else:
+            c_x, c_d, c_o, h = dpmpp2m_coefficients(sig, i, h_last if old is not None else None)
+            x = c_x * x + c_d * d + (0 if c_o is None else c_o * (d - old))
+        old, h_last = d, h
+    assert float((x - g["dpmpp2m"]).norm() / g["dpmpp2m"].norm()) < 2e-6
+    sd, su = get_ancestral_step(sig[3], sig[4])
+    assert abs(float(sd ** 2 + su ** 2) - float(sig[4] ** 2)) < 1e-5
+
+
+def test_shard_range_partitions_everything():
+    for n, w in [(64, 8), (64, 2), (10, 4), (3, 8), (1, 1)]:
+        got = []
+        for r in range(w):
+            lo, hi = shard_range(n, r, w)
+            got += list(range(lo, hi))
+        assert got == list(range(n))
+
+
+def _gather_worker(rank, world, port, n_total, q):
+    import torch.distributed as dist
+    from lightdiffusion_b200.pipeline import gather_images, shard_range
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = shard_range(n_total, rank, world)
+    local = torch.stack([torch.full((4, 4, 3), float(i)) for i in range(lo, hi)]) if hi > lo else torch.zeros(0, 4, 4, 3)
+    out = gather_images(local, n_total)
+    if rank == 0:
+        q.put(out[:, 0, 0, 0].tolist())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [6, 5])
+def test_gather_images_world2_gloo(n_total):
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [float(i) for i in range(n_total)]
