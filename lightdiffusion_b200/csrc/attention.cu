@@ -24,20 +24,26 @@ int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* 
 static constexpr int ATT_THREADS = 192;
 static constexpr int BQ = 128;
 static constexpr int BKV = 64;
+#ifndef LDX_ATT_KST
+#define LDX_ATT_KST 1
+#endif
+#ifndef LDX_ATT_VST
+#define LDX_ATT_VST 1
+#endif
 
 template <int D>
 struct AttnCfg {
   static constexpr int DK = (D + 15) / 16;          // 16-wide K steps of Q K^T
   static constexpr int DCH = (D + 63) / 64;         // 64-column smem chunks per row
   static constexpr int DN = DK * 16;                // UMMA N of P V
-  static constexpr int KST = 2;
-  static constexpr int VST = DCH == 1 ? 2 : 1;
+  static constexpr int KST = DCH == 1 ? LDX_ATT_KST : 2;
+  static constexpr int VST = DCH == 1 ? LDX_ATT_VST : 1;
   static constexpr int Q_BYTES = DCH * BQ * 128;
   static constexpr int KV_BYTES = DCH * BKV * 128;
   static constexpr int P_BYTES = BQ * BKV * 2;
   static constexpr int TMEM_COLS = (64 + DN) <= 128 ? 128 : 256;
   static constexpr int SMEM = Q_BYTES + (KST + VST) * KV_BYTES + P_BYTES + 256 + 1024;
-  static constexpr int MIN_BLOCKS = SMEM <= 72 * 1024 ? 3 : (SMEM <= 110 * 1024 ? 2 : 1);
+  static constexpr int MIN_BLOCKS = SMEM <= 55 * 1024 ? 4 : (SMEM <= 72 * 1024 ? 3 : (SMEM <= 110 * 1024 ? 2 : 1));
 };
 
 struct AttnBarriers {
@@ -97,6 +103,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
   const uint32_t tmem_base = bars->tmem_base;
   const uint32_t tS = tmem_base;          // 64 fp32 columns
   const uint32_t tO = tmem_base + 64;     // DN fp32 columns
+  pdl_prologue();
 
   if (warp == 0) {
     // ---- TMA producer: warp-uniform loop, one elected lane issues
@@ -346,8 +353,7 @@ static int attention_launch_t(const AttnLaunch* L, cudaStream_t st) {
                                   AttnCfg<D>::SMEM));
     attr = true;
   }
-  ldx_attention_kernel<D><<<L->grid, ATT_THREADS, AttnCfg<D>::SMEM, st>>>(L->p);
-  LDX_CUDA(cudaGetLastError());
+  LDX_CUDA(launch_k(ldx_attention_kernel<D>, L->grid, dim3(ATT_THREADS), (size_t)AttnCfg<D>::SMEM, st, 1, L->p));
   return LDX_OK;
 }
 

@@ -31,6 +31,13 @@ LDX_DEVICE bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: let the next kernel in the stream start its prologue now, then wait
+// until every kernel this one depends on has completed and flushed (no-op for a normal launch).
+LDX_DEVICE void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------- mbarrier
 LDX_DEVICE void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -31,6 +31,7 @@ __device__ __forceinline__ uint4 gn_load(const GnArgs& a, int b, int pix, int ve
 
 __global__ void gn_stats_kernel(const GnArgs a) {
   extern __shared__ float sm[];          // [P][C][2]
+  pdl_prologue();
   const int b = blockIdx.x, slab = blockIdx.y;
   const int vec = threadIdx.x % a.nvec, pl = threadIdx.x / a.nvec;
   float s[8], ss[8];
@@ -77,6 +78,7 @@ __global__ void gn_stats_kernel(const GnArgs a) {
 
 __global__ void gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_slab_apply) {
   __shared__ float s_mean[32], s_rstd[32];
+  pdl_prologue();
   const int b = blockIdx.x, slab = blockIdx.y;
   {
     // 8 threads per group sum the slab partials in a fixed order (bit-reproducible), in double
@@ -145,6 +147,7 @@ static constexpr int GN_SMALL_VPT = 8;
 __global__ void __launch_bounds__(256) gn_small_kernel(const GnArgs a) {
   __shared__ float red[2][8];
   __shared__ float s_stat[2];
+  pdl_prologue();
   const int b = blockIdx.x >> 5, g = blockIdx.x & 31;
   const int vpg = a.cpg >> 3;                 // 16-byte vectors per group per pixel
   const int nv = a.HW * vpg;
@@ -226,8 +229,7 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
     a.P = 1; a.pix_per_slab = HW; a.nslab = 1;
     a.eps = eps; a.silu = silu; a.gamma = gamma; a.beta = beta;
     a.y = (__half*)y; a.ldy = ldy; a.partial = stats;
-    gn_small_kernel<<<B * 32, 256, 0, stream>>>(a);
-    LDX_CUDA(cudaGetLastError());
+    LDX_CUDA(launch_k(gn_small_kernel, dim3(B * 32), dim3(256), 0, stream, 1, a));
     return LDX_OK;
   }
   a.P = a.nvec >= 256 ? 1 : 256 / a.nvec;
@@ -255,8 +257,7 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
     attr = true;
   }
   LDX_CHECK_ARG(smem <= 128 * 1024, "group_norm: smem");
-  gn_stats_kernel<<<dim3(B, nslab), threads, smem, stream>>>(a);
-  LDX_CUDA(cudaGetLastError());
+  LDX_CUDA(launch_k(gn_stats_kernel, dim3(B, nslab), dim3(threads), smem, stream, 1, a));
   // apply: more slabs for bandwidth
   int nslab2 = (8 * sms + B - 1) / B;
   if (nslab2 > max_slabs) nslab2 = max_slabs;
@@ -264,8 +265,7 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
   int pps2 = (HW + nslab2 - 1) / nslab2;
   pps2 = (pps2 + a.P - 1) / a.P * a.P;
   nslab2 = (HW + pps2 - 1) / pps2;
-  gn_apply_kernel<<<dim3(B, nslab2), threads, 0, stream>>>(a, nslab2, pps2);
-  LDX_CUDA(cudaGetLastError());
+  LDX_CUDA(launch_k(gn_apply_kernel, dim3(B, nslab2), dim3(threads), 0, stream, 1, a, nslab2, pps2));
   return LDX_OK;
 }
 
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const __half* __restric
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   const int nvec = C >> 3;
+  pdl_prologue();
   constexpr bool kParamsInRegs = VPL <= 2;   // wider rows re-read the (L1-resident) parameters as float4
   constexpr int PV = kParamsInRegs ? VPL : 1;
   float g[PV][8], bt[PV][8];
@@ -364,10 +365,9 @@ static int layer_norm_impl(const void* x, int64_t ldx_, int rows, int C, float e
   const int vpl = (C / 8 + 31) / 32;
   const __half* xx = (const __half*)x;
   __half* yy = (__half*)y;
-  if (vpl <= 2) layer_norm_kernel<2><<<blocks, threads, 0, stream>>>(xx, ldx_, rows, C, eps, gamma, beta, yy, ldy);
-  else if (vpl <= 5) layer_norm_kernel<5><<<blocks, threads, 0, stream>>>(xx, ldx_, rows, C, eps, gamma, beta, yy, ldy);
-  else layer_norm_kernel<8><<<blocks, threads, 0, stream>>>(xx, ldx_, rows, C, eps, gamma, beta, yy, ldy);
-  LDX_CUDA(cudaGetLastError());
+  if (vpl <= 2) LDX_CUDA(launch_k(layer_norm_kernel<2>, dim3(blocks), dim3(threads), 0, stream, 1, xx, ldx_, rows, C, eps, gamma, beta, yy, ldy));
+  else if (vpl <= 5) LDX_CUDA(launch_k(layer_norm_kernel<5>, dim3(blocks), dim3(threads), 0, stream, 1, xx, ldx_, rows, C, eps, gamma, beta, yy, ldy));
+  else LDX_CUDA(launch_k(layer_norm_kernel<8>, dim3(blocks), dim3(threads), 0, stream, 1, xx, ldx_, rows, C, eps, gamma, beta, yy, ldy));
   return LDX_OK;
 }
 

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
   if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  pdl_prologue();   // everything above overlaps the tail of the previous kernel
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
@@ -730,21 +731,9 @@ int gemm_launch(const GemmLaunch* g, cudaStream_t stream) {
     attr_set = true;
   }
   if (g->ctas == 2) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(g->grid);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = g->smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    LDX_CUDA(cudaLaunchKernelEx(&cfg, ldx_gemm_kernel<2>, g->p));
+    LDX_CUDA(launch_k(ldx_gemm_kernel<2>, dim3(g->grid), dim3(GEMM_THREADS), (size_t)g->smem_bytes, stream, 2, g->p));
   } else {
-    ldx_gemm_kernel<1><<<g->grid, GEMM_THREADS, g->smem_bytes, stream>>>(g->p);
+    LDX_CUDA(launch_k(ldx_gemm_kernel<1>, dim3(g->grid), dim3(GEMM_THREADS), (size_t)g->smem_bytes, stream, 1, g->p));
   }
   LDX_CUDA(cudaGetLastError());
   return LDX_OK;

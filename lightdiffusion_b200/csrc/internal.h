@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/ldx.h"
 
@@ -28,6 +29,44 @@ int cuda_fail(cudaError_t e, const char* what);
   } while (0)
 
 inline cudaStream_t as_stream(ldx_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LDX_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v != 0;
+}
+
+// Launch with programmatic stream serialization (the kernel must call pdl_prologue() before it touches
+// global memory written by its predecessors) and an optional thread-block cluster.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            int cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = (unsigned)n;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
 int num_sms();
 
 // ---- implicit GEMM: frozen kernel parameters (TMA descriptors encoded once)
