@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libldx.so")
+LIB_PATH = os.environ.get("LDX_LIB_PATH") or os.path.join(_HERE, "libldx.so")   # override: kernel-variant experiments
 
 LDX_MAX_SRC = 4
 LDX_MAX_SEG = 16

@@ -2,17 +2,26 @@
 //   o[b, i, h*d:(h+1)*d] = softmax_j( q_i . k_j / sqrt(d) ) v_j      (no mask, dropout 0)
 // with head dims 40 / 80 / 160 (SD1.5: 8 heads at 320 / 640 / 1280 channels) plus 64 / 128.
 //
-// One CTA = 128 query rows of one (batch, head); keys/values are streamed in tiles of 64.
-//   warp 0   : TMA producer (Q once, K double buffered, V)
-//   warp 1   : tcgen05.mma issuer (one thread): S = Q K^T (fp32 in TMEM), O += P V (fp32 in TMEM)
-//   warps 2-5: online softmax, one thread per query row: S from TMEM -> exp2 -> P (fp16) into smem in
-//              the K-major SWIZZLE_128B layout tcgen05.mma reads; lazy rescale of O in TMEM
+// One CTA = NG groups of 128 query rows of one (batch, head); keys/values are streamed ONCE per CTA in
+// tiles of 64 and shared by all groups (for 128-row CTAs the K/V re-reads from L2 were the bound at
+// d = 40; NG = 4 cuts them 4x).
+//   warp 0        : TMA producer (Q per group, K/V rings)
+//   warp 1        : V patcher (row sums on the tensor core, see AttnCfg::ONES)
+//   warps 2..NG+1 : tcgen05.mma issuers, one per group (S_g = Q_g K^T into TMEM, O_g += P_g V); the groups
+//                   run independently apart from the shared K/V ring, so one group's exponentials overlap
+//                   another's TMEM loads / P stores / barrier round trips
+//   warps NG+2..  : online softmax, 4 warps per group, one thread per query row, at HALF-tile (32 key)
+//                   granularity: S from TMEM -> exp2 -> P (fp16) into smem in the K-major SWIZZLE_128B
+//                   layout tcgen05.mma reads; lazy rescale of O in TMEM
 // Head slices are addressed by a 4-D TMA view (d, heads, N, B) of the [B, N, heads*d] tensor, so the
 // box's columns beyond d are out of bounds and arrive as zeros (K padding for d = 40).
 // V is consumed straight from its row-major tile through an MN-major smem descriptor.
-// Several CTAs share an SM (TMEM: 64 + ceil16(d) columns each), so one CTA's softmax overlaps
-// another's MMAs.  Roofline: 4*Nq*Nk*d*heads FLOPs per batch element against the tensor peak; for
-// d = 40 the exp throughput (MUFU) is the practical bound.
+// Roofline: 4*Nq*Nk*d*heads FLOPs per batch element against the tensor peak.  For d <= 80 the practical
+// bounds are per-score, not per-FLOP: every score crosses TMEM -> registers as fp32 (measured 52-64 B/clk
+// per SM for tcgen05.ld, scripts/ubench/tmem_bw.cu, i.e. ~14-16 scores/clk/SM) and costs one MUFU.EX2
+// (16/clk/SM).  At d = 40 that caps the kernel near 600 TFLOP/s.  Evaluating a share of the exponentials
+// on the FMA pipe (POLY_MOD) or moving the row sums to the tensor core (ONES) therefore buys nothing
+// and both are off by default.
 #include "common.cuh"
 #include "internal.h"
 
@@ -21,14 +30,20 @@ namespace ldx {
 int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
 
-static constexpr int ATT_THREADS = 192;
 static constexpr int BQ = 128;
 static constexpr int BKV = 64;
-#ifndef LDX_ATT_KST
-#define LDX_ATT_KST 1
+static constexpr int ATT_MAX_NG = 4;
+#ifndef LDX_ATT_DBG
+#define LDX_ATT_DBG 0           // timing experiments only: 1 = no exponentials
 #endif
-#ifndef LDX_ATT_VST
-#define LDX_ATT_VST 1
+#ifndef LDX_ATT_NG_SMALL
+#define LDX_ATT_NG_SMALL 4      // query groups per CTA for d <= 64
+#endif
+#ifndef LDX_ATT_ONES
+#define LDX_ATT_ONES 0           // measured: no gain once TMEM reads bound the kernel (see header)
+#endif
+#ifndef LDX_ATT_POLY_MOD
+#define LDX_ATT_POLY_MOD 0      // every POLY_MOD-th exponential runs on the FMA pipe (0 = all on MUFU); no gain, see header
 #endif
 
 template <int D>
@@ -36,18 +51,33 @@ struct AttnCfg {
   static constexpr int DK = (D + 15) / 16;          // 16-wide K steps of Q K^T
   static constexpr int DCH = (D + 63) / 64;         // 64-column smem chunks per row
   static constexpr int DN = DK * 16;                // UMMA N of P V
-  static constexpr int KST = DCH == 1 ? LDX_ATT_KST : 2;
-  static constexpr int VST = DCH == 1 ? LDX_ATT_VST : 1;
-  static constexpr int Q_BYTES = DCH * BQ * 128;
+  static constexpr int NG = DCH == 1 ? LDX_ATT_NG_SMALL : 1;   // 128-row query groups per CTA
+  static constexpr int THREADS = 32 * (2 + NG + 4 * NG);   // producer, V patcher, NG MMA issuers, 4 softmax warps / group
+  // Row sums on the tensor core: when P V has a spare accumulator column (DN > D) the V tile's column D is
+  // set to 1.0 after it lands, so O[:, D] accumulates sum_j P_ij and the softmax warps skip 64 FADDs a tile.
+  static constexpr bool ONES = (DN > D) && (LDX_ATT_ONES != 0);
+  static constexpr int KST = 2;
+  static constexpr int VST = DCH == 1 ? 2 : 1;
+  static constexpr int Q_BYTES = DCH * BQ * 128;    // per group
   static constexpr int KV_BYTES = DCH * BKV * 128;
-  static constexpr int P_BYTES = BQ * BKV * 2;
-  static constexpr int TMEM_COLS = (64 + DN) <= 128 ? 128 : 256;
-  static constexpr int SMEM = Q_BYTES + (KST + VST) * KV_BYTES + P_BYTES + 256 + 1024;
-  static constexpr int MIN_BLOCKS = SMEM <= 55 * 1024 ? 4 : (SMEM <= 72 * 1024 ? 3 : (SMEM <= 110 * 1024 ? 2 : 1));
+  static constexpr int PB = DCH == 1 ? 2 : 1;       // P tiles per group: with one, P(j) waits for P V(j-1) to drain
+  static constexpr int P_BYTES = BQ * BKV * 2;      // per group and buffer
+  static constexpr int TMEM_NEED = NG * (BKV + DN);
+  static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
+  static constexpr int SMEM = NG * (Q_BYTES + PB * P_BYTES) + (KST + VST) * KV_BYTES + 512 + 1024;
+  static constexpr int BY_TMEM = 512 / TMEM_COLS;
+  static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
+  static constexpr int BY_THREADS = 2048 / THREADS;
+  static constexpr int B0 = BY_TMEM < BY_SMEM ? BY_TMEM : BY_SMEM;
+  static constexpr int B1 = B0 < BY_THREADS ? B0 : BY_THREADS;
+  static constexpr int MIN_BLOCKS = B1 < 1 ? 1 : B1;
+  static_assert(TMEM_NEED <= 512, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "smem budget");
 };
 
 struct AttnBarriers {
-  uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_free, p_full, o_done;
+  uint64_t q_full[ATT_MAX_NG], s_full[ATT_MAX_NG], s_free[ATT_MAX_NG], p_full[ATT_MAX_NG][2], pv_done[ATT_MAX_NG][2];
+  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2], v_ready[2];
   uint32_t tmem_base;
 };
 
@@ -59,41 +89,61 @@ struct alignas(64) AttnParams {
   float scale_log2;   // log2(e) / sqrt(d)
 };
 
+// 2^x for x <= 0 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative
+// error 7.5e-5 -- below fp16 rounding of P), so a share of the exponentials does not queue on MUFU.
+LDX_DEVICE float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = __fadd_rd(x, 12582912.0f);            // floor(x) in the low mantissa bits
+  const float fr = x - (t - 12582912.0f);               // [0, 1)
+  float p = fmaf(0.07802422344684601f, fr, 0.22606723010540009f);
+  p = fmaf(p, fr, 0.695833683013916f);
+  p = fmaf(p, fr, 0.9999251961708069f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 template <int D>
-__global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_attention_kernel(
+__global__ void __launch_bounds__(AttnCfg<D>::THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_attention_kernel(
     const __grid_constant__ AttnParams p) {
   using C = AttnCfg<D>;
+  constexpr int NG = C::NG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + C::Q_BYTES;
+  uint8_t* sQ = smem;                                 // NG x Q_BYTES
+  uint8_t* sK = sQ + NG * C::Q_BYTES;
   uint8_t* sV = sK + C::KST * C::KV_BYTES;
-  uint8_t* sP = sV + C::VST * C::KV_BYTES;
-  AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(sP + C::P_BYTES);
+  uint8_t* sP = sV + C::VST * C::KV_BYTES;            // NG x PB x P_BYTES
+  AttnBarriers* bars = reinterpret_cast<AttnBarriers*>(sP + NG * C::PB * C::P_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  const int q_cta = blockIdx.x * (NG * BQ), h = blockIdx.y, b = blockIdx.z;
   const int nkv = (p.Nk + BKV - 1) / BKV;
+  const int rows_left = p.Nq - q_cta;
+  const int ng_act = rows_left >= NG * BQ ? NG : (rows_left + BQ - 1) / BQ;   // groups with at least one query row
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.qmap);
     tma_prefetch_desc(&p.kmap);
     tma_prefetch_desc(&p.vmap);
-    mbar_init(&bars->q_full, 1);
+    for (int g = 0; g < ATT_MAX_NG; ++g) {
+      mbar_init(&bars->q_full[g], 1);
+      mbar_init(&bars->s_full[g], 1);
+      mbar_init(&bars->s_free[g], 4);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bars->p_full[g][i], 4);
+        mbar_init(&bars->pv_done[g][i], 1);
+      }
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars->k_full[i], 1);
-      mbar_init(&bars->k_empty[i], 1);
+      mbar_init(&bars->k_empty[i], ng_act);    // one tcgen05.commit per active group
       mbar_init(&bars->v_full[i], 1);
-      mbar_init(&bars->v_empty[i], 1);
+      mbar_init(&bars->v_empty[i], ng_act);
+      mbar_init(&bars->v_ready[i], 1);
     }
-    mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->s_free, 4);
-    mbar_init(&bars->p_full, 4);
-    mbar_init(&bars->o_done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == 2) {
     tmem_alloc(&bars->tmem_base, C::TMEM_COLS);
     tmem_relinquish();
   }
@@ -101,206 +151,268 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const uint32_t tS = tmem_base;          // 64 fp32 columns
-  const uint32_t tO = tmem_base + 64;     // DN fp32 columns
+  const uint32_t tS = tmem_base;                      // group g: 64 fp32 columns at g * 64
+  const uint32_t tO = tmem_base + NG * BKV;           // group g: DN fp32 columns at g * DN
   pdl_prologue();
 
   if (warp == 0) {
-    // ---- TMA producer: warp-uniform loop, one elected lane issues
+    // ---- TMA producer: warp-uniform loop, one elected lane issues.  K runs one tile ahead of V: the K
+    // buffer frees as soon as every group's S = Q K^T has been issued, the V buffer only after the softmax.
     if (elect_one()) {
-      mbar_arrive_expect_tx(&bars->q_full, C::Q_BYTES);
-      for (int c = 0; c < C::DCH; ++c) tma_load_4d(sQ + c * (BQ * 128), &p.qmap, &bars->q_full, c * 64, h, q0, b);
+      for (int g = 0; g < ng_act; ++g) {
+        mbar_arrive_expect_tx(&bars->q_full[g], C::Q_BYTES);
+        for (int c = 0; c < C::DCH; ++c)
+          tma_load_4d(sQ + g * C::Q_BYTES + c * (BQ * 128), &p.qmap, &bars->q_full[g], c * 64, h, q_cta + g * BQ, b);
+      }
     }
     __syncwarp();
-    for (int j = 0; j < nkv; ++j) {
-      const int ks = j % C::KST, vs = j % C::VST;
-      mbar_wait(&bars->k_empty[ks], ((j / C::KST) & 1) ^ 1);
+    auto load_k = [&](int t) {
+      const int ks = t % C::KST;
+      mbar_wait(&bars->k_empty[ks], ((t / C::KST) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->k_full[ks], C::KV_BYTES);
         for (int c = 0; c < C::DCH; ++c)
-          tma_load_4d(sK + ks * C::KV_BYTES + c * (BKV * 128), &p.kmap, &bars->k_full[ks], c * 64, h, j * BKV, b);
+          tma_load_4d(sK + ks * C::KV_BYTES + c * (BKV * 128), &p.kmap, &bars->k_full[ks], c * 64, h, t * BKV, b);
       }
       __syncwarp();
-      mbar_wait(&bars->v_empty[vs], ((j / C::VST) & 1) ^ 1);
+    };
+    for (int t = 0; t < C::KST - 1 && t < nkv; ++t) load_k(t);
+    for (int t = 0; t < nkv; ++t) {
+      if (t + C::KST - 1 < nkv) load_k(t + C::KST - 1);
+      const int vs = t % C::VST;
+      mbar_wait(&bars->v_empty[vs], ((t / C::VST) & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->v_full[vs], C::KV_BYTES);
         for (int c = 0; c < C::DCH; ++c)
-          tma_load_4d(sV + vs * C::KV_BYTES + c * (BKV * 128), &p.vmap, &bars->v_full[vs], c * 64, h, j * BKV, b);
+          tma_load_4d(sV + vs * C::KV_BYTES + c * (BKV * 128), &p.vmap, &bars->v_full[vs], c * 64, h, t * BKV, b);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: warp-uniform control flow, one elected lane issues tcgen05.mma / commit
-    const uint32_t idesc_s = umma_idesc_f16(BQ, BKV, 0, 0);
-    const uint32_t idesc_o = umma_idesc_f16(BQ, C::DN, 0, 1);       // B = V is MN-major
-    const uint32_t q_addr = smem_u32(sQ), p_addr = smem_u32(sP);
-    auto mma_s = [&](int j) {
-      const int ks = j % C::KST;
-      mbar_wait(&bars->k_full[ks], (j / C::KST) & 1);
-      tc_fence_after();
-      const uint32_t k_addr = smem_u32(sK + ks * C::KV_BYTES);
-      if (elect_one()) {
+    // ---- V patcher: column D of every landed V tile becomes 1.0 (see AttnCfg::ONES)
+    if constexpr (C::ONES) {
+      const __half one = __float2half(1.0f);
+      for (int t = 0; t < nkv; ++t) {
+        const int vs = t % C::VST;
+        mbar_wait(&bars->v_full[vs], (t / C::VST) & 1);
+        uint8_t* tile = sV + vs * C::KV_BYTES + (D / 64) * (BKV * 128);
 #pragma unroll
-        for (int s = 0; s < C::DK; ++s) {
-          const uint32_t qa = q_addr + (s / 4) * (BQ * 128) + (s % 4) * 32;
-          const uint32_t ka = k_addr + (s / 4) * (BKV * 128) + (s % 4) * 32;
-          umma_f16_ss(tS, umma_desc_kmajor_sw128(qa), umma_desc_kmajor_sw128(ka), idesc_s, (uint32_t)(s != 0));
+        for (int rr = 0; rr < BKV; rr += 32) {
+          const int r = rr + lane;
+          *reinterpret_cast<__half*>(tile + r * 128 + ((((D % 64) / 8) ^ (r & 7)) << 4) + (D % 8) * 2) = one;
         }
-        umma_commit(&bars->k_empty[ks]);
-        umma_commit(&bars->s_full);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars->v_ready[vs]);
       }
-      __syncwarp();
-    };
-    mbar_wait(&bars->q_full, 0);
-    mma_s(0);
-    for (int j = 0; j < nkv; ++j) {
-      if (j + 1 < nkv) {
-        mbar_wait(&bars->s_free, j & 1);
-        tc_fence_after();
-        mma_s(j + 1);
-      }
-      const int vs = j % C::VST;
-      mbar_wait(&bars->p_full, j & 1);
-      mbar_wait(&bars->v_full[vs], (j / C::VST) & 1);
-      tc_fence_after();
-      const uint32_t v_addr = smem_u32(sV + vs * C::KV_BYTES);
-      if (elect_one()) {
-#pragma unroll
-        for (int s = 0; s < BKV / 16; ++s) {
-          umma_f16_ss(tO, umma_desc_kmajor_sw128(p_addr + s * 32),
-                      umma_desc_mnmajor_sw128(v_addr + s * 2048, BKV * 128), idesc_o, (uint32_t)((j | s) != 0));
-        }
-        umma_commit(&bars->v_empty[vs]);
-        umma_commit(&bars->o_done);
-      }
-      __syncwarp();
     }
-  } else {
-    // ------------------------------------------------------------------ softmax warps
-    const int qd = warp & 3;
+  } else if (warp < 2 + NG) {
+    // ---- MMA issuers, one warp per query group (warp-uniform control flow, one elected lane issues
+    // tcgen05.mma / commit).  S_g(t+1) is issued as soon as the softmax has read S_g(t) out of TMEM, so it
+    // overlaps the exponentials of tile t; a K/V ring slot is released by the LAST group's commit (the
+    // slot's "empty" barrier counts one tcgen05.commit per active group).
+    const int g = warp - 2;
+    if (g < ng_act) {
+      const uint32_t idesc_s = umma_idesc_f16(BQ, BKV, 0, 0);
+      const uint32_t idesc_o = umma_idesc_f16(BQ, C::DN, 0, 1);       // B = V is MN-major
+      const uint32_t q_addr = smem_u32(sQ + g * C::Q_BYTES), p_addr = smem_u32(sP + g * C::PB * C::P_BYTES);
+      const uint32_t tSg = tS + g * BKV, tOg = tO + g * C::DN;
+      auto mma_s = [&](int t) {
+        const int ks = t % C::KST;
+        mbar_wait(&bars->k_full[ks], (t / C::KST) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sK + ks * C::KV_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < C::DK; ++s) {
+            const uint32_t qa = q_addr + (s / 4) * (BQ * 128) + (s % 4) * 32;
+            const uint32_t ka = k_addr + (s / 4) * (BKV * 128) + (s % 4) * 32;
+            umma_f16_ss(tSg, umma_desc_kmajor_sw128(qa), umma_desc_kmajor_sw128(ka), idesc_s, (uint32_t)(s != 0));
+          }
+          umma_commit(&bars->s_full[g]);
+          umma_commit(&bars->k_empty[ks]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(&bars->q_full[g], 0);
+      mma_s(0);
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) {
+          mbar_wait(&bars->s_free[g], j & 1);
+          tc_fence_after();
+          mma_s(j + 1);
+        }
+        const int vs = j % C::VST, pb = j % C::PB;
+        mbar_wait(&bars->p_full[g][pb], (j / C::PB) & 1);
+        mbar_wait(C::ONES ? &bars->v_ready[vs] : &bars->v_full[vs], (j / C::VST) & 1);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sV + vs * C::KV_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int s = 0; s < BKV / 16; ++s) {
+            umma_f16_ss(tOg, umma_desc_kmajor_sw128(p_addr + pb * C::P_BYTES + s * 32),
+                        umma_desc_mnmajor_sw128(v_addr + s * 2048, BKV * 128), idesc_o, (uint32_t)((j | s) != 0));
+          }
+          umma_commit(&bars->pv_done[g][pb]);
+          umma_commit(&bars->v_empty[vs]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if ((warp - 2 - NG) / 4 < ng_act) {
+    // ------------------------------------------------------------------ softmax warps (thread = query row)
+    // Online softmax at HALF-tile granularity (32 keys): one TMEM read per score, 32 live score registers,
+    // and the running-max test sits on a 32-element chain instead of a 64-element one.
+    const int g = (warp - 2 - NG) / 4;
+    const int qd = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
+    const uint32_t tSg = tS + g * BKV + lane_off, tOg = tO + g * C::DN + lane_off;
+    uint64_t* s_full = &bars->s_full[g];
+    uint64_t* s_free = &bars->s_free[g];
+    uint64_t* p_full = &bars->p_full[g][0];
+    uint64_t* pv_done = &bars->pv_done[g][0];
+    uint8_t* prow0 = sP + g * C::PB * C::P_BYTES + row * 128;
     const float c = p.scale_log2;
     float m_used = -INFINITY;   // row max the exponentials are relative to (raw score units)
     float l = 0.f;
-    uint8_t* prow = sP + row * 128;
     for (int j = 0; j < nkv; ++j) {
-      mbar_wait(&bars->s_full, j & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int kv_left = p.Nk - j * BKV;   // valid keys in this tile (>= 1)
-      const bool full_tile = kv_left >= BKV;   // only the last tile of a ragged Nk needs key masking
-      uint32_t r[32];
-      float m_tile = -INFINITY;
+      const int pb = j % C::PB;
+      uint8_t* prow = prow0 + pb * C::P_BYTES;
+      const int kv_left = p.Nk - j * BKV;      // valid keys in this tile (>= 1)
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        tmem_ld32(tS + lane_off + hf * 32, r);
-        tmem_ld_wait();
-        if (full_tile) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (hf * 32 + i < kv_left) m_tile = fmaxf(m_tile, __uint_as_float(r[i]));
-        }
-      }
-      if (j > 0) {
-        mbar_wait(&bars->o_done, (j - 1) & 1);   // P buffer and O are free again
-        tc_fence_after();
-      }
-      // lazy rescale: only when some row of this warp grew its max by more than 2^8 after scaling
-      const bool grow = (m_tile - m_used) * c > 8.0f;
-      if (j == 0) {
-        m_used = m_tile;
-      } else if (__any_sync(0xffffffffu, grow)) {
-        const float m_new = fmaxf(m_used, m_tile);
-        const float alpha = ex2_approx((m_used - m_new) * c);
-        m_used = m_new;
-        l *= alpha;
-#pragma unroll
-        for (int cc = 0; cc < C::DN / 16; ++cc) {
-          uint32_t o[16];
-          tmem_ld16(tO + lane_off + cc * 16, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          asm volatile(
-              "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
-              "%13, %14, %15};" ::"r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]),
-              "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]),
-              "r"(tO + lane_off + cc * 16)
-              : "memory");
-        }
-        tmem_st_wait();
-      }
-      const float mc = m_used * c;
-      float l0 = 0.f, l1 = 0.f;
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        tmem_ld32(tS + lane_off + hf * 32, r);
+        uint32_t r[32];
+        tmem_ld32(tSg + hf * 32, r);
         tmem_ld_wait();
         if (hf == 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars->s_free);   // S may be overwritten by the next Q K^T
+          if (lane == 0) mbar_arrive(s_free);   // S(j) has been read: the accumulator may be reused
         }
-        uint32_t pk[16];
-        if (full_tile) {
+        float s[32];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2_approx(__uint_as_float(r[2 * i]) * c - mc);
-            const float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) * c - mc);
-            l0 += p0;
-            l1 += p1;
-            pk[i] = pack_h2(p0, p1);
+        for (int i = 0; i < 32; ++i) s[i] = __uint_as_float(r[i]);
+        if (kv_left < BKV) {                     // only the last tile of a ragged Nk needs key masking
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (hf * 32 + i >= kv_left) s[i] = -INFINITY;
+        }
+        float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+#pragma unroll
+        for (int i = 4; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
+          mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+        }
+        const float m_h = fmaxf(mx0, mx1);
+        // lazy rescale: only when some row of this warp grew its max by more than 2^8 after scaling
+        const bool grow = (m_h - m_used) * c > 8.0f;
+        if (j == 0 && hf == 0) {
+          m_used = m_h;
+        } else if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = fmaxf(m_used, m_h);
+          const float alpha = ex2_approx((m_used - m_new) * c);
+          m_used = m_new;
+          if constexpr (!C::ONES) l *= alpha;
+          if (j > 0) {
+            mbar_wait(pv_done + (j - 1) % C::PB, ((j - 1) / C::PB) & 1);     // O is quiescent
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < C::DN / 16; ++cc) {
+              uint32_t o[16];
+              tmem_ld16(tOg + cc * 16, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              asm volatile(
+                  "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+                  "%12, %13, %14, %15};" ::"r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]),
+                  "r"(o[7]), "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]),
+                  "r"(o[15]), "r"(tOg + cc * 16)
+                  : "memory");
+            }
+            tmem_st_wait();
           }
-        } else {
+          if (hf == 1) {                          // the first half of this tile's P row is already in smem
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float p0 = ex2_approx(__uint_as_float(r[2 * i]) * c - mc);
-            float p1 = ex2_approx(__uint_as_float(r[2 * i + 1]) * c - mc);
-            if (hf * 32 + 2 * i >= kv_left) p0 = 0.f;
-            if (hf * 32 + 2 * i + 1 >= kv_left) p1 = 0.f;
-            l0 += p0;
-            l1 += p1;
-            pk[i] = pack_h2(p0, p1);
+            for (int ch = 0; ch < 4; ++ch) {
+              uint4* q4 = reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4));
+              uint4 u = *q4;
+              float2 a0 = unpack_h2(u.x), a1 = unpack_h2(u.y), a2 = unpack_h2(u.z), a3 = unpack_h2(u.w);
+              u.x = pack_h2(a0.x * alpha, a0.y * alpha);
+              u.y = pack_h2(a1.x * alpha, a1.y * alpha);
+              u.z = pack_h2(a2.x * alpha, a2.y * alpha);
+              u.w = pack_h2(a3.x * alpha, a3.y * alpha);
+              *q4 = u;
+            }
           }
         }
+        const float mc = m_used * c;
+        if (hf == 0 && j >= C::PB) mbar_wait(pv_done + pb, ((j - C::PB) / C::PB) & 1);   // P V(j - PB) has read this buffer
+        float l0 = 0.f, l1 = 0.f;
         // 32 keys = 4 16-byte chunks; chunk index XOR (row % 8) is the SWIZZLE_128B pattern
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = ch * 8 + 2 * i;
+            const float x0 = fmaf(s[e], c, -mc), x1 = fmaf(s[e + 1], c, -mc);
+            float p0, p1;
+            if (LDX_ATT_DBG == 1) {
+              p0 = x0;
+              p1 = x1;
+            } else {
+              if (LDX_ATT_POLY_MOD > 0 && e % LDX_ATT_POLY_MOD == LDX_ATT_POLY_MOD - 1) p0 = ex2_poly(x0);
+              else p0 = ex2_approx(x0);
+              if (LDX_ATT_POLY_MOD > 0 && (e + 1) % LDX_ATT_POLY_MOD == LDX_ATT_POLY_MOD - 1) p1 = ex2_poly(x1);
+              else p1 = ex2_approx(x1);
+            }
+            if constexpr (!C::ONES) {
+              l0 += p0;
+              l1 += p1;
+            }
+            pk[i] = pack_h2(p0, p1);
+          }
           const int chunk = (hf * 4 + ch) ^ (row & 7);
-          *reinterpret_cast<uint4*>(prow + chunk * 16) =
-              make_uint4(pk[ch * 4 + 0], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+          *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+        l += l0 + l1;
       }
-      l += l0 + l1;
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->p_full);
+      if (lane == 0) mbar_arrive(p_full + pb);
     }
     // ------------------------------------------------------------------ finalise: O / l -> global
-    mbar_wait(&bars->o_done, (nkv - 1) & 1);
+    mbar_wait(pv_done + (nkv - 1) % C::PB, ((nkv - 1) / C::PB) & 1);
     tc_fence_after();
+    if constexpr (C::ONES) {                    // the row sum is accumulator column D
+      uint32_t lv;
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(lv) : "r"(tOg + D) : "memory");
+      tmem_ld_wait();
+      l = __uint_as_float(lv);
+    }
     const float inv_l = 1.0f / l;
-    const int qrow = q0 + row;
+    const int qrow = q_cta + g * BQ + row;
     __half* orow = p.o + ((int64_t)b * p.Nq + qrow) * p.ldo + h * D;
 #pragma unroll
     for (int cc = 0; cc < C::DN / 16; ++cc) {
       uint32_t o[16];
-      tmem_ld16(tO + lane_off + cc * 16, o);
+      tmem_ld16(tOg + cc * 16, o);
       tmem_ld_wait();
       if (qrow < p.Nq) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const int col = cc * 16 + g * 8;
+        for (int g8 = 0; g8 < 2; ++g8) {
+          const int col = cc * 16 + g8 * 8;
           if (col < D) {
             uint4 u;
-            u.x = pack_h2(__uint_as_float(o[g * 8 + 0]) * inv_l, __uint_as_float(o[g * 8 + 1]) * inv_l);
-            u.y = pack_h2(__uint_as_float(o[g * 8 + 2]) * inv_l, __uint_as_float(o[g * 8 + 3]) * inv_l);
-            u.z = pack_h2(__uint_as_float(o[g * 8 + 4]) * inv_l, __uint_as_float(o[g * 8 + 5]) * inv_l);
-            u.w = pack_h2(__uint_as_float(o[g * 8 + 6]) * inv_l, __uint_as_float(o[g * 8 + 7]) * inv_l);
+            u.x = pack_h2(__uint_as_float(o[g8 * 8 + 0]) * inv_l, __uint_as_float(o[g8 * 8 + 1]) * inv_l);
+            u.y = pack_h2(__uint_as_float(o[g8 * 8 + 2]) * inv_l, __uint_as_float(o[g8 * 8 + 3]) * inv_l);
+            u.z = pack_h2(__uint_as_float(o[g8 * 8 + 4]) * inv_l, __uint_as_float(o[g8 * 8 + 5]) * inv_l);
+            u.w = pack_h2(__uint_as_float(o[g8 * 8 + 6]) * inv_l, __uint_as_float(o[g8 * 8 + 7]) * inv_l);
             *reinterpret_cast<uint4*>(orow + col) = u;
           }
         }
@@ -310,7 +422,7 @@ __global__ void __launch_bounds__(ATT_THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_atten
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if (warp == 2) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
 struct AttnLaunch {
@@ -318,6 +430,12 @@ struct AttnLaunch {
   dim3 grid;
   int d;
 };
+
+template <int D>
+static dim3 attention_grid(int B, int Nq, int heads) {
+  constexpr int rows = AttnCfg<D>::NG * BQ;
+  return dim3((Nq + rows - 1) / rows, heads, B);
+}
 
 static int attention_prepare(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                              void* o, int64_t ldo, int B, int Nq, int Nk, int heads, int d, AttnLaunch* L) {
@@ -340,7 +458,13 @@ static int attention_prepare(const void* q, int64_t ldq, const void* k, int64_t 
   L->p.ldo = ldo;
   L->p.B = B; L->p.Nq = Nq; L->p.Nk = Nk; L->p.heads = heads;
   L->p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
-  L->grid = dim3((Nq + BQ - 1) / BQ, heads, B);
+  switch (d) {
+    case 40: L->grid = attention_grid<40>(B, Nq, heads); break;
+    case 64: L->grid = attention_grid<64>(B, Nq, heads); break;
+    case 80: L->grid = attention_grid<80>(B, Nq, heads); break;
+    case 128: L->grid = attention_grid<128>(B, Nq, heads); break;
+    default: L->grid = attention_grid<160>(B, Nq, heads); break;
+  }
   L->d = d;
   return LDX_OK;
 }
@@ -353,7 +477,7 @@ static int attention_launch_t(const AttnLaunch* L, cudaStream_t st) {
                                   AttnCfg<D>::SMEM));
     attr = true;
   }
-  LDX_CUDA(launch_k(ldx_attention_kernel<D>, L->grid, dim3(ATT_THREADS), (size_t)AttnCfg<D>::SMEM, st, 1, L->p));
+  LDX_CUDA(launch_k(ldx_attention_kernel<D>, L->grid, dim3(AttnCfg<D>::THREADS), (size_t)AttnCfg<D>::SMEM, st, 1, L->p));
   return LDX_OK;
 }
 

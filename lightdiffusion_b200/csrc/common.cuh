@@ -56,22 +56,29 @@ LDX_DEVICE void mbar_arrive(uint64_t* bar) {
 #ifndef LDX_WAIT_LIMIT_CYCLES
 #define LDX_WAIT_LIMIT_CYCLES (1ll << 32)
 #endif
+#ifndef LDX_TRYWAIT_HINT_NS
+#define LDX_TRYWAIT_HINT_NS 20000u
+#endif
+LDX_DEVICE bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity), "r"(LDX_TRYWAIT_HINT_NS)   // suspend-time hint: fewer spin iterations stealing issue slots
+      : "memory");
+  return done != 0;
+}
 LDX_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
+  if (mbar_try_wait(addr, parity)) return;      // common case: the phase has already completed
   long long t0 = 0;
-  for (uint32_t it = 0;; ++it) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if ((it & 1023u) == 1023u) {
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait(addr, parity)) break;
+    if ((it & 1023u) == 0u) {
       const long long now = clock64();
       if (t0 == 0) t0 = now;
       else if (now - t0 > LDX_WAIT_LIMIT_CYCLES) __trap();

@@ -1,0 +1,18 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from lightdiffusion_b200 import kernels as K
+def timeit(fn, iters=10):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+shapes = [(16, 4096, 4096, 8, 40), (16, 4096, 4096, 8, 64), (16, 1024, 1024, 8, 80)]
+for (B, Nq, Nk, H, d) in shapes:
+    q = torch.randn(B, Nq, H * d, device="cuda").half(); k = torch.randn(B, Nk, H * d, device="cuda").half(); v = torch.randn(B, Nk, H * d, device="cuda").half()
+    o = torch.empty_like(q)
+    prog = K.Program(); prog.add(K.attention_op(q, k, v, o, H))
+    ms = timeit(prog.run)
+    print(f"attn B={B} Nq={Nq} Nk={Nk} d={d}: {ms*1e3:8.1f} us  {4.0*B*Nq*Nk*H*d/ms/1e9:7.1f} TF/s", flush=True)
