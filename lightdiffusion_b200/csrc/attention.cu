@@ -17,11 +17,11 @@
 // box's columns beyond d are out of bounds and arrive as zeros (K padding for d = 40).
 // V is consumed straight from its row-major tile through an MN-major smem descriptor.
 // Roofline: 4*Nq*Nk*d*heads FLOPs per batch element against the tensor peak.  For d <= 80 the practical
-// bounds are per-score, not per-FLOP: every score crosses TMEM -> registers as fp32 (measured 52-64 B/clk
-// per SM for tcgen05.ld, scripts/ubench/tmem_bw.cu, i.e. ~14-16 scores/clk/SM) and costs one MUFU.EX2
-// (16/clk/SM).  At d = 40 that caps the kernel near 600 TFLOP/s.  Evaluating a share of the exponentials
-// on the FMA pipe (POLY_MOD) or moving the row sums to the tensor core (ONES) therefore buys nothing
-// and both are off by default.
+// bound is per score, not per FLOP: each of the Nq*Nk scores costs one MUFU.EX2 (16/clk/SM, measured by
+// scripts/ubench/tmem_bw.cu) plus ~4-6 issue slots of fp32 work (scale/max/pack/convert), and the four
+// schedulers of an SM run at 60-70 % issue utilisation in the ncu capture (profiles/).  At d = 40 the MUFU
+// floor alone is ~480 us for the 16 x 8 x 4096^2 SD1.5 shape; the kernel runs at ~730 us.  Evaluating a
+// share of the exponentials on the FMA pipe (POLY_MOD) adds instructions and measured no gain.
 #include "common.cuh"
 #include "internal.h"
 
@@ -40,10 +40,13 @@ static constexpr int ATT_MAX_NG = 4;
 #define LDX_ATT_NG_SMALL 4      // query groups per CTA for d <= 64
 #endif
 #ifndef LDX_ATT_ONES
-#define LDX_ATT_ONES 0           // measured: no gain once TMEM reads bound the kernel (see header)
+#define LDX_ATT_ONES 1           // row sums on the tensor core where P V has a spare column (d = 40): ~4 %
+#endif
+#ifndef LDX_ATT_SLEEP_NS
+#define LDX_ATT_SLEEP_NS 64       // poll back-off of the producer / patcher / MMA-issuer warps
 #endif
 #ifndef LDX_ATT_POLY_MOD
-#define LDX_ATT_POLY_MOD 0      // every POLY_MOD-th exponential runs on the FMA pipe (0 = all on MUFU); no gain, see header
+#define LDX_ATT_POLY_MOD 0      // every POLY_MOD-th exponential runs on the FMA pipe (0 = all on MUFU); measured: no gain
 #endif
 
 template <int D>
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(AttnCfg<D>::THREADS, AttnCfg<D>::MIN_BLOCKS) l
     __syncwarp();
     auto load_k = [&](int t) {
       const int ks = t % C::KST;
-      mbar_wait(&bars->k_empty[ks], ((t / C::KST) & 1) ^ 1);
+      mbar_wait_relaxed(&bars->k_empty[ks], ((t / C::KST) & 1) ^ 1, LDX_ATT_SLEEP_NS);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->k_full[ks], C::KV_BYTES);
         for (int c = 0; c < C::DCH; ++c)
@@ -180,7 +183,7 @@ __global__ void __launch_bounds__(AttnCfg<D>::THREADS, AttnCfg<D>::MIN_BLOCKS) l
     for (int t = 0; t < nkv; ++t) {
       if (t + C::KST - 1 < nkv) load_k(t + C::KST - 1);
       const int vs = t % C::VST;
-      mbar_wait(&bars->v_empty[vs], ((t / C::VST) & 1) ^ 1);
+      mbar_wait_relaxed(&bars->v_empty[vs], ((t / C::VST) & 1) ^ 1, LDX_ATT_SLEEP_NS);
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars->v_full[vs], C::KV_BYTES);
         for (int c = 0; c < C::DCH; ++c)
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(AttnCfg<D>::THREADS, AttnCfg<D>::MIN_BLOCKS) l
       const __half one = __float2half(1.0f);
       for (int t = 0; t < nkv; ++t) {
         const int vs = t % C::VST;
-        mbar_wait(&bars->v_full[vs], (t / C::VST) & 1);
+        mbar_wait_relaxed(&bars->v_full[vs], (t / C::VST) & 1, LDX_ATT_SLEEP_NS);
         uint8_t* tile = sV + vs * C::KV_BYTES + (D / 64) * (BKV * 128);
 #pragma unroll
         for (int rr = 0; rr < BKV; rr += 32) {
@@ -219,7 +222,7 @@ __global__ void __launch_bounds__(AttnCfg<D>::THREADS, AttnCfg<D>::MIN_BLOCKS) l
       const uint32_t tSg = tS + g * BKV, tOg = tO + g * C::DN;
       auto mma_s = [&](int t) {
         const int ks = t % C::KST;
-        mbar_wait(&bars->k_full[ks], (t / C::KST) & 1);
+        mbar_wait_relaxed(&bars->k_full[ks], (t / C::KST) & 1, LDX_ATT_SLEEP_NS);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + ks * C::KV_BYTES);
         if (elect_one()) {
@@ -238,13 +241,13 @@ __global__ void __launch_bounds__(AttnCfg<D>::THREADS, AttnCfg<D>::MIN_BLOCKS) l
       mma_s(0);
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) {
-          mbar_wait(&bars->s_free[g], j & 1);
+          mbar_wait_relaxed(&bars->s_free[g], j & 1, LDX_ATT_SLEEP_NS);
           tc_fence_after();
           mma_s(j + 1);
         }
         const int vs = j % C::VST, pb = j % C::PB;
-        mbar_wait(&bars->p_full[g][pb], (j / C::PB) & 1);
-        mbar_wait(C::ONES ? &bars->v_ready[vs] : &bars->v_full[vs], (j / C::VST) & 1);
+        mbar_wait_relaxed(&bars->p_full[g][pb], (j / C::PB) & 1, LDX_ATT_SLEEP_NS);
+        mbar_wait_relaxed(C::ONES ? &bars->v_ready[vs] : &bars->v_full[vs], (j / C::VST) & 1, LDX_ATT_SLEEP_NS);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sV + vs * C::KV_BYTES);
         if (elect_one()) {

@@ -86,6 +86,23 @@ LDX_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for service warps whose wake-up latency is not critical: back off between polls so the spin loop
+// does not take issue slots from the compute warps sharing the scheduler.
+LDX_DEVICE void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+  const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return;
+  long long t0 = 0;
+  for (uint32_t it = 1;; ++it) {
+    __nanosleep(sleep_ns);
+    if (mbar_try_wait(addr, parity)) break;
+    if ((it & 1023u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > LDX_WAIT_LIMIT_CYCLES) __trap();
+    }
+  }
+}
+
 // generic-proxy writes to smem -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 LDX_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -9,7 +9,7 @@ def timeit(fn, iters=10):
     for _ in range(iters): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / iters
-shapes = [(16, 4096, 4096, 8, 40), (16, 4096, 4096, 8, 64), (16, 1024, 1024, 8, 80)]
+shapes = [(16, 4096, 4096, 8, 40), (16, 4096, 4096, 8, 40), (16, 1024, 1024, 8, 80)]
 for (B, Nq, Nk, H, d) in shapes:
     q = torch.randn(B, Nq, H * d, device="cuda").half(); k = torch.randn(B, Nk, H * d, device="cuda").half(); v = torch.randn(B, Nk, H * d, device="cuda").half()
     o = torch.empty_like(q)
