@@ -57,10 +57,11 @@ LDX_DEVICE void mbar_arrive(uint64_t* bar) {
 #define LDX_WAIT_LIMIT_CYCLES (1ll << 32)
 #endif
 #ifndef LDX_TRYWAIT_HINT_NS
-#define LDX_TRYWAIT_HINT_NS 20000u
+#define LDX_TRYWAIT_HINT_NS 0
 #endif
 LDX_DEVICE bool mbar_try_wait(uint32_t addr, uint32_t parity) {
   uint32_t done;
+#if LDX_TRYWAIT_HINT_NS > 0
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
@@ -68,8 +69,19 @@ LDX_DEVICE bool mbar_try_wait(uint32_t addr, uint32_t parity) {
       "selp.u32 %0, 1, 0, p;\n\t"
       "}"
       : "=r"(done)
-      : "r"(addr), "r"(parity), "r"(LDX_TRYWAIT_HINT_NS)   // suspend-time hint: fewer spin iterations stealing issue slots
+      : "r"(addr), "r"(parity), "r"((uint32_t)LDX_TRYWAIT_HINT_NS)
       : "memory");
+#else
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+#endif
   return done != 0;
 }
 LDX_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -154,8 +166,11 @@ LDX_DEVICE uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Arrive on a peer CTA's mbarrier.  Default semantics (.release.cta): the data this orders is TMEM, which the
+// tcgen05 fences cover; a cluster-scope release made every arrive wait ~1000 cycles for the thread's
+// outstanding global traffic.
 LDX_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
 // smem -> global tensor store (bulk async group); OOB parts of the box are clipped
@@ -305,7 +320,13 @@ LDX_DEVICE float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-LDX_DEVICE float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with one MUFU.EX2 and one MUFU.RCP (an IEEE division costs ~10 more issue slots per
+// element, which made the GroupNorm+SiLU pass issue-bound instead of bandwidth-bound)
+LDX_DEVICE float silu_f(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(-1.4426950408889634f * x)));
+  return x * r;
+}
 LDX_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|abs err| < 1.5e-7, far below fp16 output
 // rounding): 2 MUFU + ~10 FMA-pipe ops instead of erff's ~30.

@@ -41,12 +41,12 @@ __global__ void gn_stats_kernel(const GnArgs a) {
   const int p_end = min(a.HW, p_begin + a.pix_per_slab);
   if (pl < a.P) {
     int pix = p_begin + pl;
-    for (; pix + 3 * a.P < p_end; pix += 4 * a.P) {     // 4 independent 16-byte loads in flight
-      uint4 v[4];
+    for (; pix + 7 * a.P < p_end; pix += 8 * a.P) {     // 8 independent 16-byte loads in flight
+      uint4 v[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = gn_load(a, b, pix + u * a.P, vec);
+      for (int u = 0; u < 8; ++u) v[u] = gn_load(a, b, pix + u * a.P, vec);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const float2 f0 = unpack_h2(v[u].x), f1 = unpack_h2(v[u].y), f2 = unpack_h2(v[u].z), f3 = unpack_h2(v[u].w);
         const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
@@ -76,18 +76,39 @@ __global__ void gn_stats_kernel(const GnArgs a) {
   }
 }
 
-__global__ void gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_slab_apply) {
+__global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_slab_apply) {
   __shared__ float s_mean[32], s_rstd[32];
-  pdl_prologue();
   const int b = blockIdx.x, slab = blockIdx.y;
+  const int vec = threadIdx.x % a.nvec, pl = threadIdx.x / a.nvec;
+  const bool active = pl < a.P;
+  // affine parameters do not depend on the previous kernel: fetch them before the grid dependency resolves
+  float gm[8], bt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gm[j] = active ? __ldg(a.gamma + vec * 8 + j) : 0.f;
+    bt[j] = active ? __ldg(a.beta + vec * 8 + j) : 0.f;
+  }
+  pdl_prologue();
+  const int p_begin = slab * pix_per_slab_apply;
+  const int p_end = min(a.HW, p_begin + pix_per_slab_apply);
+  // first batch of activations in flight while the statistics are reduced
+  constexpr int U = 4;
+  uint4 v[U];
+  int pix = p_begin + pl;
+  const bool first_full = active && pix + (U - 1) * a.P < p_end;
+  if (first_full) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = gn_load(a, b, pix + u * a.P, vec);
+  }
   {
     // 8 threads per group sum the slab partials in a fixed order (bit-reproducible), in double
     const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
     double s = 0.0, ss = 0.0;
     if (g < 32) {
       for (int k = sub; k < a.nslab; k += 8) {
-        s += (double)a.partial[(((size_t)b * a.nslab + k) * 32 + g) * 2 + 0];
-        ss += (double)a.partial[(((size_t)b * a.nslab + k) * 32 + g) * 2 + 1];
+        const float2 pr = __ldg(reinterpret_cast<const float2*>(a.partial + (((size_t)b * a.nslab + k) * 32 + g) * 2));
+        s += (double)pr.x;
+        ss += (double)pr.y;
       }
     }
 #pragma unroll
@@ -105,21 +126,18 @@ __global__ void gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_sla
     }
   }
   __syncthreads();
-  const int vec = threadIdx.x % a.nvec, pl = threadIdx.x / a.nvec;
-  if (pl >= a.P) return;
+  if (!active) return;
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = vec * 8 + j;
     const int g = c / a.cpg;
-    const float w = a.gamma[c] * s_rstd[g];
+    const float w = gm[j] * s_rstd[g];
     sc[j] = w;
-    sh[j] = a.beta[c] - s_mean[g] * w;
+    sh[j] = bt[j] - s_mean[g] * w;
   }
-  const int p_begin = slab * pix_per_slab_apply;
-  const int p_end = min(a.HW, p_begin + pix_per_slab_apply);
-  auto apply_store = [&](const uint4& v, int pix) {
-    const float2 f0 = unpack_h2(v.x), f1 = unpack_h2(v.y), f2 = unpack_h2(v.z), f3 = unpack_h2(v.w);
+  auto apply_store = [&](const uint4& vv, int px) {
+    const float2 f0 = unpack_h2(vv.x), f1 = unpack_h2(vv.y), f2 = unpack_h2(vv.z), f3 = unpack_h2(vv.w);
     float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -128,15 +146,25 @@ __global__ void gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_sla
     }
     uint4 o;
     o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(a.y + ((int64_t)b * a.HW + pix) * a.ldy + vec * 8) = o;
+    *reinterpret_cast<uint4*>(a.y + ((int64_t)b * a.HW + px) * a.ldy + vec * 8) = o;
   };
-  int pix = p_begin + pl;
-  for (; pix + 3 * a.P < p_end; pix += 4 * a.P) {
-    uint4 v[4];
+  if (first_full) {
+    // software pipeline: the next batch is requested before the current one is transformed and stored
+    for (;;) {
+      const int nxt = pix + U * a.P;
+      const bool more = nxt + (U - 1) * a.P < p_end;
+      uint4 w[U];
+      if (more) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = gn_load(a, b, pix + u * a.P, vec);
+        for (int u = 0; u < U; ++u) w[u] = gn_load(a, b, nxt + u * a.P, vec);
+      }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) apply_store(v[u], pix + u * a.P);
+      for (int u = 0; u < U; ++u) apply_store(v[u], pix + u * a.P);
+      pix = nxt;
+      if (!more) break;
+#pragma unroll
+      for (int u = 0; u < U; ++u) v[u] = w[u];
+    }
   }
   for (; pix < p_end; pix += a.P) apply_store(gn_load(a, b, pix, vec), pix);
 }

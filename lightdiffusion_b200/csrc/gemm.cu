@@ -31,18 +31,40 @@ static constexpr int EPI_GROUPS = 2;                          // epilogue warpgr
 static constexpr int GEMM_THREADS = 64 + EPI_GROUPS * 128;   // warp 0 TMA, warp 1 MMA, then the epilogue groups
 static constexpr int MAX_STAGES = 6;
 
-static constexpr int EPI_CHUNK = 32;                         // output columns per staged chunk
-static constexpr int EPI_BUF_BYTES = BM * EPI_CHUNK * 2;     // 8 KiB, SWIZZLE_64B rows of 64 bytes
-static constexpr int EPI_NBUF = 4;                           // staging buffers per epilogue group
-static constexpr int EPI_THREADS = 128;
-static constexpr int EPI_SMEM = EPI_GROUPS * EPI_NBUF * EPI_BUF_BYTES;
+static constexpr int EPI_CHUNK = 32;                         // output columns per TMEM load
+static constexpr int EPI_PASS = 64;                          // output columns per staged pass (one fence + one TMA store)
+static constexpr int EPI_SLOT_BYTES = 32 * EPI_PASS * 2;     // 4 KiB: one warp's 32 rows x 128 bytes, SWIZZLE_128B
+static constexpr int EPI_NSLOT = 2;                          // staging slots per epilogue warp
+static constexpr int EPI_SMEM = EPI_GROUPS * 4 * EPI_NSLOT * EPI_SLOT_BYTES;
+
+#ifdef LDX_GEMM_TIMING
+// Variant-build instrumentation: CTA 0 stamps %globaltimer at pipeline milestones (ns).
+__device__ unsigned long long g_gemm_ts[16];
+__device__ __forceinline__ void ts_mark(int i) {
+  if (blockIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_gemm_ts[i] = t;
+  }
+}
+#define TS_MARK(i) ts_mark(i)
+#define PH_DECL long long ph_t = clock64(), ph_acc[7] = {0, 0, 0, 0, 0, 0, 0}; int ph_n = 0;
+#define PH(i) { const long long ph_now = clock64(); ph_acc[i] += ph_now - ph_t; ph_t = ph_now; }
+#define PH_COUNT ++ph_n;
+#define PH_FLUSH if (blockIdx.x == 0 && threadIdx.x == 64) { for (int i = 0; i < 7; ++i) g_gemm_ts[8 + i] = (unsigned long long)ph_acc[i]; g_gemm_ts[15] = (unsigned long long)ph_n; }
+#else
+#define TS_MARK(i)
+#define PH_DECL
+#define PH(i)
+#define PH_COUNT
+#define PH_FLUSH
+#endif
 
 struct __align__(8) GemmBarriers {
   uint64_t full[MAX_STAGES];
   uint64_t empty[MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
-  uint64_t res_full[EPI_GROUPS * EPI_NBUF];
   uint32_t tmem_base;
 };
 
@@ -138,6 +160,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TS_MARK(0);
   const int stages = p.stages;
   const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
   const int worker = (int)blockIdx.x / kCtas, nworkers = (int)gridDim.x / kCtas;
@@ -159,9 +182,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       mbar_init(&bars->tmem_full[a], 1);
       mbar_init(&bars->tmem_empty[a], 4 * EPI_GROUPS * kCtas);
     }
-    for (int a = 0; a < EPI_GROUPS * EPI_NBUF; ++a) mbar_init(&bars->res_full[a], 1);
     tma_prefetch_desc(&p.omap);
-    tma_prefetch_desc(&p.rmap);
+    tma_prefetch_desc(&p.omap64);
+    tma_prefetch_desc(&p.idmap);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -177,7 +200,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
   if constexpr (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if (threadIdx.x == 0) TS_MARK(1);
   pdl_prologue();   // everything above overlaps the tail of the previous kernel
+  if (threadIdx.x == 0) TS_MARK(2);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (warp-uniform loop)
@@ -189,32 +214,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
         const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
         const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * p.bn + (int)cta_rank * bn_cta;
         int kcol = 0;
+        auto load_step = [&](const CUtensorMap* am, int ac0, int ax, int ay, const CUtensorMap* bm, int bk, int bn0) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* dA = sA + (size_t)stage * A_STAGE_BYTES;
+          uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
+          if constexpr (kCtas == 2) {
+            // both CTAs' loads complete on the leader's barrier, which the leader arms for the pair
+            const uint32_t lbar = mapa_shared(smem_u32(&bars->full[stage]), 0);
+            if (elect_one()) {
+              if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2 * (A_STAGE_BYTES + b_stage_bytes));
+              tma_load_4d_pair(dA, am, lbar, ac0, ax, ay, b0);
+              tma_load_2d_pair(dB, bm, lbar, bk, bn0);
+            }
+          } else {
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&bars->full[stage], A_STAGE_BYTES + b_stage_bytes);
+              tma_load_4d(dA, am, &bars->full[stage], ac0, ax, ay, b0);
+              tma_load_2d(dB, bm, &bars->full[stage], bk, bn0);
+            }
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        };
         for (int s = 0; s < p.nseg; ++s) {
           const KSeg sg = p.seg[s];
           for (int ch = 0; ch < sg.nchunks; ++ch) {
-            mbar_wait(&bars->empty[stage], phase ^ 1);
-            uint8_t* dA = sA + (size_t)stage * A_STAGE_BYTES;
-            uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
-            if constexpr (kCtas == 2) {
-              // both CTAs' loads complete on the leader's barrier, which the leader arms for the pair
-              const uint32_t lbar = mapa_shared(smem_u32(&bars->full[stage]), 0);
-              if (elect_one()) {
-                if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2 * (A_STAGE_BYTES + b_stage_bytes));
-                tma_load_4d_pair(dA, &p.amap[sg.map], lbar, sg.c0 + ch * BK, x0 + sg.dx, y0 + sg.dy, b0);
-                tma_load_2d_pair(dB, &p.bmap, lbar, kcol, n0);
-              }
-            } else {
-              if (elect_one()) {
-                mbar_arrive_expect_tx(&bars->full[stage], A_STAGE_BYTES + b_stage_bytes);
-                tma_load_4d(dA, &p.amap[sg.map], &bars->full[stage], sg.c0 + ch * BK, x0 + sg.dx, y0 + sg.dy, b0);
-                tma_load_2d(dB, &p.bmap, &bars->full[stage], kcol, n0);
-              }
-            }
-            __syncwarp();
+            load_step(&p.amap[sg.map], sg.c0 + ch * BK, x0 + sg.dx, y0 + sg.dy, &p.bmap, kcol, n0);
             kcol += BK;
-            if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
+        // residual fused as an identity K segment (see gemm_prepare): A = the residual tile's own column
+        // range, B = the matching rows of I
+        for (int dk = 0; dk < p.diag_chunks; ++dk)
+          load_step(&p.amap[p.diag_src], nt * p.bn + dk * BK, x0, y0, &p.idmap, dk * BK, (int)cta_rank * bn_cta);
       }
     }
   } else if (warp == 1) {
@@ -234,6 +266,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
         for (int kb = 0; kb < p.nk; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
+          if (lane == 0 && it == 0 && kb == 0) TS_MARK(3);
+          if (lane == 0 && it == 0 && kb == p.nk - 1) TS_MARK(4);
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
           if (elect_one()) {
@@ -256,10 +290,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue: EPI_GROUPS warpgroups.
-    // Group g owns the 32-column chunks c = g, g + EPI_GROUPS, ... of every tile; a thread owns one row.
-    // Per chunk: TMEM -> regs -> (+bias, +rowadd, +residual tile that TMA prefetched into the staging
-    // buffer, activation) -> fp16 into the SWIZZLE_64B staging tile -> TMA store (coalesced, clipped).
+    // ------------------------------------------------------------------ epilogue: EPI_GROUPS x 4 warps.
+    // A thread owns one output row; group g owns the 64-column passes ps = g, g + EPI_GROUPS, ... of a tile.
+    // Per pass: two 32-column steps TMEM -> regs -> (+bias, +rowadd, activation) -> fp16 into the warp's
+    // staging slot (32 rows x 128 B, SWIZZLE_128B), then ONE proxy fence and ONE TMA store of the warp's
+    // 32-row sub-box.  Every warp runs its own pipeline (own slots, own bulk groups): there is no block- or
+    // group-level barrier in the loop.  The residual never reaches the epilogue: it is accumulated by the
+    // tensor core through an identity K segment.
     const int grp = (warp - 2) >> 2;
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
@@ -268,44 +305,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
     const int n_out_tile = geglu ? p.bn / 2 : p.bn;
     const int n_out_total = geglu ? p.N / 2 : p.N;
     const int osz = f32 ? 4 : 2;
-    const bool elected = ((threadIdx.x - 64) & 127) == 0;   // first thread of the group issues its TMA traffic
-    uint8_t* sCg = sC + grp * (EPI_NBUF * EPI_BUF_BYTES);
-    uint64_t* res_full = &bars->res_full[grp * EPI_NBUF];
+    const bool elected = lane == 0;             // lane 0 of each warp issues the warp's TMA stores
+    uint8_t* sW = sC + (size_t)((grp * 4 + q) * EPI_NSLOT) * EPI_SLOT_BYTES;   // this warp's staging ring
+    // origin of the warp's 32 rows inside the 128-pixel tile box (bw, bh, bb are powers of two)
+    const int sub_x = (q * 32) % p.bw, sub_y = ((q * 32) / p.bw) % p.bh, sub_b = (q * 32) / (p.bw * p.bh);
     const uint32_t leader_empty0 = kCtas == 2 ? mapa_shared(smem_u32(&bars->tmem_empty[0]), 0) : 0u;
     const uint32_t leader_empty1 = kCtas == 2 ? mapa_shared(smem_u32(&bars->tmem_empty[1]), 0) : 0u;
     auto release_tmem = [&](int as) {
       if constexpr (kCtas == 2) mbar_arrive_cluster(as ? leader_empty1 : leader_empty0);
       else mbar_arrive(&bars->tmem_empty[as]);
     };
-    auto tile_nchunk = [&](int tile) {
-      const int n_out0 = (tile % p.n_tiles) * n_out_tile;
-      return (min(n_out_tile, n_out_total - n_out0) + EPI_CHUNK - 1) / EPI_CHUNK;
-    };
-    // residual prefetch cursor: runs EPI_RES_AHEAD items ahead of the consume cursor over the same sequence
-    constexpr int EPI_RES_AHEAD = 2;
-    int pf_tile = worker, pf_chunk = grp;
-    uint32_t pf_idx = 0;
-    auto pf_normalise = [&]() {
-      while (pf_tile < p.num_tiles && pf_chunk >= tile_nchunk(pf_tile)) { pf_tile += nworkers; pf_chunk = grp; }
-    };
-    auto pf_issue = [&]() {                     // elected thread only
-      pf_normalise();
-      if (pf_tile >= p.num_tiles) return;
-      const int nt = pf_tile % p.n_tiles, mt = (pf_tile / p.n_tiles) * kCtas + (int)cta_rank;
-      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
-      const uint32_t buf = pf_idx % EPI_NBUF;
-      mbar_arrive_expect_tx(&res_full[buf], EPI_BUF_BYTES);
-      tma_load_4d(sCg + buf * EPI_BUF_BYTES, &p.rmap, &res_full[buf], nt * n_out_tile + pf_chunk * EPI_CHUNK,
-                  tx * p.bw, ty * p.bh, tb * p.bb);
-      pf_chunk += EPI_GROUPS;
-      ++pf_idx;
-    };
-    const bool use_res = p.tma_epi && p.res != nullptr;
-    if (use_res && elected) {
-      for (int i = 0; i < EPI_RES_AHEAD; ++i) pf_issue();
-    }
-    uint32_t cidx = 0;                          // this group's running chunk counter (staging buffer ring)
+    uint32_t pidx = 0;                          // this warp's running pass counter (staging ring)
     int it = 0;
+    PH_DECL
     for (int tile = worker; tile < p.num_tiles; tile += nworkers, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
@@ -319,10 +331,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       const float* rowadd_row = (p.rowadd && valid) ? p.rowadd + (int64_t)b * p.ld_rowadd : nullptr;
       const int n_out0 = nt * n_out_tile;
       const uint32_t trow = tmem_base + as * p.acc_stride + ((uint32_t)(q * 32) << 16);
-      const int nchunk = tile_nchunk(tile);
+      const int n_here = min(n_out_tile, n_out_total - n_out0);        // output columns of this tile
+      const int npass = (n_here + EPI_PASS - 1) / EPI_PASS;
 
+      PH(5)
       mbar_wait(&bars->tmem_full[as], aphase);
       tc_fence_after();
+      PH(0)
+      if (threadIdx.x == 64 && it == 0) TS_MARK(5);
 
       if (p.flags & (1 << 17)) {               // debug: epilogue only drains the accumulator
         tc_fence_before();
@@ -331,102 +347,108 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
         continue;
       }
       if (p.tma_epi) {
-        int last_c = grp;                       // this group's last chunk of the tile
-        while (last_c + EPI_GROUPS < nchunk) last_c += EPI_GROUPS;
-        if (grp >= nchunk) {                    // nothing to do for this group in a narrow tile
+        if (grp >= npass) {                     // nothing to do for this group in a narrow tile
           tc_fence_before();
           __syncwarp();
           if (lane == 0) release_tmem(as);
           continue;
         }
-        for (int c = grp; c < nchunk; c += EPI_GROUPS, ++cidx) {
-          const uint32_t buf = cidx % EPI_NBUF;
-          uint8_t* cbuf = sCg + buf * EPI_BUF_BYTES;
-          const int n_glob = n_out0 + c * EPI_CHUNK;
-          if (elected) {
-            tma_store_wait_read<1>();           // stores older than the previous chunk have drained their buffers
-            if (use_res) pf_issue();            // residual tile EPI_RES_AHEAD chunks ahead (buffer of chunk cidx-2)
-          }
-          uint32_t r[32];
-          float v[32];
-          tmem_ld32(trow + c * EPI_CHUNK, r);
-          if (geglu) {
-            uint32_t g[32];
-            tmem_ld32(trow + c * EPI_CHUNK + p.bn / 2, g);
-            tmem_ld_wait();
-            const int n_packed = nt * p.bn + c * EPI_CHUNK;
+        int last_ps = grp;                      // this group's last pass of the tile
+        while (last_ps + EPI_GROUPS < npass) last_ps += EPI_GROUPS;
+        for (int ps = grp; ps < npass; ps += EPI_GROUPS, ++pidx) {
+          uint8_t* cbuf = sW + (pidx % EPI_NSLOT) * EPI_SLOT_BYTES;
+          // a pass is 64 columns wide unless the tile's width leaves a 32-column tail
+          const bool wide = n_out_tile - ps * EPI_PASS >= EPI_PASS;
+          const int nhalf = wide ? 2 : 1;
+          PH(5)
+          if (elected) tma_store_wait_read<EPI_NSLOT - 1>();   // the slot's previous store has drained it
+          __syncwarp();
+          PH(1)
+          PH_COUNT
+          for (int half = 0; half < nhalf; ++half) {
+            const int c = ps * EPI_PASS + half * EPI_CHUNK;     // column inside the tile
+            const int n_glob = n_out0 + c;
+            uint32_t r[32];
+            float v[32];
+            tmem_ld32(trow + c, r);
+            if (geglu) {
+              uint32_t g[32];
+              tmem_ld32(trow + c + p.bn / 2, g);
+              tmem_ld_wait();
+              const int n_packed = nt * p.bn + c;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-              if (p.bias) {
-                ba = __ldg(reinterpret_cast<const float4*>(p.bias + n_packed) + j4);
-                bg = __ldg(reinterpret_cast<const float4*>(p.bias + n_packed + p.bn / 2) + j4);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+                if (p.bias) {
+                  ba = __ldg(reinterpret_cast<const float4*>(p.bias + n_packed) + j4);
+                  bg = __ldg(reinterpret_cast<const float4*>(p.bias + n_packed + p.bn / 2) + j4);
+                }
+                v[j4 * 4 + 0] = (__uint_as_float(r[j4 * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 0]) + bg.x);
+                v[j4 * 4 + 1] = (__uint_as_float(r[j4 * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 1]) + bg.y);
+                v[j4 * 4 + 2] = (__uint_as_float(r[j4 * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 2]) + bg.z);
+                v[j4 * 4 + 3] = (__uint_as_float(r[j4 * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 3]) + bg.w);
               }
-              v[j4 * 4 + 0] = (__uint_as_float(r[j4 * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 0]) + bg.x);
-              v[j4 * 4 + 1] = (__uint_as_float(r[j4 * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 1]) + bg.y);
-              v[j4 * 4 + 2] = (__uint_as_float(r[j4 * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 2]) + bg.z);
-              v[j4 * 4 + 3] = (__uint_as_float(r[j4 * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 3]) + bg.w);
-            }
-          } else {
-            tmem_ld_wait();
+            } else {
+              // bias / rowadd values are fetched while the TMEM load is in flight
+              float4 bb4[8];
+              const bool bias_vec = p.bias && n_glob + EPI_CHUNK <= p.N;
+              if (bias_vec) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.bias) {
-              if (n_glob + EPI_CHUNK <= p.N) {
+                for (int j4 = 0; j4 < 8; ++j4) bb4[j4] = __ldg(reinterpret_cast<const float4*>(p.bias + n_glob) + j4);
+              }
+              tmem_ld_wait();
+              PH(3)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              if (bias_vec) {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 bb4 = __ldg(reinterpret_cast<const float4*>(p.bias + n_glob) + j4);
-                  v[j4 * 4 + 0] += bb4.x; v[j4 * 4 + 1] += bb4.y; v[j4 * 4 + 2] += bb4.z; v[j4 * 4 + 3] += bb4.w;
+                  v[j4 * 4 + 0] += bb4[j4].x; v[j4 * 4 + 1] += bb4[j4].y; v[j4 * 4 + 2] += bb4[j4].z; v[j4 * 4 + 3] += bb4[j4].w;
                 }
-              } else {
+              } else if (p.bias) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (n_glob + j < p.N) v[j] += __ldg(p.bias + n_glob + j);
               }
-            }
-            if (rowadd_row) {
+              if (rowadd_row) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n_glob + j < p.N) v[j] += __ldg(rowadd_row + n_glob + j);
+                for (int j = 0; j < 32; ++j)
+                  if (n_glob + j < p.N) v[j] += __ldg(rowadd_row + n_glob + j);
+              }
             }
-          }
-          if (c == last_c) {                    // this group has read all its accumulator columns
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) release_tmem(as);
-          }
-          // SWIZZLE_64B tile: row r at r*64 bytes, 16-byte chunk index XOR ((r >> 1) & 3)
-          uint8_t* srow = cbuf + row * 64;
-          const int sw = (row >> 1) & 3;
-          if (use_res) {
-            mbar_wait(&res_full[buf], (cidx / EPI_NBUF) & 1);
+            PH(2)
+            if (ps == last_ps && half == nhalf - 1) {   // this warp has read all its accumulator columns
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) release_tmem(as);
+            }
+            if (p.flags & LDX_EPI_SILU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+            }
+            // wide: SWIZZLE_128B rows of 128 B, 16-byte chunk index XOR (row & 7);
+            // tail: SWIZZLE_64B rows of 64 B, chunk index XOR ((row >> 1) & 3)
+            uint8_t* srow = wide ? cbuf + lane * 128 : cbuf + lane * 64;
+            const int sw = wide ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
-              const uint4 rr = *reinterpret_cast<const uint4*>(srow + ((ch ^ sw) << 4));
-              const float2 a0 = unpack_h2(rr.x), a1 = unpack_h2(rr.y), a2 = unpack_h2(rr.z), a3 = unpack_h2(rr.w);
-              v[ch * 8 + 0] += a0.x; v[ch * 8 + 1] += a0.y; v[ch * 8 + 2] += a1.x; v[ch * 8 + 3] += a1.y;
-              v[ch * 8 + 4] += a2.x; v[ch * 8 + 5] += a2.y; v[ch * 8 + 6] += a3.x; v[ch * 8 + 7] += a3.y;
+              uint4 o;
+              o.x = pack_h2(v[ch * 8 + 0], v[ch * 8 + 1]);
+              o.y = pack_h2(v[ch * 8 + 2], v[ch * 8 + 3]);
+              o.z = pack_h2(v[ch * 8 + 4], v[ch * 8 + 5]);
+              o.w = pack_h2(v[ch * 8 + 6], v[ch * 8 + 7]);
+              *reinterpret_cast<uint4*>(srow + (((half * 4 + ch) ^ sw) << 4)) = o;
             }
           }
-          if (p.flags & LDX_EPI_SILU) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
-          }
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint4 o;
-            o.x = pack_h2(v[ch * 8 + 0], v[ch * 8 + 1]);
-            o.y = pack_h2(v[ch * 8 + 2], v[ch * 8 + 3]);
-            o.z = pack_h2(v[ch * 8 + 4], v[ch * 8 + 5]);
-            o.w = pack_h2(v[ch * 8 + 6], v[ch * 8 + 7]);
-            *reinterpret_cast<uint4*>(srow + ((ch ^ sw) << 4)) = o;
-          }
+          PH(4)
           fence_proxy_async_smem();
-          named_bar_sync(1 + grp, EPI_THREADS);
+          PH(6)
+          __syncwarp();
           if (elected && !(p.flags & (1 << 16))) {   // (bit 16: debug, skip the store)
-            tma_store_4d(&p.omap, cbuf, n_glob, x0, y0, b0);
+            tma_store_4d(wide ? &p.omap64 : &p.omap, cbuf, n_out0 + ps * EPI_PASS, x0 + sub_x, y0 + sub_y, b0 + sub_b);
             tma_store_commit();
           }
+          PH(1)
         }
         continue;
       }
@@ -450,7 +472,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       __syncwarp();
       if (lane == 0) release_tmem(as);
     }
+    PH_FLUSH
+    if (threadIdx.x == 64) TS_MARK(6);
     if (p.tma_epi && elected) tma_store_wait_all();
+    if (threadIdx.x == 64) TS_MARK(7);
   }
 
   tc_fence_before();
@@ -535,6 +560,23 @@ static int pow2_ceil(int v) {
   return p;
 }
 
+// 256 x 256 fp16 identity in device memory (lazily created, lives for the process): B operand of the
+// fused-residual K steps.  Any bn x 64 slice of a larger identity that a tile needs equals a slice of this one.
+static const void* identity256() {
+  static void* dev = nullptr;
+  if (!dev) {
+    __half* host = (__half*)calloc(256 * 256, sizeof(__half));
+    if (!host) return nullptr;
+    for (int i = 0; i < 256; ++i) host[i * 256 + i] = __float2half(1.0f);
+    void* ptr = nullptr;
+    if (cudaMalloc(&ptr, 256 * 256 * sizeof(__half)) == cudaSuccess &&
+        cudaMemcpy(ptr, host, 256 * 256 * sizeof(__half), cudaMemcpyHostToDevice) == cudaSuccess)
+      dev = ptr;
+    free(host);
+  }
+  return dev;
+}
+
 // Tile configuration: N tile width and 1-CTA vs CTA-pair kernel.  Cost model per 16-wide K step and per
 // SM: tensor pipe bn/2 cycles vs operand fetch (L2 -> smem) of (128 + bn/ctas) rows x 32 bytes at an
 // effective ~61 B/clk/SM (calibrated on B200: the 1-CTA 128x256 tile runs at ~0.64 of the MMA rate).
@@ -598,6 +640,16 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     const char* e = getenv("LDX_GEMM_CTAS");
     force_ctas = e ? atoi(e) : 0;
   }
+  // TMA-store epilogue (fp16 outputs whose strides satisfy the TMA rules); otherwise direct stores
+  const int osz = (d->flags & LDX_EPI_OUT_F32) ? 4 : 2;
+  bool tma_ok = osz == 2 && ((reinterpret_cast<uintptr_t>(d->out) + (uint64_t)d->o_off * 2) % 16 == 0) &&
+                (d->o_sx * 2) % 16 == 0 && (d->o_sy * 2) % 16 == 0 && (d->o_sb * 2) % 16 == 0 && d->o_sx > 0;
+  if (d->bias && (reinterpret_cast<uintptr_t>(d->bias) % 16 != 0)) tma_ok = false;   // float4 bias loads
+  // Residual: fused into the GEMM as an identity K segment (A = the residual tile's own columns, B = I),
+  // so it rides the operand pipeline and the fp32 accumulator adds it exactly.
+  bool fuse_res = d->residual && tma_ok && d->nsrc < LDX_MAX_SRC && (reinterpret_cast<uintptr_t>(d->residual) % 16 == 0) &&
+                  (d->ldr * 2) % 16 == 0;
+  if (d->residual && !fuse_res) tma_ok = false;                 // direct-store path adds the residual itself
   int bn = d->bn, ctas = 1;
   if (bn == 0) {
     choose_config(d->N, m_tiles, d->flags, sms, force_ctas, &bn, &ctas);
@@ -627,8 +679,13 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     nk += sg.nchunks;
   }
   p.nseg = d->nseg;
-  p.nk = nk;
   LDX_CHECK_ARG(d->ldw >= (int64_t)nk * BK, "weight pitch %lld < K %d", (long long)d->ldw, nk * BK);
+  const int k_weights = nk;                   // K steps that read the weight matrix
+  p.diag_src = 0;
+  // ceil(bn / 64) identity steps: I's rows stop at bn, so the columns past bn of the last step add nothing
+  p.diag_chunks = fuse_res ? (bn + 63) / 64 : 0;
+  nk += p.diag_chunks;
+  p.nk = nk;
 
   const uint32_t b_stage = (uint32_t)(bn / ctas) * BK * 2;
   int stages = (int)((224 * 1024 - EPI_SMEM - 2048) / (A_STAGE_BYTES + b_stage));
@@ -657,8 +714,24 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     if (rc) return rc;
   }
   for (int i = d->nsrc; i < LDX_MAX_SRC; ++i) p.amap[i] = p.amap[0];
+  p.idmap = p.bmap;
+  if (fuse_res) {
+    p.diag_src = d->nsrc;
+    const uint64_t dims[4] = {(uint64_t)d->N, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
+    const uint64_t str[3] = {(uint64_t)d->ldr * 2, (uint64_t)d->ldr * 2 * d->W, (uint64_t)d->ldr * 2 * d->W * d->H};
+    const uint32_t box[4] = {(uint32_t)BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    int rc = encode_map_f16(&p.amap[d->nsrc], d->residual, 4, dims, str, box);
+    if (rc) return rc;
+    const void* ident = identity256();
+    LDX_CHECK_ARG(ident != nullptr, "identity matrix allocation failed");
+    const uint64_t idims[2] = {256, 256};
+    const uint64_t istr[1] = {256 * 2};
+    const uint32_t ibox[2] = {(uint32_t)BK, (uint32_t)(bn / ctas)};
+    rc = encode_map_f16(&p.idmap, ident, 2, idims, istr, ibox);
+    if (rc) return rc;
+  }
   {
-    const uint64_t dims[2] = {(uint64_t)nk * BK, (uint64_t)d->N};
+    const uint64_t dims[2] = {(uint64_t)k_weights * BK, (uint64_t)d->N};
     const uint64_t str[1] = {(uint64_t)d->ldw * 2};
     const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(bn / ctas)};
     int rc = encode_map_f16(&p.bmap, d->w, 2, dims, str, box);
@@ -670,7 +743,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.bias = d->bias;
   p.rowadd = d->rowadd;
   p.ld_rowadd = d->ld_rowadd;
-  p.res = d->residual;
+  p.res = fuse_res ? nullptr : d->residual;    // only the direct-store epilogue still sees a residual pointer
   p.ldr = d->ldr;
   p.flags = d->flags;
   {
@@ -686,39 +759,32 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     if (dbg == 1) p.flags |= (1 << 16);
     if (dbg == 2) p.flags |= (1 << 17);
   }
-  const int osz = (d->flags & LDX_EPI_OUT_F32) ? 4 : 2;
   const int n_out = (d->flags & LDX_EPI_GEGLU) ? d->N / 2 : d->N;
   bool vec = (n_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->out) + (uint64_t)d->o_off * osz) % 16 == 0) &&
              ((d->o_sx * osz) % 16 == 0) && ((d->o_sy * osz) % 16 == 0) && ((d->o_sb * osz) % 16 == 0);
   if (d->residual) vec = vec && (reinterpret_cast<uintptr_t>(d->residual) % 16 == 0) && ((d->ldr * 2) % 16 == 0);
   p.vec_ok = vec ? 1 : 0;
 
-  // TMA-store epilogue (fp16 outputs whose strides satisfy the TMA rules); otherwise direct stores
   auto fix = [](int64_t s, int64_t fallback) { return (uint64_t)(s > 0 ? s : fallback) * 2; };
-  bool tma_ok = osz == 2 && ((reinterpret_cast<uintptr_t>(d->out) + (uint64_t)d->o_off * 2) % 16 == 0) &&
-                (d->o_sx * 2) % 16 == 0 && (d->o_sy * 2) % 16 == 0 && (d->o_sb * 2) % 16 == 0 && d->o_sx > 0;
-  if (d->residual) tma_ok = tma_ok && (reinterpret_cast<uintptr_t>(d->residual) % 16 == 0) && ((d->ldr * 2) % 16 == 0);
   p.tma_epi = 0;
   p.omap = p.bmap;
-  p.rmap = p.bmap;
+  p.omap64 = p.bmap;
   if (tma_ok) {
-    const uint32_t box[4] = {(uint32_t)EPI_CHUNK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bb};
+    // one epilogue warp moves 32 of the tile's 128 pixels: a (sw, sh, sb) sub-box of the (bw, bh, bb) tile
+    const int sw_ = bw < 32 ? bw : 32, sh_ = bh < 32 / sw_ ? bh : 32 / sw_, sb_ = 32 / (sw_ * sh_);
+    const uint32_t box[4] = {(uint32_t)EPI_CHUNK, (uint32_t)sw_, (uint32_t)sh_, (uint32_t)sb_};
+    const uint32_t box64[4] = {(uint32_t)EPI_PASS, (uint32_t)sw_, (uint32_t)sh_, (uint32_t)sb_};
     const uint64_t odims[4] = {(uint64_t)n_out, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
     const uint64_t sx = (uint64_t)d->o_sx * 2;
     const uint64_t sy = fix(d->o_sy, d->o_sx * d->W);
     const uint64_t sb = fix(d->o_sb, (d->o_sy > 0 ? d->o_sy : d->o_sx * d->W) * d->H);
     const uint64_t ostr[3] = {sx, sy, sb};
-    int rc = encode_map_f16_sw(&p.omap, reinterpret_cast<const char*>(d->out) + d->o_off * 2, 4, odims, ostr, box,
-                               CU_TENSOR_MAP_SWIZZLE_64B);
+    const char* obase = reinterpret_cast<const char*>(d->out) + d->o_off * 2;
+    int rc = encode_map_f16_sw(&p.omap, obase, 4, odims, ostr, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
-    if (d->residual) {
-      const uint64_t rdims[4] = {(uint64_t)d->N, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->B};
-      const uint64_t rstr[3] = {(uint64_t)d->ldr * 2, (uint64_t)d->ldr * 2 * d->W, (uint64_t)d->ldr * 2 * d->W * d->H};
-      rc = encode_map_f16_sw(&p.rmap, d->residual, 4, rdims, rstr, box, CU_TENSOR_MAP_SWIZZLE_64B);
-      if (rc) return rc;
-    }
+    rc = encode_map_f16_sw(&p.omap64, obase, 4, odims, ostr, box64, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
     p.tma_epi = 1;
-    if (p.bias && (reinterpret_cast<uintptr_t>(p.bias) % 16 != 0)) p.tma_epi = 0;   // float4 bias loads
   }
   return LDX_OK;
 }
@@ -790,6 +856,12 @@ __global__ void pack_geglu_kernel(const __half* __restrict__ w, const float* __r
 }  // namespace ldx
 
 using namespace ldx;
+
+#ifdef LDX_GEMM_TIMING
+extern "C" int ldx_debug_gemm_ts(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, g_gemm_ts, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream) {
   GemmLaunch g;

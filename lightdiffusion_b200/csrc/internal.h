@@ -77,10 +77,12 @@ struct KSeg {
 struct alignas(64) GemmKParams {
   CUtensorMap amap[LDX_MAX_SRC];
   CUtensorMap bmap;
-  CUtensorMap omap;   // output, box (32, bw, bh, bb), SWIZZLE_64B (TMA-store epilogue)
-  CUtensorMap rmap;   // residual, same box
+  CUtensorMap omap;    // output, box (32 cols, one warp's 32-pixel sub-box), SWIZZLE_64B: tail passes
+  CUtensorMap omap64;  // output, box (64 cols, same sub-box), SWIZZLE_128B: full passes
+  CUtensorMap idmap;   // 256 x 256 identity, box (64, bn / ctas): B operand of the fused-residual K steps
   KSeg seg[LDX_MAX_SEG];
-  int32_t nseg, nk;
+  int32_t nseg, nk;    // nk = K steps per tile, including diag_chunks
+  int32_t diag_src, diag_chunks;   // residual fused as an identity K segment: amap index, bn / 64 steps (0 = none)
   int32_t N, W, H, B;
   int32_t bw, bh, bb;
   int32_t tiles_x, tiles_y, tiles_b, n_tiles, num_tiles;

@@ -7,6 +7,7 @@ from lightdiffusion_b200 import _lib as L, kernels as K
 ap = argparse.ArgumentParser()
 ap.add_argument("--case", default="all")
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--hot", action="store_true", help="no L2 flush: inputs stay L2-resident between iterations")
 args = ap.parse_args()
 dev = "cuda"
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -15,7 +16,8 @@ def timeit(fn, iters):
     fn(); torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
-        flush.zero_()
+        if not args.hot:
+            flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); fn(); e1.record(); torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
@@ -60,6 +62,11 @@ CASES = {
     "conv2560_8": lambda: conv(16, 8, 8, 2560, 1280),
 }
 names = list(CASES) if args.case == "all" else args.case.split(",")
+for n in list(names):
+    if n.startswith("lin:"):            # lin:M:N:K[:res]
+        f = n.split(":")
+        M_, N_, K_ = int(f[1]), int(f[2]), int(f[3])
+        CASES[n] = (lambda M_=M_, N_=N_, K_=K_, r_=len(f) > 4: lin(M_, N_, K_, res=r_))
 for n in names:
     fn, fl, keep = CASES[n]()
     ms = timeit(fn, args.iters)
