@@ -49,21 +49,22 @@ static constexpr int ATT_MAX_NG = 4;
 #define LDX_ATT_POLY_MOD 0      // every POLY_MOD-th exponential runs on the FMA pipe (0 = all on MUFU); measured: no gain
 #endif
 
-template <int D>
+template <int D, int NG_>
 struct AttnCfg {
   static constexpr int DK = (D + 15) / 16;          // 16-wide K steps of Q K^T
   static constexpr int DCH = (D + 63) / 64;         // 64-column smem chunks per row
   static constexpr int DN = DK * 16;                // UMMA N of P V
-  static constexpr int NG = DCH == 1 ? LDX_ATT_NG_SMALL : 1;   // 128-row query groups per CTA
+  static constexpr int NG = NG_;                    // 128-row query groups per CTA
   static constexpr int THREADS = 32 * (2 + NG + 4 * NG);   // producer, V patcher, NG MMA issuers, 4 softmax warps / group
   // Row sums on the tensor core: when P V has a spare accumulator column (DN > D) the V tile's column D is
   // set to 1.0 after it lands, so O[:, D] accumulates sum_j P_ij and the softmax warps skip 64 FADDs a tile.
   static constexpr bool ONES = (DN > D) && (LDX_ATT_ONES != 0);
-  static constexpr int KST = 2;
-  static constexpr int VST = DCH == 1 ? 2 : 1;
+  // single-group CTAs (short K/V: cross-attention) stay small so that several fit on an SM
+  static constexpr int KST = (DCH == 1 && NG == 1) ? 1 : 2;
+  static constexpr int VST = (DCH == 1 && NG > 1) ? 2 : 1;
   static constexpr int Q_BYTES = DCH * BQ * 128;    // per group
   static constexpr int KV_BYTES = DCH * BKV * 128;
-  static constexpr int PB = DCH == 1 ? 2 : 1;       // P tiles per group: with one, P(j) waits for P V(j-1) to drain
+  static constexpr int PB = (DCH == 1 && NG > 1) ? 2 : 1;   // P tiles per group: with one, P(j) waits for P V(j-1) to drain
   static constexpr int P_BYTES = BQ * BKV * 2;      // per group and buffer
   static constexpr int TMEM_NEED = NG * (BKV + DN);
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
@@ -72,7 +73,9 @@ struct AttnCfg {
   static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
   static constexpr int BY_THREADS = 2048 / THREADS;
   static constexpr int B0 = BY_TMEM < BY_SMEM ? BY_TMEM : BY_SMEM;
-  static constexpr int B1 = B0 < BY_THREADS ? B0 : BY_THREADS;
+  static constexpr int BY_REGS = 65536 / (80 * ((THREADS + 127) / 128 * 128));   // at least 80 registers per thread
+  static constexpr int B1a = B0 < BY_THREADS ? B0 : BY_THREADS;
+  static constexpr int B1 = B1a < BY_REGS ? B1a : BY_REGS;
   static constexpr int MIN_BLOCKS = B1 < 1 ? 1 : B1;
   static_assert(TMEM_NEED <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "smem budget");
@@ -104,10 +107,10 @@ LDX_DEVICE float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <int D>
-__global__ void __launch_bounds__(AttnCfg<D>::THREADS, AttnCfg<D>::MIN_BLOCKS) ldx_attention_kernel(
+template <int D, int NG_>
+__global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN_BLOCKS) ldx_attention_kernel(
     const __grid_constant__ AttnParams p) {
-  using C = AttnCfg<D>;
+  using C = AttnCfg<D, NG_>;
   constexpr int NG = C::NG;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -431,14 +434,12 @@ __global__ void __launch_bounds__(AttnCfg<D>::THREADS, AttnCfg<D>::MIN_BLOCKS) l
 struct AttnLaunch {
   AttnParams p;
   dim3 grid;
-  int d;
+  int d, ng;
 };
 
-template <int D>
-static dim3 attention_grid(int B, int Nq, int heads) {
-  constexpr int rows = AttnCfg<D>::NG * BQ;
-  return dim3((Nq + rows - 1) / rows, heads, B);
-}
+// Query groups per CTA: 4 for the long self-attention streams of narrow heads (K/V read once per 512 queries),
+// 1 when K/V is short (cross-attention over 77 tokens: more, smaller CTAs hide the per-CTA latency chain).
+static int attention_groups(int d, int Nk) { return (d <= 64 && Nk > 256) ? LDX_ATT_NG_SMALL : 1; }
 
 static int attention_prepare(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                              void* o, int64_t ldo, int B, int Nq, int Nk, int heads, int d, AttnLaunch* L) {
@@ -461,36 +462,31 @@ static int attention_prepare(const void* q, int64_t ldq, const void* k, int64_t 
   L->p.ldo = ldo;
   L->p.B = B; L->p.Nq = Nq; L->p.Nk = Nk; L->p.heads = heads;
   L->p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
-  switch (d) {
-    case 40: L->grid = attention_grid<40>(B, Nq, heads); break;
-    case 64: L->grid = attention_grid<64>(B, Nq, heads); break;
-    case 80: L->grid = attention_grid<80>(B, Nq, heads); break;
-    case 128: L->grid = attention_grid<128>(B, Nq, heads); break;
-    default: L->grid = attention_grid<160>(B, Nq, heads); break;
-  }
   L->d = d;
+  L->ng = attention_groups(d, Nk);
+  L->grid = dim3((Nq + L->ng * BQ - 1) / (L->ng * BQ), heads, B);
   return LDX_OK;
 }
 
-template <int D>
+template <int D, int NG_>
 static int attention_launch_t(const AttnLaunch* L, cudaStream_t st) {
+  using C = AttnCfg<D, NG_>;
   static bool attr = false;
   if (!attr) {
-    LDX_CUDA(cudaFuncSetAttribute(ldx_attention_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  AttnCfg<D>::SMEM));
+    LDX_CUDA(cudaFuncSetAttribute(ldx_attention_kernel<D, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     attr = true;
   }
-  LDX_CUDA(launch_k(ldx_attention_kernel<D>, L->grid, dim3(AttnCfg<D>::THREADS), (size_t)AttnCfg<D>::SMEM, st, 1, L->p));
+  LDX_CUDA(launch_k(ldx_attention_kernel<D, NG_>, L->grid, dim3(C::THREADS), (size_t)C::SMEM, st, 1, L->p));
   return LDX_OK;
 }
 
 static int attention_launch(const AttnLaunch* L, cudaStream_t st) {
   switch (L->d) {
-    case 40: return attention_launch_t<40>(L, st);
-    case 64: return attention_launch_t<64>(L, st);
-    case 80: return attention_launch_t<80>(L, st);
-    case 128: return attention_launch_t<128>(L, st);
-    case 160: return attention_launch_t<160>(L, st);
+    case 40: return L->ng == 1 ? attention_launch_t<40, 1>(L, st) : attention_launch_t<40, LDX_ATT_NG_SMALL>(L, st);
+    case 64: return L->ng == 1 ? attention_launch_t<64, 1>(L, st) : attention_launch_t<64, LDX_ATT_NG_SMALL>(L, st);
+    case 80: return attention_launch_t<80, 1>(L, st);
+    case 128: return attention_launch_t<128, 1>(L, st);
+    case 160: return attention_launch_t<160, 1>(L, st);
   }
   set_error("attention: head dim %d unsupported", L->d);
   return LDX_E_INVALID;

@@ -68,6 +68,20 @@ struct __align__(8) GemmBarriers {
   uint32_t tmem_base;
 };
 
+// tile index -> (n tile, x / y / batch tile) with multiply-high instead of integer division (exact while
+// index * divisor < 2^32, far beyond any launch here); the divisions cost ~1000 cycles per tile and warp.
+template <int kCtas>
+__device__ __forceinline__ void tile_coords(const GemmKParams& p, int tile, int cta_rank, int& nt, int& tx, int& ty,
+                                            int& tb) {
+  const int mq = p.n_tiles == 1 ? tile : (int)__umulhi((uint32_t)tile, p.inv_n_tiles);
+  nt = tile - mq * p.n_tiles;
+  const int mt = mq * kCtas + cta_rank;
+  tb = p.tiles_x * p.tiles_y == 1 ? mt : (int)__umulhi((uint32_t)mt, p.inv_tiles_xy);
+  const int rem = mt - tb * (p.tiles_x * p.tiles_y);
+  ty = p.tiles_x == 1 ? rem : (int)__umulhi((uint32_t)rem, p.inv_tiles_x);
+  tx = rem - ty * p.tiles_x;
+}
+
 template <bool kGeglu, bool kOutF32>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, uint32_t tmem_row_addr, int col, int n_glob,
                                                bool row_valid, char* out_row, const __half* res_row,
@@ -210,8 +224,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
-        const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * kCtas + (int)cta_rank;
-        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+        int nt, tx, ty, tb;
+        tile_coords<kCtas>(p, tile, (int)cta_rank, nt, tx, ty, tb);
         const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * p.bn + (int)cta_rank * bn_cta;
         int kcol = 0;
         auto load_step = [&](const CUtensorMap* am, int ac0, int ax, int ay, const CUtensorMap* bm, int bk, int bn0) {
@@ -321,8 +335,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
     for (int tile = worker; tile < p.num_tiles; tile += nworkers, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int nt = tile % p.n_tiles, mt = (tile / p.n_tiles) * kCtas + (int)cta_rank;
-      const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+      int nt, tx, ty, tb;
+      tile_coords<kCtas>(p, tile, (int)cta_rank, nt, tx, ty, tb);
       const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
       const int x = x0 + row % p.bw;
       const int y = y0 + (row / p.bw) % p.bh;
@@ -375,14 +389,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               uint32_t g[32];
               tmem_ld32(trow + c + p.bn / 2, g);
               tmem_ld_wait();
-              const int n_packed = nt * p.bn + c;
+              // p.bias is never null here (gemm_prepare substitutes a zero vector): no per-load predicates
+              const float4* bv = reinterpret_cast<const float4*>(p.bias + nt * p.bn + c);
+              const float4* bgp = bv + (p.bn >> 3);
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
-                if (p.bias) {
-                  ba = __ldg(reinterpret_cast<const float4*>(p.bias + n_packed) + j4);
-                  bg = __ldg(reinterpret_cast<const float4*>(p.bias + n_packed + p.bn / 2) + j4);
-                }
+                const float4 ba = __ldg(bv + j4), bg = __ldg(bgp + j4);
                 v[j4 * 4 + 0] = (__uint_as_float(r[j4 * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 0]) + bg.x);
                 v[j4 * 4 + 1] = (__uint_as_float(r[j4 * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 1]) + bg.y);
                 v[j4 * 4 + 2] = (__uint_as_float(r[j4 * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 2]) + bg.z);
@@ -391,7 +403,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
             } else {
               // bias / rowadd values are fetched while the TMEM load is in flight
               float4 bb4[8];
-              const bool bias_vec = p.bias && n_glob + EPI_CHUNK <= p.N;
+              const bool bias_vec = n_glob + EPI_CHUNK <= p.N;      // p.bias is never null on this path
               if (bias_vec) {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) bb4[j4] = __ldg(reinterpret_cast<const float4*>(p.bias + n_glob) + j4);
@@ -405,7 +417,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
                 for (int j4 = 0; j4 < 8; ++j4) {
                   v[j4 * 4 + 0] += bb4[j4].x; v[j4 * 4 + 1] += bb4[j4].y; v[j4 * 4 + 2] += bb4[j4].z; v[j4 * 4 + 3] += bb4[j4].w;
                 }
-              } else if (p.bias) {
+              } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
                   if (n_glob + j < p.N) v[j] += __ldg(p.bias + n_glob + j);
@@ -577,6 +589,21 @@ static const void* identity256() {
   return dev;
 }
 
+// Zero fp32 vector (lazily created): stands in for a missing bias so the TMA-store epilogue needs no null checks.
+static const float* zeros_f32(int n) {
+  static float* dev = nullptr;
+  static int cap = 0;
+  if (n > cap) {
+    const int want = n > 16384 ? n : 16384;
+    float* ptr = nullptr;
+    if (cudaMalloc(&ptr, (size_t)want * sizeof(float)) != cudaSuccess) return nullptr;
+    if (cudaMemset(ptr, 0, (size_t)want * sizeof(float)) != cudaSuccess) return nullptr;
+    dev = ptr;            // an older, smaller vector stays alive for launches that already captured it
+    cap = want;
+  }
+  return dev;
+}
+
 // Tile configuration: N tile width and 1-CTA vs CTA-pair kernel.  Cost model per 16-wide K step and per
 // SM: tensor pipe bn/2 cycles vs operand fetch (L2 -> smem) of (128 + bn/ctas) rows x 32 bytes at an
 // effective ~61 B/clk/SM (calibrated on B200: the 1-CTA 128x256 tile runs at ~0.64 of the MMA rate).
@@ -667,6 +694,12 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.bn = bn;
   p.n_tiles = (d->N + bn - 1) / bn;
   p.num_tiles = ((m_tiles + ctas - 1) / ctas) * p.n_tiles;   // (pair-)tiles
+  auto inv32 = [](int dv) { return dv <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)dv - 1) / (uint64_t)dv); };
+  // divisor 1 has no 32-bit reciprocal: tile_coords() must then see quotient = index, which umulhi(x, 0) = 0
+  // would break, so those cases use the identity below
+  p.inv_n_tiles = inv32(p.n_tiles);
+  p.inv_tiles_x = inv32(p.tiles_x);
+  p.inv_tiles_xy = inv32(p.tiles_x * p.tiles_y);
   p.acc_stride = (uint32_t)pow2_ceil(bn < 32 ? 32 : bn);
   p.tmem_cols = 2 * p.acc_stride;
 
@@ -785,6 +818,10 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     rc = encode_map_f16_sw(&p.omap64, obase, 4, odims, ostr, box64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     p.tma_epi = 1;
+    if (!p.bias) {
+      p.bias = zeros_f32(d->N);
+      LDX_CHECK_ARG(p.bias != nullptr, "zero bias allocation failed");
+    }
   }
   return LDX_OK;
 }

@@ -86,6 +86,7 @@ struct alignas(64) GemmKParams {
   int32_t N, W, H, B;
   int32_t bw, bh, bb;
   int32_t tiles_x, tiles_y, tiles_b, n_tiles, num_tiles;
+  uint32_t inv_n_tiles, inv_tiles_x, inv_tiles_xy;   // ceil(2^32 / d): tile index -> coordinates without integer division
   int32_t bn, stages;
   uint32_t tmem_cols, acc_stride;
   void* out;
