@@ -64,6 +64,10 @@ typedef struct {
 #define LDX_EPI_GEGLU 2     /* out[:, j] = a * gelu_erf(gate)     (GEGLU.forward, LD.py:4513-4515);
                                weight rows must be interleaved by ldx_pack_geglu; out has N/2 columns */
 #define LDX_EPI_OUT_F32 4   /* store fp32 instead of fp16 */
+#define LDX_EPI_ROWNORM 8   /* LayerNorm of the A rows folded into the GEMM (F.layer_norm LD.py:2403 followed by
+                               F.linear LD.py:2368): with w' = w * gamma (caller-folded), gsum[n] = sum_k w'[n,k] and
+                               bias' = bias + w @ beta,  out = rstd_r * (acc - mean_r * gsum[n]) + bias'[n], where
+                               (mean_r, rstd_r) come from the row statistics the producing GEMM left in rowstats_in */
 
 typedef struct {
   ldx_src_t src[LDX_MAX_SRC];
@@ -84,9 +88,21 @@ typedef struct {
   int64_t ldr;
   int32_t flags;            /* LDX_EPI_* */
   int32_t bn;               /* N tile (multiple of 32, <= 256); 0 = choose */
+  float* rowstats_out;      /* NULL, or [rows, ldx_gemm_rowstats_parts(d), 2] fp32: per output row the (sum, sum of
+                               squares) of this GEMM's outputs, one pair per column part (summed by the consumer in a
+                               fixed order: bit-reproducible).  Needs fp16 outputs with TMA-compatible strides. */
+  const float* rowstats_in; /* LDX_EPI_ROWNORM: [rows, rowstats_in_parts, 2] written by the GEMM that produced A */
+  int32_t rowstats_in_parts;
+  float ln_eps;             /* LDX_EPI_ROWNORM: LayerNorm eps */
+  const float* ln_gsum;     /* LDX_EPI_ROWNORM: [N] fp32 (packed like the bias for LDX_EPI_GEGLU) */
+  int32_t ln_c;             /* LDX_EPI_ROWNORM: normalised width C (the A row length before K padding) */
+  int32_t reserved_;
 } ldx_gemm_desc_t;
 
 int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream);
+/* Number of column parts the GEMM described by d writes per row into rowstats_out (depends on the tile
+ * configuration the library picks for d); < 0 on error. */
+int ldx_gemm_rowstats_parts(const ldx_gemm_desc_t* d);
 
 /* One-time weight layout transforms (ldx_pack_weights_* of SURVEY.md §8b). */
 /* torch conv weight [Cout, Cin, 3, 3] fp16 -> [Cout, 9 * ceil64(Cin)] fp16 (tap-major, zero padded). */

@@ -14,6 +14,7 @@ LDX_MAX_SEG = 16
 EPI_SILU = 1
 EPI_GEGLU = 2
 EPI_OUT_F32 = 4
+EPI_ROWNORM = 8
 
 OP_GEMM, OP_GROUP_NORM, OP_LAYER_NORM, OP_ATTENTION = 1, 2, 3, 4
 OP_NCHW_TO_NHWC, OP_TIMESTEP_EMB, OP_UPSAMPLE2X, OP_EPS_TO_DENOISED = 5, 6, 7, 8
@@ -44,7 +45,9 @@ class GemmDesc(C.Structure):
                 ("o_sx", C.c_int64), ("o_sy", C.c_int64), ("o_sb", C.c_int64), ("o_off", C.c_int64),
                 ("bias", C.c_void_p), ("rowadd", C.c_void_p), ("ld_rowadd", C.c_int64),
                 ("residual", C.c_void_p), ("ldr", C.c_int64),
-                ("flags", C.c_int32), ("bn", C.c_int32)]
+                ("flags", C.c_int32), ("bn", C.c_int32),
+                ("rowstats_out", C.c_void_p), ("rowstats_in", C.c_void_p), ("rowstats_in_parts", C.c_int32),
+                ("ln_eps", C.c_float), ("ln_gsum", C.c_void_p), ("ln_c", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class GenericOp(C.Structure):
@@ -60,6 +63,7 @@ _SIGS = {
     "ldx_last_error_string": (C.c_char_p, []),
     "ldx_device_check": (C.c_int, []),
     "ldx_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
+    "ldx_gemm_rowstats_parts": (C.c_int, [C.POINTER(GemmDesc)]),
     "ldx_pack_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldx_pack_upconv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldx_pack_geglu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -166,7 +166,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, uint32_t tm
 // kCtas = 1: one CTA per 128 x bn tile.  kCtas = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) per
 // 256 x bn tile: each CTA loads its own 128 A rows and HALF of the B tile, so the L2->smem operand
 // traffic per FLOP drops by a third and the MMA reads B from both CTAs' shared memory.
-template <int kCtas>
+// kEpi: epilogue features compiled in (bit 0 GEGLU, bit 1 LayerNorm-folded input rows, bit 2 row statistics
+// out).  They are template parameters because the epilogue is register-bound: a single kernel carrying every
+// path spilled inside the hot loop and slowed the plain GEMMs too.
+constexpr int KEPI_GEGLU = 1, KEPI_ROWNORM = 2, KEPI_ROWSTATS = 4;
+template <int kCtas, int kEpi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -314,7 +318,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
     const int grp = (warp - 2) >> 2;
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
-    const bool geglu = (p.flags & LDX_EPI_GEGLU) != 0;
+    constexpr bool geglu = (kEpi & KEPI_GEGLU) != 0;
+    constexpr bool rownorm = (kEpi & KEPI_ROWNORM) != 0;
+    constexpr bool rowstats = (kEpi & KEPI_ROWSTATS) != 0;
     const bool f32 = (p.flags & LDX_EPI_OUT_F32) != 0;
     const int n_out_tile = geglu ? p.bn / 2 : p.bn;
     const int n_out_total = geglu ? p.N / 2 : p.N;
@@ -361,12 +367,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
         continue;
       }
       if (p.tma_epi) {
+        const int64_t m_lin = ((int64_t)b * p.H + y) * p.W + x;      // output row index
+        const int rs_parts = p.n_tiles * EPI_GROUPS;
         if (grp >= npass) {                     // nothing to do for this group in a narrow tile
           tc_fence_before();
           __syncwarp();
           if (lane == 0) release_tmem(as);
+          if (rowstats && valid)
+            *reinterpret_cast<float2*>(p.rowstats_out + (m_lin * rs_parts + nt * EPI_GROUPS + grp) * 2) = make_float2(0.f, 0.f);
           continue;
         }
+        // LayerNorm folded into this GEMM: statistics of the A row (= output row of a plain GEMM)
+        float ln_mean = 0.f, ln_rstd = 1.f;
+        if (rownorm && valid) {
+          float s1 = 0.f, s2 = 0.f;
+          const float2* st = reinterpret_cast<const float2*>(p.rowstats_in) + m_lin * p.rs_in_parts;
+          for (int i = 0; i < p.rs_in_parts; ++i) {     // fixed order: bit-reproducible
+            const float2 t2 = __ldg(st + i);
+            s1 += t2.x;
+            s2 += t2.y;
+          }
+          ln_mean = s1 * p.ln_inv_c;
+          ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
+        }
+        float rs1 = 0.f, rs2 = 0.f;             // row statistics of this warp's output columns
         int last_ps = grp;                      // this group's last pass of the tile
         while (last_ps + EPI_GROUPS < npass) last_ps += EPI_GROUPS;
         for (int ps = grp; ps < npass; ps += EPI_GROUPS, ++pidx) {
@@ -393,6 +417,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               const float4* bv = reinterpret_cast<const float4*>(p.bias + nt * p.bn + c);
               const float4* bgp = bv + (p.bn >> 3);
 #pragma unroll
+              if (rownorm) {                   // acc -> rstd * (acc - mean * gsum[n]); the bias is already bias'
+                const float4* gv = reinterpret_cast<const float4*>(p.ln_gsum + nt * p.bn + c);
+                const float4* ggp = gv + (p.bn >> 3);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 ga = __ldg(gv + j4), gg = __ldg(ggp + j4);
+                  r[j4 * 4 + 0] = __float_as_uint((__uint_as_float(r[j4 * 4 + 0]) - ln_mean * ga.x) * ln_rstd);
+                  r[j4 * 4 + 1] = __float_as_uint((__uint_as_float(r[j4 * 4 + 1]) - ln_mean * ga.y) * ln_rstd);
+                  r[j4 * 4 + 2] = __float_as_uint((__uint_as_float(r[j4 * 4 + 2]) - ln_mean * ga.z) * ln_rstd);
+                  r[j4 * 4 + 3] = __float_as_uint((__uint_as_float(r[j4 * 4 + 3]) - ln_mean * ga.w) * ln_rstd);
+                  g[j4 * 4 + 0] = __float_as_uint((__uint_as_float(g[j4 * 4 + 0]) - ln_mean * gg.x) * ln_rstd);
+                  g[j4 * 4 + 1] = __float_as_uint((__uint_as_float(g[j4 * 4 + 1]) - ln_mean * gg.y) * ln_rstd);
+                  g[j4 * 4 + 2] = __float_as_uint((__uint_as_float(g[j4 * 4 + 2]) - ln_mean * gg.z) * ln_rstd);
+                  g[j4 * 4 + 3] = __float_as_uint((__uint_as_float(g[j4 * 4 + 3]) - ln_mean * gg.w) * ln_rstd);
+                }
+              }
+#pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 ba = __ldg(bv + j4), bg = __ldg(bgp + j4);
                 v[j4 * 4 + 0] = (__uint_as_float(r[j4 * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 0]) + bg.x);
@@ -412,6 +453,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               PH(3)
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+              if (rownorm) {                   // N % 32 == 0 is checked on the host
+                const float4* gv = reinterpret_cast<const float4*>(p.ln_gsum + n_glob);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  const float4 ga = __ldg(gv + j4);
+                  v[j4 * 4 + 0] = (v[j4 * 4 + 0] - ln_mean * ga.x) * ln_rstd;
+                  v[j4 * 4 + 1] = (v[j4 * 4 + 1] - ln_mean * ga.y) * ln_rstd;
+                  v[j4 * 4 + 2] = (v[j4 * 4 + 2] - ln_mean * ga.z) * ln_rstd;
+                  v[j4 * 4 + 3] = (v[j4 * 4 + 3] - ln_mean * ga.w) * ln_rstd;
+                }
+              }
               if (bias_vec) {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -438,6 +490,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
             }
+            if (rowstats) {                    // row statistics for a LayerNorm folded into the consumer GEMM
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n_glob + j < n_out_total) { rs1 += v[j]; rs2 = fmaf(v[j], v[j], rs2); }
+            }
             // wide: SWIZZLE_128B rows of 128 B, 16-byte chunk index XOR (row & 7);
             // tail: SWIZZLE_64B rows of 64 B, chunk index XOR ((row >> 1) & 3)
             uint8_t* srow = wide ? cbuf + lane * 128 : cbuf + lane * 64;
@@ -462,6 +519,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
           }
           PH(1)
         }
+        if (rowstats && valid)
+          *reinterpret_cast<float2*>(p.rowstats_out + (m_lin * rs_parts + nt * EPI_GROUPS + grp) * 2) = make_float2(rs1, rs2);
         continue;
       }
 
@@ -818,28 +877,60 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     rc = encode_map_f16_sw(&p.omap64, obase, 4, odims, ostr, box64, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     p.tma_epi = 1;
+    p.rowstats_out = d->rowstats_out;
+    if (d->flags & LDX_EPI_ROWNORM) {
+      LDX_CHECK_ARG(d->rowstats_in && d->ln_gsum && d->rowstats_in_parts >= 1 && d->rowstats_in_parts <= 256 &&
+                        d->ln_c >= 1,
+                    "LDX_EPI_ROWNORM needs rowstats_in / ln_gsum / parts / ln_c");
+      LDX_CHECK_ARG(d->H == 1 && d->B == 1 && !d->rowadd && (reinterpret_cast<uintptr_t>(d->ln_gsum) % 16 == 0) &&
+                        d->N % 32 == 0,
+                    "LDX_EPI_ROWNORM: plain [M, K] x [N, K] GEMMs only");
+      p.rowstats_in = d->rowstats_in;
+      p.rs_in_parts = d->rowstats_in_parts;
+      p.ln_gsum = d->ln_gsum;
+      p.ln_eps = d->ln_eps;
+      p.ln_inv_c = 1.0f / (float)d->ln_c;
+    }
     if (!p.bias) {
       p.bias = zeros_f32(d->N);
       LDX_CHECK_ARG(p.bias != nullptr, "zero bias allocation failed");
     }
   }
+  LDX_CHECK_ARG(p.tma_epi || (!d->rowstats_out && !(d->flags & LDX_EPI_ROWNORM)),
+                "rowstats_out / LDX_EPI_ROWNORM need the TMA-store epilogue (fp16 output, 16-byte aligned strides)");
   return LDX_OK;
 }
 
-int gemm_launch(const GemmLaunch* g, cudaStream_t stream) {
+template <int kCtas, int kEpi>
+static int gemm_launch_t(const GemmLaunch* g, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    LDX_CUDA(cudaFuncSetAttribute(ldx_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    LDX_CUDA(cudaFuncSetAttribute(ldx_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    LDX_CUDA(cudaFuncSetAttribute(ldx_gemm_kernel<kCtas, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  if (g->ctas == 2) {
-    LDX_CUDA(launch_k(ldx_gemm_kernel<2>, dim3(g->grid), dim3(GEMM_THREADS), (size_t)g->smem_bytes, stream, 2, g->p));
-  } else {
-    LDX_CUDA(launch_k(ldx_gemm_kernel<1>, dim3(g->grid), dim3(GEMM_THREADS), (size_t)g->smem_bytes, stream, 1, g->p));
-  }
-  LDX_CUDA(cudaGetLastError());
+  LDX_CUDA(launch_k(ldx_gemm_kernel<kCtas, kEpi>, dim3(g->grid), dim3(GEMM_THREADS), (size_t)g->smem_bytes, stream, kCtas,
+                    g->p));
   return LDX_OK;
+}
+
+template <int kCtas>
+static int gemm_launch_c(const GemmLaunch* g, cudaStream_t stream) {
+  const int epi = ((g->p.flags & LDX_EPI_GEGLU) ? KEPI_GEGLU : 0) | ((g->p.flags & LDX_EPI_ROWNORM) ? KEPI_ROWNORM : 0) |
+                  (g->p.rowstats_out ? KEPI_ROWSTATS : 0);
+  switch (epi) {
+    case 0: return gemm_launch_t<kCtas, 0>(g, stream);
+    case KEPI_GEGLU: return gemm_launch_t<kCtas, KEPI_GEGLU>(g, stream);
+    case KEPI_ROWNORM: return gemm_launch_t<kCtas, KEPI_ROWNORM>(g, stream);
+    case KEPI_ROWSTATS: return gemm_launch_t<kCtas, KEPI_ROWSTATS>(g, stream);
+    case KEPI_GEGLU | KEPI_ROWNORM: return gemm_launch_t<kCtas, KEPI_GEGLU | KEPI_ROWNORM>(g, stream);
+    case KEPI_ROWNORM | KEPI_ROWSTATS: return gemm_launch_t<kCtas, KEPI_ROWNORM | KEPI_ROWSTATS>(g, stream);
+  }
+  set_error("unsupported epilogue combination %d (GEGLU cannot write row statistics)", epi);
+  return LDX_E_INVALID;
+}
+
+int gemm_launch(const GemmLaunch* g, cudaStream_t stream) {
+  return g->ctas == 2 ? gemm_launch_c<2>(g, stream) : gemm_launch_c<1>(g, stream);
 }
 
 // ================================================================================ weight packing kernels
@@ -899,6 +990,16 @@ extern "C" int ldx_debug_gemm_ts(unsigned long long* out) {
   return cudaMemcpyFromSymbol(out, g_gemm_ts, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 1;
 }
 #endif
+
+extern "C" int ldx_gemm_rowstats_parts(const ldx_gemm_desc_t* d) {
+  GemmLaunch g;
+  if (gemm_prepare(d, &g) != LDX_OK) return -1;
+  if (!g.p.tma_epi) {
+    set_error("rowstats_out needs the TMA-store epilogue (fp16 output, 16-byte aligned strides)");
+    return -1;
+  }
+  return g.p.n_tiles * EPI_GROUPS;
+}
 
 extern "C" int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream) {
   GemmLaunch g;

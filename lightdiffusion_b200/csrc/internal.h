@@ -97,6 +97,11 @@ struct alignas(64) GemmKParams {
   const void* res;
   int64_t ldr;
   int32_t flags;
+  float* rowstats_out;        // [rows][n_tiles * 2][2]
+  const float* rowstats_in;   // [rows][rs_in_parts][2]
+  const float* ln_gsum;
+  int32_t rs_in_parts;
+  float ln_eps, ln_inv_c;
   int32_t vec_ok;   // 16-byte vector epilogue allowed (direct-store path)
   int32_t tma_epi;  // 1: stage 32-column chunks in smem and TMA-store them (fp16 outputs)
 };

@@ -12,6 +12,8 @@ from __future__ import annotations
 import math
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -30,6 +32,11 @@ def sigma_tables():
     sig = ((1 - acp) / acp) ** 0.5
     return sig.float(), sig.log().float()
 
+
+# norm3 feeds the GEGLU projection, whose epilogue (erf-GELU on every gate) is already the longest in the
+# UNet; folding the LayerNorm in as well is a small net win (17.27 -> 17.19 ms per UNet step on B200).
+# LDX_FUSE_LN3=0 keeps the separate LayerNorm kernel (A/B measurements).
+FUSE_LN3 = os.environ.get("LDX_FUSE_LN3", "1") == "1"
 
 class _Pool:
     """Size-keyed free list so that dead activations are reused (keeps the working set L2-friendly)."""
@@ -141,15 +148,23 @@ class UNetEngine:
         w[p + ".gn.g"], w[p + ".gn.b"] = _f32(sd, p + ".norm.weight", dev), _f32(sd, p + ".norm.bias", dev)
         w[p + ".pin.w"], w[p + ".pin.b"] = K.pack_linear(sd[p + ".proj_in.weight"]), _f32(sd, p + ".proj_in.bias", dev)
         w[p + ".pout.w"], w[p + ".pout.b"] = K.pack_linear(sd[p + ".proj_out.weight"]), _f32(sd, p + ".proj_out.bias", dev)
-        for n in ("norm1", "norm2", "norm3"):
-            w[f"{p}.{n}.g"], w[f"{p}.{n}.b"] = _f32(sd, f"{t}.{n}.weight", dev), _f32(sd, f"{t}.{n}.bias", dev)
-        w[p + ".qkv.w"] = K.pack_linear(torch.cat([sd[t + ".attn1.to_q.weight"], sd[t + ".attn1.to_k.weight"],
-                                                   sd[t + ".attn1.to_v.weight"]], 0))
+        # The three LayerNorms of BasicTransformerBlock (LD.py:4117-4162) are folded into the GEMMs that consume
+        # them (LDX_EPI_ROWNORM): w' = w * gamma, gsum = rowsum(w'), bias' = bias + w @ beta.
+        ln = lambda n: (sd[f"{t}.{n}.weight"].to(F16).float(), sd[f"{t}.{n}.bias"].to(F16).float())
+        wqkv = torch.cat([sd[t + ".attn1.to_q.weight"], sd[t + ".attn1.to_k.weight"], sd[t + ".attn1.to_v.weight"]], 0)
+        w[p + ".qkv.w"], w[p + ".qkv.g"], w[p + ".qkv.b"] = K.fold_layer_norm(wqkv, None, *ln("norm1"))
         w[p + ".o1.w"], w[p + ".o1.b"] = K.pack_linear(sd[t + ".attn1.to_out.0.weight"]), _f32(sd, t + ".attn1.to_out.0.bias", dev)
-        w[p + ".q2.w"] = K.pack_linear(sd[t + ".attn2.to_q.weight"])
+        w[p + ".q2.w"], w[p + ".q2.g"], w[p + ".q2.b"] = K.fold_layer_norm(sd[t + ".attn2.to_q.weight"], None, *ln("norm2"))
         w[p + ".o2.w"], w[p + ".o2.b"] = K.pack_linear(sd[t + ".attn2.to_out.0.weight"]), _f32(sd, t + ".attn2.to_out.0.bias", dev)
-        w[p + ".ff1.w"], w[p + ".ff1.b"] = K.pack_geglu(sd[t + ".ff.net.0.proj.weight"],
-                                                       sd[t + ".ff.net.0.proj.bias"].to(F16).float(), 128)
+        if FUSE_LN3:
+            wf, gf, bf = K.fold_layer_norm(sd[t + ".ff.net.0.proj.weight"], sd[t + ".ff.net.0.proj.bias"].to(F16).float(),
+                                           *ln("norm3"))
+            w[p + ".ff1.w"], w[p + ".ff1.b"] = K.pack_geglu(wf, bf, 128)
+            _, w[p + ".ff1.g"] = K.pack_geglu(wf, gf, 128)
+        else:
+            w[p + ".norm3.g"], w[p + ".norm3.b"] = _f32(sd, t + ".norm3.weight", dev), _f32(sd, t + ".norm3.bias", dev)
+            w[p + ".ff1.w"], w[p + ".ff1.b"] = K.pack_geglu(sd[t + ".ff.net.0.proj.weight"],
+                                                           sd[t + ".ff.net.0.proj.bias"].to(F16).float(), 128)
         w[p + ".ff2.w"], w[p + ".ff2.b"] = K.pack_linear(sd[t + ".ff.net.2.weight"]), _f32(sd, t + ".ff.net.2.bias", dev)
 
     # ---- plans
@@ -198,6 +213,7 @@ class UNetPlan:
         self.den = torch.zeros(nb, cfg.out_channels, H, W, dtype=F32, device=dev)
         self.cfg_scale = torch.tensor([1.0])    # host copy; the CFG op is re-recorded when it changes
         self.stats = torch.empty(B * L.GN_STATS_FLOATS_PER_BATCH, dtype=F32, device=dev)
+        self._rs_cache = {}
         self.kv_all = torch.empty(B * 77, eng.kv_total, dtype=F16, device=dev)
         self.ctx_prog = K.Program()
         self.ctx_prog.add(K.linear_desc(self.ctx.view(B * 77, -1), eng.w["kv_all.w"], self.kv_all))
@@ -246,43 +262,62 @@ class UNetPlan:
         self.pool.free(y2)
         return out
 
+    def _rowstats(self, d, rows: int, slot: int):
+        """[rows, parts, 2] fp32 buffer (cached per shape, two alternating slots) that GEMM `d` fills with the
+        per-row (sum, sum of squares) of its outputs for the LayerNorm folded into the next GEMM."""
+        parts = K.rowstats_parts(d)
+        key = (rows, parts, slot)
+        if key not in self._rs_cache:
+            self._rs_cache[key] = torch.empty(rows, parts, 2, dtype=F32, device=self.eng.dev)
+        st = self._rs_cache[key]
+        d.rowstats_out = st.data_ptr()
+        return st
+
     def _attn(self, s: AttnSpec, x):
         eng, w, p, pool = self.eng, self.eng.w, s.name, self.pool
         Bn, h, wd, c = x.shape
         n, m = h * wd, Bn * h * wd
         y = self._gn(x, None, w[p + ".gn.g"], w[p + ".gn.b"], 1e-6, False)
         t = pool.alloc(m, c)
-        self.prog.add(K.linear_desc(y, w[p + ".pin.w"], t, bias=w[p + ".pin.b"]))
+        d = K.linear_desc(y, w[p + ".pin.w"], t, bias=w[p + ".pin.b"])
+        st1 = self._rowstats(d, m, 0)          # row statistics of t for norm1, folded into the QKV GEMM
+        self.prog.add(d)
         pool.free(y)
         # attn1 (self)
-        nrm = pool.alloc(m, c)
-        self.prog.add(K.layer_norm_op(t, w[p + ".norm1.g"], w[p + ".norm1.b"], nrm))
         qkv = pool.alloc(m, 3 * c)
-        self.prog.add(K.linear_desc(nrm, w[p + ".qkv.w"], qkv))
+        self.prog.add(K.linear_desc(t, w[p + ".qkv.w"], qkv, bias=w[p + ".qkv.b"], rownorm=(st1, w[p + ".qkv.g"], 1e-5, c)))
         a = pool.alloc(m, c)
         q3 = qkv.view(Bn, n, 3 * c)
         self.prog.add(K.attention_op(q3[:, :, :c], q3[:, :, c:2 * c], q3[:, :, 2 * c:], a.view(Bn, n, c), s.heads))
         pool.free(qkv)
         t2 = pool.alloc(m, c)
-        self.prog.add(K.linear_desc(a, w[p + ".o1.w"], t2, bias=w[p + ".o1.b"], residual=t))
+        d = K.linear_desc(a, w[p + ".o1.w"], t2, bias=w[p + ".o1.b"], residual=t)
+        st2 = self._rowstats(d, m, 1)          # norm2 -> attn2.to_q
+        self.prog.add(d)
         pool.free(t)
         # attn2 (cross; K/V of the step-invariant context come from the kv_all GEMM)
-        self.prog.add(K.layer_norm_op(t2, w[p + ".norm2.g"], w[p + ".norm2.b"], nrm))
         q2 = a
-        self.prog.add(K.linear_desc(nrm, w[p + ".q2.w"], q2))
+        self.prog.add(K.linear_desc(t2, w[p + ".q2.w"], q2, bias=w[p + ".q2.b"], rownorm=(st2, w[p + ".q2.g"], 1e-5, c)))
         kvo = eng.kv_off[p]
         kv3 = self.kv_all.view(Bn, 77, eng.kv_total)
         a2 = pool.alloc(m, c)
         self.prog.add(K.attention_op(q2.view(Bn, n, c), kv3[:, :, kvo:kvo + c], kv3[:, :, kvo + c:kvo + 2 * c],
                                      a2.view(Bn, n, c), s.heads))
         t3 = pool.alloc(m, c)
-        self.prog.add(K.linear_desc(a2, w[p + ".o2.w"], t3, bias=w[p + ".o2.b"], residual=t2))
+        d = K.linear_desc(a2, w[p + ".o2.w"], t3, bias=w[p + ".o2.b"], residual=t2)
+        st3 = self._rowstats(d, m, 0) if FUSE_LN3 else None     # norm3 -> GEGLU projection
+        self.prog.add(d)
         pool.free(a2); pool.free(t2); pool.free(q2)
-        # feed-forward (GEGLU gate fused in the first GEMM's epilogue)
-        self.prog.add(K.layer_norm_op(t3, w[p + ".norm3.g"], w[p + ".norm3.b"], nrm))
+        # feed-forward (the GEGLU gate lives in the first GEMM's epilogue)
         g = pool.alloc(m, 4 * c)
-        self.prog.add(K.linear_desc(nrm, w[p + ".ff1.w"], g, bias=w[p + ".ff1.b"], flags=L.EPI_GEGLU, bn=256))
-        pool.free(nrm)
+        if FUSE_LN3:
+            self.prog.add(K.linear_desc(t3, w[p + ".ff1.w"], g, bias=w[p + ".ff1.b"], flags=L.EPI_GEGLU, bn=256,
+                                        rownorm=(st3, w[p + ".ff1.g"], 1e-5, c)))
+        else:
+            nrm = pool.alloc(m, c)
+            self.prog.add(K.layer_norm_op(t3, w[p + ".norm3.g"], w[p + ".norm3.b"], nrm))
+            self.prog.add(K.linear_desc(nrm, w[p + ".ff1.w"], g, bias=w[p + ".ff1.b"], flags=L.EPI_GEGLU, bn=256))
+            pool.free(nrm)
         t4 = pool.alloc(m, c)
         self.prog.add(K.linear_desc(g, w[p + ".ff2.w"], t4, bias=w[p + ".ff2.b"], residual=t3))
         pool.free(g); pool.free(t3)

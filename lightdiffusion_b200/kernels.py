@@ -63,8 +63,11 @@ def _fill_out(d: L.GemmDesc, out: torch.Tensor, n_out: int):
 
 def gemm_desc(srcs: Sequence[torch.Tensor], segs: Sequence[tuple], w: torch.Tensor, out: torch.Tensor, n: int,
               bias: Optional[torch.Tensor] = None, rowadd: Optional[torch.Tensor] = None,
-              residual: Optional[torch.Tensor] = None, flags: int = 0, bn: int = 0) -> L.GemmDesc:
-    """segs: (src_index, c0, dx, dy, nchunks).  w: fp16 [N, K] (K = 64 * total chunks, row stride free)."""
+              residual: Optional[torch.Tensor] = None, flags: int = 0, bn: int = 0,
+              rownorm: Optional[tuple] = None) -> L.GemmDesc:
+    """segs: (src_index, c0, dx, dy, nchunks).  w: fp16 [N, K] (K = 64 * total chunks, row stride free).
+    rownorm = (stats [M, parts, 2] fp32, gsum [N] fp32, eps, C): LayerNorm of the A rows folded into the GEMM
+    (w, bias must already be the folded w * gamma and bias + w @ beta, see fold_layer_norm)."""
     d = L.GemmDesc()
     d.nsrc = len(srcs)
     for i, t in enumerate(srcs):
@@ -93,8 +96,43 @@ def gemm_desc(srcs: Sequence[torch.Tensor], segs: Sequence[tuple], w: torch.Tens
         else:
             d.ldr = r2.stride(0)
         d.residual = residual.data_ptr()
+    if rownorm is not None:
+        stats, gsum, eps, c = rownorm
+        assert stats.dtype == torch.float32 and stats.is_contiguous() and stats.dim() == 3 and stats.shape[2] == 2
+        assert gsum.dtype == torch.float32 and gsum.is_contiguous() and gsum.numel() == n
+        d.rowstats_in, d.rowstats_in_parts = stats.data_ptr(), stats.shape[1]
+        d.ln_gsum, d.ln_eps, d.ln_c = gsum.data_ptr(), float(eps), int(c)
+        flags |= L.EPI_ROWNORM
     d.flags, d.bn = flags, bn
     return d
+
+
+def rowstats_parts(d: L.GemmDesc) -> int:
+    """Column parts per row that GEMM `d` will write into its rowstats_out buffer."""
+    n = L.lib().ldx_gemm_rowstats_parts(C.byref(d))
+    if n < 0:
+        raise L.LdxError("ldx_gemm_rowstats_parts: " + L.lib().ldx_last_error_string().decode())
+    return n
+
+
+def attach_rowstats(d: L.GemmDesc, rows: int) -> torch.Tensor:
+    """Allocates [rows, parts, 2] fp32 and makes GEMM `d` write its per-row output statistics there."""
+    stats = torch.empty(rows, rowstats_parts(d), 2, dtype=torch.float32, device="cuda")
+    d.rowstats_out = stats.data_ptr()
+    return stats
+
+
+def fold_layer_norm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm(gamma, beta) followed by Linear(w, bias)  ->  (w' fp16 [N, K], gsum fp32 [N], bias' fp32 [N]) for
+    LDX_EPI_ROWNORM: w' = w * gamma, gsum = rowsum(w'), bias' = bias + w @ beta (F.layer_norm LD.py:2403 + F.linear)."""
+    w32 = w.to(device="cuda", dtype=torch.float16).float()
+    g32, b32 = gamma.to(device="cuda", dtype=torch.float32), beta.to(device="cuda", dtype=torch.float32)
+    wf = (w32 * g32[None, :]).to(torch.float16)
+    gsum = wf.float().sum(1).contiguous()
+    bf = w32 @ b32
+    if bias is not None:
+        bf = bf + bias.to(device="cuda", dtype=torch.float32)
+    return wf.contiguous(), gsum, bf.contiguous()
 
 
 # ----------------------------------------------------------------------------- descriptor builders

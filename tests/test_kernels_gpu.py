@@ -96,6 +96,39 @@ def test_geglu(M, Kd, Fd, half_bn):
     assert rel(out, ref) < 1e-3
 
 
+@pytest.mark.parametrize("M,C,N,geglu", [(1024, 320, 960, False), (4096 + 77, 640, 640, False), (512, 1280, 1280, False),
+                                         (2048, 320, 2560, True), (300, 640, 5120, True)])
+def test_layer_norm_folded_into_gemm(M, C, N, geglu):
+    """x = a @ w0^T + b0 + r (producer, leaves per-row statistics) ; out = Linear(LayerNorm(x)) with the
+    normalisation folded into the consumer GEMM (LD.py:4117-4162: x += attn(norm(x)), ff(norm3(x)))."""
+    K0 = 320
+    a, w0, b0 = h16(rnd(M, K0, seed=30)), h16(rnd(C, K0, seed=31, scale=K0 ** -0.5)), rnd(C, seed=32)
+    r = h16(rnd(M, C, seed=33) + 0.7)                 # non-zero row mean
+    x = torch.empty(M, C, dtype=torch.float16, device=DEV)
+    d0 = K.linear_desc(a, w0, x, bias=b0, residual=r)
+    stats = K.attach_rowstats(d0, M)
+    K.run_gemm(d0)
+    xs = x.float()
+    assert rel(stats[:, :, 0].sum(1), xs.sum(1)) < 2e-3
+    assert rel(stats[:, :, 1].sum(1), (xs * xs).sum(1)) < 2e-3
+
+    gamma, beta = 1.0 + 0.2 * rnd(C, seed=34), 0.3 * rnd(C, seed=35)
+    w, bias = h16(rnd(N, C, seed=36, scale=C ** -0.5)), rnd(N, seed=37, scale=0.3)
+    wf, gsum, bf = K.fold_layer_norm(w, bias, gamma, beta)
+    y = F.layer_norm(xs, (C,), gamma, beta, 1e-5) @ w.float().t() + bias
+    if geglu:
+        wp, bp = K.pack_geglu(wf, bf, 128)
+        _, gp = K.pack_geglu(wf, gsum, 128)
+        out = torch.empty(M, N // 2, dtype=torch.float16, device=DEV)
+        K.run_gemm(K.linear_desc(x, wp, out, bias=bp, flags=L.EPI_GEGLU, bn=256, rownorm=(stats, gp, 1e-5, C)))
+        ref = y[:, :N // 2] * F.gelu(y[:, N // 2:])
+    else:
+        out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+        K.run_gemm(K.linear_desc(x, wf, out, bias=bf, rownorm=(stats, gsum, 1e-5, C)))
+        ref = y
+    assert rel(out, ref) < 1.5e-3, rel(out, ref)
+
+
 def test_rowadd_timestep_broadcast():
     B, H, W, Cin, Cout = 3, 16, 16, 64, 96
     x = h16(rnd(B, H, W, Cin, seed=15))
