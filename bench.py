@@ -272,9 +272,15 @@ def run_ours(args):
     t_total = sum(t_kind.values())
     gemm_ms = t_kind.get("gemm", 0.0)
     achieved = GF_UNET_GEMM_SAMPLE * 1e9 * 2 * b / (gemm_ms * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")     # committed ncu measurement (per launch)
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/r01_gemm_traffic.json: " + tj.get("source", "")
     roofline = {"kernel": "ldx_gemm_kernel (implicit-GEMM conv / linear, tcgen05)", "bound": "tensor",
                 "achieved": achieved, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops_sustained"], "traffic": None,
+                "frac": achieved / peaks["tflops_sustained"], "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peaks["source"] + ", sustained bf16 cuBLAS figure (kernel timed inside a long step)",
                 "launches_per_unet_step": n_kind.get("gemm", 0), "ms_per_unet_step": gemm_ms,
                 "share_of_unet_step": gemm_ms / t_total,

@@ -9,6 +9,9 @@
 namespace ldx {
 
 // ----------------------------------------------------------------------------- GroupNorm
+// (A one-pass variant -- a thread-block cluster per (batch, 4-group channel slice) holding its pixels in shared
+// memory between statistics and normalisation -- was measured slower: a 40-channel slice is an 80-byte piece
+// of every 640-byte pixel row, so each cluster drags partial DRAM bursts that its neighbours re-fetch.)
 // Pass 1 (stats): per (b, slab) partial sums per group.  bytes: read B*HW*C*2.
 // Pass 2 (apply): y = [silu]((x - mean) * rstd * gamma + beta).  bytes: read + write B*HW*C*2.
 // Each thread owns a fixed 8-channel vector, so its per-channel accumulators / affine params stay
