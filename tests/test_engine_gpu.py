@@ -141,6 +141,20 @@ def test_unet_sd15_eps_parity(sd15_unet):
     assert max(errs) < EPS_TOL, errs
 
 
+def test_unet_sd15_eps_parity_hires_128(sd15_unet):
+    """BASELINE.json config 4: the hires-fix second pass runs the UNet on a 128x128 latent
+    (16384-token self-attention at the 320-channel level)."""
+    cfg, sd, eng = sd15_unet
+    x, ctx = _inputs(1, 128, cfg.context_dim, 21)
+    s = 2.0
+    sigma = torch.full((1,), s, device=DEV)
+    xs = x * math.sqrt(1 + s * s)
+    e = eng.eps(xs, sigma, ctx)
+    ref = _oracle_eps(sd, cfg, xs, sigma, ctx)
+    print("SD1.5 128x128 eps rel-L2:", rel(e, ref))
+    assert rel(e, ref) < EPS_TOL
+
+
 def test_unet_sd15_denoised(sd15_unet):
     cfg, sd, eng = sd15_unet
     x, ctx = _inputs(1, 32, cfg.context_dim, 12)
@@ -158,7 +172,8 @@ def vae():
     return sd, VAEDecoderEngine(sd)
 
 
-@pytest.mark.parametrize("b,hw", [(1, 16), (2, 32), (1, 64)])
+# (1, 128) is BASELINE.json config 5: a 1024x1024 decode
+@pytest.mark.parametrize("b,hw", [(1, 16), (2, 32), (1, 64), (1, 128)])
 def test_vae_decode_parity(vae, b, hw):
     sd, eng = vae
     z = torch.randn(b, 4, hw, hw, generator=torch.Generator().manual_seed(5)).to(DEV)
