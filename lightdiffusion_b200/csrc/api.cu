@@ -42,6 +42,7 @@ struct ProgOp {
   void* attn = nullptr;
   ldx_generic_op_t gen;
   int launches = 1;
+  void* ws = nullptr;          // split-K workspace (cudaMalloc)
 };
 
 }  // namespace ldx
@@ -96,6 +97,17 @@ extern "C" int ldx_program_add_gemm(ldx_program_t* prog, const ldx_gemm_desc_t* 
   ProgOp op;
   op.kind = LDX_OP_GEMM;
   op.gemm = g;
+  if (g->nsplit > 1) {                      // split-K: the program owns the fp32 partial-sum workspace
+    void* ws = nullptr;
+    if (cudaMalloc(&ws, g->ws_bytes) != cudaSuccess) {
+      delete g;
+      set_error("split-K workspace allocation of %zu bytes failed", g->ws_bytes);
+      return LDX_E_CUDA;
+    }
+    gemm_bind_workspace(g, ws);
+    op.ws = ws;
+    op.launches = 2;
+  }
   prog->ops.push_back(op);
   return LDX_OK;
 }
@@ -171,6 +183,7 @@ extern "C" void ldx_program_destroy(ldx_program_t* prog) {
   if (!prog) return;
   for (ProgOp& op : prog->ops) {
     delete op.gemm;
+    if (op.ws) cudaFree(op.ws);
     if (op.attn) attention_free_handle(op.attn);
   }
   delete prog;

@@ -229,7 +229,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       uint32_t phase = 0;
       for (int tile = worker; tile < p.num_tiles; tile += nworkers) {
         int nt, tx, ty, tb;
-        tile_coords<kCtas>(p, tile, (int)cta_rank, nt, tx, ty, tb);
+        const int split = p.nsplit > 1 ? tile / p.base_tiles : 0;
+        tile_coords<kCtas>(p, tile - split * p.base_tiles, (int)cta_rank, nt, tx, ty, tb);
+        const int k_lo = split * p.ksplit, k_hi = min(p.nk, k_lo + p.ksplit);   // this tile's K steps
         const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * p.bn + (int)cta_rank * bn_cta;
         int kcol = 0;
         auto load_step = [&](const CUtensorMap* am, int ac0, int ax, int ay, const CUtensorMap* bm, int bk, int bn0) {
@@ -254,12 +256,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
           __syncwarp();
           if (++stage == stages) { stage = 0; phase ^= 1; }
         };
+        int step = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const KSeg sg = p.seg[s];
-          for (int ch = 0; ch < sg.nchunks; ++ch) {
-            load_step(&p.amap[sg.map], sg.c0 + ch * BK, x0 + sg.dx, y0 + sg.dy, &p.bmap, kcol, n0);
-            kcol += BK;
+          if (step + sg.nchunks <= k_lo || step >= k_hi) {       // segment outside this split's K range
+            step += sg.nchunks;
+            kcol += sg.nchunks * BK;
+            continue;
           }
+          for (int ch = 0; ch < sg.nchunks; ++ch, ++step, kcol += BK)
+            if (step >= k_lo && step < k_hi)
+              load_step(&p.amap[sg.map], sg.c0 + ch * BK, x0 + sg.dx, y0 + sg.dy, &p.bmap, kcol, n0);
         }
         // residual fused as an identity K segment (see gemm_prepare): A = the residual tile's own column
         // range, B = the matching rows of I
@@ -281,11 +288,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * p.acc_stride;
-        for (int kb = 0; kb < p.nk; ++kb) {
+        const int split = p.nsplit > 1 ? tile / p.base_tiles : 0;
+        const int nk_tile = p.nsplit > 1 ? min(p.nk, (split + 1) * p.ksplit) - split * p.ksplit : p.nk;
+        for (int kb = 0; kb < nk_tile; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
           if (lane == 0 && it == 0 && kb == 0) TS_MARK(3);
-          if (lane == 0 && it == 0 && kb == p.nk - 1) TS_MARK(4);
+          if (lane == 0 && it == 0 && kb == nk_tile - 1) TS_MARK(4);
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
           if (elect_one()) {
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
             // frees the smem stage (in both CTAs) once these MMAs have read it
             if constexpr (kCtas == 2) umma_commit_pair(&bars->empty[stage], 3); else umma_commit(&bars->empty[stage]);
             // accumulator complete -> epilogue (of both CTAs)
-            if (kb == p.nk - 1) {
+            if (kb == nk_tile - 1) {
               if constexpr (kCtas == 2) umma_commit_pair(&bars->tmem_full[as], 3); else umma_commit(&bars->tmem_full[as]);
             }
           }
@@ -342,7 +351,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       int nt, tx, ty, tb;
-      tile_coords<kCtas>(p, tile, (int)cta_rank, nt, tx, ty, tb);
+      const int split = p.nsplit > 1 ? tile / p.base_tiles : 0;
+      tile_coords<kCtas>(p, tile - split * p.base_tiles, (int)cta_rank, nt, tx, ty, tb);
       const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
       const int x = x0 + row % p.bw;
       const int y = y0 + (row / p.bw) % p.bh;
@@ -525,7 +535,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
       }
 
       // ---- direct path (fp32 outputs / unaligned outputs)
-      const int64_t opix = p.o_off + (int64_t)b * p.o_sb + (int64_t)y * p.o_sy + (int64_t)x * p.o_sx;
+      const int64_t opix = p.o_off + (int64_t)b * p.o_sb + (int64_t)y * p.o_sy + (int64_t)x * p.o_sx +
+                           (int64_t)split * p.split_stride;
       char* out_row = reinterpret_cast<char*>(p.out) + opix * osz;
       const __half* res_row =
           (p.res && valid) ? reinterpret_cast<const __half*>(p.res) + (((int64_t)b * p.H + y) * p.W + x) * p.ldr
@@ -556,6 +567,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
   } else {
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// Second launch of a split-K GEMM: sums the fp32 partials in split order (bit-reproducible) and applies the
+// epilogue the single-launch path fuses (bias, timestep-embedding row add, residual, SiLU) -> fp16.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitReduce r) {
+  pdl_prologue();
+  const int nv = r.N >> 2;                                   // float4 vectors per row (N % 4 == 0)
+  const int64_t total = (int64_t)r.M * nv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / nv), n = (int)(i % nv) * 4;
+    float4 acc = __ldg(reinterpret_cast<const float4*>(r.ws + (int64_t)m * r.N + n));
+    for (int sp = 1; sp < r.nsplit; ++sp) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(r.ws + sp * r.split_stride + (int64_t)m * r.N + n));
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    const int hw = r.W * r.H;
+    const int b = m / hw, y = (m % hw) / r.W, x = m % r.W;
+    if (r.bias) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(r.bias + n));
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    if (r.rowadd) {
+      const float* ra = r.rowadd + (int64_t)b * r.ld_rowadd + n;
+      acc.x += __ldg(ra); acc.y += __ldg(ra + 1); acc.z += __ldg(ra + 2); acc.w += __ldg(ra + 3);
+    }
+    if (r.res) {
+      const uint2 rr = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(r.res) + (int64_t)m * r.ldr + n));
+      const float2 a0 = unpack_h2(rr.x), a1 = unpack_h2(rr.y);
+      acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
+    }
+    if (r.silu) { acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w); }
+    __half* o = reinterpret_cast<__half*>(r.out) + r.o_off + (int64_t)b * r.o_sb + (int64_t)y * r.o_sy + (int64_t)x * r.o_sx + n;
+    *reinterpret_cast<uint2*>(o) = make_uint2(pack_h2(acc.x, acc.y), pack_h2(acc.z, acc.w));
   }
 }
 
@@ -663,6 +708,12 @@ static const float* zeros_f32(int n) {
   return dev;
 }
 
+// fp16 output rows addressable with 8-byte vector stores (split-K reduce kernel)
+static bool tma_ok_out_aligned(const ldx_gemm_desc_t* d) {
+  return ((reinterpret_cast<uintptr_t>(d->out) + (uint64_t)d->o_off * 2) % 8 == 0) && d->o_sx % 4 == 0 &&
+         d->o_sy % 4 == 0 && d->o_sb % 4 == 0 && d->o_sx > 0;
+}
+
 // Tile configuration: N tile width and 1-CTA vs CTA-pair kernel.  Cost model per 16-wide K step and per
 // SM: tensor pipe bn/2 cycles vs operand fetch (L2 -> smem) of (128 + bn/ctas) rows x 32 bytes at an
 // effective ~61 B/clk/SM (calibrated on B200: the 1-CTA 128x256 tile runs at ~0.64 of the MMA rate).
@@ -736,8 +787,36 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   bool fuse_res = d->residual && tma_ok && d->nsrc < LDX_MAX_SRC && (reinterpret_cast<uintptr_t>(d->residual) % 16 == 0) &&
                   (d->ldr * 2) % 16 == 0;
   if (d->residual && !fuse_res) tma_ok = false;                 // direct-store path adds the residual itself
+  // Split-K: a GEMM with few output tiles and a long K (the 8x8-resolution convs: M = 1024) cannot fill the
+  // GPU with output tiles, and narrow tiles re-read A once per N tile.  Use 256-wide pair tiles and give each
+  // of `nsplit` CTA-pair groups a slice of K; fp32 partials go to a workspace and a second launch reduces them
+  // and applies the epilogue.
+  int k_chunks = 0;
+  for (int s = 0; s < d->nseg; ++s) k_chunks += d->seg[s].nchunks;
+  int nsplit = 1;
+  {
+    static int split_env = -1;
+    if (split_env < 0) { const char* e = getenv("LDX_GEMM_SPLITK"); split_env = e ? atoi(e) : 1; }
+    const int pair_tiles = ((m_tiles + 1) / 2) * ((d->N + 255) / 256);
+    const int workers2 = sms / 2;
+    const bool eligible = split_env && d->bn == 0 && osz == 2 && !(d->flags & (LDX_EPI_GEGLU | LDX_EPI_ROWNORM)) &&
+                          !d->rowstats_out && d->N % 8 == 0 && d->N >= 256 && tma_ok_out_aligned(d) &&
+                          (!d->residual || ((reinterpret_cast<uintptr_t>(d->residual) % 8 == 0) && d->ldr % 4 == 0)) &&
+                          (!d->bias || reinterpret_cast<uintptr_t>(d->bias) % 16 == 0);
+    if (eligible && pair_tiles * 2 <= workers2 && k_chunks >= 160) {   // measured: K = 5120 is faster unsplit
+      nsplit = workers2 / pair_tiles;
+      if (nsplit > k_chunks / 16) nsplit = k_chunks / 16;
+      if (nsplit > 8) nsplit = 8;
+      if (nsplit < 2) nsplit = 1;
+    }
+  }
+  if (nsplit > 1) { tma_ok = false; fuse_res = false; }
+  g->nsplit = nsplit;
   int bn = d->bn, ctas = 1;
-  if (bn == 0) {
+  if (nsplit > 1) {
+    bn = 256;
+    ctas = 2;
+  } else if (bn == 0) {
     choose_config(d->N, m_tiles, d->flags, sms, force_ctas, &bn, &ctas);
   } else {
     int bn_unused;
@@ -752,7 +831,9 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   }
   p.bn = bn;
   p.n_tiles = (d->N + bn - 1) / bn;
-  p.num_tiles = ((m_tiles + ctas - 1) / ctas) * p.n_tiles;   // (pair-)tiles
+  p.base_tiles = ((m_tiles + ctas - 1) / ctas) * p.n_tiles;  // (pair-)tiles
+  p.num_tiles = p.base_tiles * nsplit;
+  p.nsplit = nsplit;
   auto inv32 = [](int dv) { return dv <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)dv - 1) / (uint64_t)dv); };
   // divisor 1 has no 32-bit reciprocal: tile_coords() must then see quotient = index, which umulhi(x, 0) = 0
   // would break, so those cases use the identity below
@@ -778,6 +859,11 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.diag_chunks = fuse_res ? (bn + 63) / 64 : 0;
   nk += p.diag_chunks;
   p.nk = nk;
+  p.ksplit = nsplit > 1 ? (nk + nsplit - 1) / nsplit : nk;
+  if (nsplit > 1 && (nsplit - 1) * p.ksplit >= nk) {           // every split needs at least one K step
+    set_error("split-K: %d splits of %d steps do not cover K = %d steps", nsplit, p.ksplit, nk);
+    return LDX_E_INVALID;
+  }
 
   const uint32_t b_stage = (uint32_t)(bn / ctas) * BK * 2;
   int stages = (int)((224 * 1024 - EPI_SMEM - 2048) / (A_STAGE_BYTES + b_stage));
@@ -838,6 +924,20 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.res = fuse_res ? nullptr : d->residual;    // only the direct-store epilogue still sees a residual pointer
   p.ldr = d->ldr;
   p.flags = d->flags;
+  p.split_stride = 0;
+  if (nsplit > 1) {
+    const int64_t rows = (int64_t)d->W * d->H * d->B;
+    p.split_stride = rows * d->N;
+    g->ws_bytes = (size_t)nsplit * (size_t)p.split_stride * sizeof(float);
+    g->red = SplitReduce{nullptr, nsplit, p.split_stride, (int)rows, d->N, d->W, d->H, d->bias, d->rowadd, d->ld_rowadd,
+                         d->residual, d->ldr, (d->flags & LDX_EPI_SILU) ? 1 : 0, d->out, d->o_sx,
+                         d->o_sy > 0 ? d->o_sy : d->o_sx * d->W,
+                         d->o_sb > 0 ? d->o_sb : (d->o_sy > 0 ? d->o_sy : d->o_sx * d->W) * d->H, d->o_off};
+    p.out = nullptr;                        // bound by gemm_bind_workspace()
+    p.o_sx = d->N; p.o_sy = (int64_t)d->N * d->W; p.o_sb = (int64_t)d->N * d->W * d->H; p.o_off = 0;
+    p.bias = nullptr; p.rowadd = nullptr; p.res = nullptr;
+    p.flags = LDX_EPI_OUT_F32;
+  }
   {
     static int verbose = -1;
     if (verbose < 0) { const char* e = getenv("LDX_GEMM_VERBOSE"); verbose = e ? atoi(e) : 0; }
@@ -856,6 +956,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
              ((d->o_sx * osz) % 16 == 0) && ((d->o_sy * osz) % 16 == 0) && ((d->o_sb * osz) % 16 == 0);
   if (d->residual) vec = vec && (reinterpret_cast<uintptr_t>(d->residual) % 16 == 0) && ((d->ldr * 2) % 16 == 0);
   p.vec_ok = vec ? 1 : 0;
+  if (nsplit > 1) p.vec_ok = 1;             // fp32 partial rows: N % 8 == 0, 256-byte aligned workspace
 
   auto fix = [](int64_t s, int64_t fallback) { return (uint64_t)(s > 0 ? s : fallback) * 2; };
   p.tma_epi = 0;
@@ -929,8 +1030,24 @@ static int gemm_launch_c(const GemmLaunch* g, cudaStream_t stream) {
   return LDX_E_INVALID;
 }
 
+void gemm_bind_workspace(GemmLaunch* g, void* ws) {
+  g->p.out = ws;
+  g->red.ws = reinterpret_cast<const float*>(ws);
+}
+
 int gemm_launch(const GemmLaunch* g, cudaStream_t stream) {
-  return g->ctas == 2 ? gemm_launch_c<2>(g, stream) : gemm_launch_c<1>(g, stream);
+  if (g->nsplit > 1 && !g->p.out) {
+    set_error("split-K GEMM launched without a workspace");
+    return LDX_E_INVALID;
+  }
+  int rc = g->ctas == 2 ? gemm_launch_c<2>(g, stream) : gemm_launch_c<1>(g, stream);
+  if (rc || g->nsplit == 1) return rc;
+  const int64_t vecs = (int64_t)g->red.M * (g->red.N >> 2);
+  int blocks = (int)((vecs + 255) / 256);
+  const int cap = num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  LDX_CUDA(launch_k(splitk_reduce_kernel, dim3(blocks), dim3(256), 0, stream, 1, g->red));
+  return LDX_OK;
 }
 
 // ================================================================================ weight packing kernels
@@ -1005,7 +1122,13 @@ extern "C" int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream) {
   GemmLaunch g;
   int rc = gemm_prepare(d, &g);
   if (rc) return rc;
-  return gemm_launch(&g, as_stream(stream));
+  if (g.nsplit == 1) return gemm_launch(&g, as_stream(stream));
+  void* ws = nullptr;                       // one-shot call: stream-ordered workspace
+  LDX_CUDA(cudaMallocAsync(&ws, g.ws_bytes, as_stream(stream)));
+  gemm_bind_workspace(&g, ws);
+  rc = gemm_launch(&g, as_stream(stream));
+  cudaFreeAsync(ws, as_stream(stream));
+  return rc;
 }
 
 extern "C" int ldx_pack_conv3x3(const void* w, void* out, int cout, int cin, ldx_stream_t stream) {

@@ -86,7 +86,11 @@ struct alignas(64) GemmKParams {
   int32_t N, W, H, B;
   int32_t bw, bh, bb;
   int32_t tiles_x, tiles_y, tiles_b, n_tiles, num_tiles;
-  uint32_t inv_n_tiles, inv_tiles_x, inv_tiles_xy;   // ceil(2^32 / d): tile index -> coordinates without integer division
+  uint32_t inv_n_tiles, inv_tiles_x, inv_tiles_xy;
+  // split-K: num_tiles = nsplit * base_tiles, split = tile / base_tiles owns K steps [split * ksplit, ...) and
+  // writes an fp32 partial [rows, N] at out + split * split_stride (elements)
+  int32_t nsplit, base_tiles, ksplit;
+  int64_t split_stride;   // ceil(2^32 / d): tile index -> coordinates without integer division
   int32_t bn, stages;
   uint32_t tmem_cols, acc_stride;
   void* out;
@@ -106,12 +110,32 @@ struct alignas(64) GemmKParams {
   int32_t tma_epi;  // 1: stage 32-column chunks in smem and TMA-store them (fp16 outputs)
 };
 
+// second launch of a split-K GEMM: out = act(sum_s partial[s] + bias + rowadd + residual) as fp16
+struct SplitReduce {
+  const float* ws;
+  int nsplit;
+  int64_t split_stride;
+  int M, N, W, H;
+  const float* bias;
+  const float* rowadd;
+  int64_t ld_rowadd;
+  const void* res;
+  int64_t ldr;
+  int silu;
+  void* out;
+  int64_t o_sx, o_sy, o_sb, o_off;
+};
+
 struct GemmLaunch {
   GemmKParams p;
   int grid;
   int smem_bytes;
   int ctas;      // 1, or 2 = CTA-pair kernel (cluster of 2, tcgen05 cta_group::2)
+  int nsplit = 1;             // > 1: split-K, two launches (GEMM into the workspace, then SplitReduce)
+  size_t ws_bytes = 0;        // fp32 workspace the caller must bind with gemm_bind_workspace()
+  SplitReduce red;
 };
+void gemm_bind_workspace(GemmLaunch* g, void* ws);
 
 int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* out);
 int gemm_launch(const GemmLaunch* g, cudaStream_t stream);

@@ -13,16 +13,28 @@ dev = "cuda"
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
 def timeit(fn, iters):
+    """Median over `iters` rounds of the per-launch time of 20 back-to-back replays (steady state, as inside
+    the UNet program); with --flush the L2 is flushed before every round instead (cold first launch)."""
     fn(); torch.cuda.synchronize()
     ts = []
+    reps = 1 if not args.hot else 20
     for _ in range(iters):
         if not args.hot:
             flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / reps)
     ts.sort()
     return ts[len(ts) // 2]
+
+def prog_of(d):
+    """A recorded one-op program: prepared once (tensor maps, split-K workspace), replayed per iteration."""
+    prog = K.Program()
+    prog.add(d)
+    return prog.run
 
 def lin(M, N, Kd, res=False, bias=True, geglu=False, bn=0):
     a = torch.randn(M, Kd, device=dev).half(); w = (torch.randn(N, Kd, device=dev) * Kd ** -0.5).half()
@@ -35,7 +47,7 @@ def lin(M, N, Kd, res=False, bias=True, geglu=False, bn=0):
     else:
         out = torch.empty(M, N, dtype=torch.float16, device=dev)
         d = K.linear_desc(a, w, out, bias=b, residual=r, bn=bn)
-    return (lambda: K.run_gemm(d)), 2.0 * M * N * Kd, (a, w, b, r, out)
+    return prog_of(d), 2.0 * M * N * Kd, (a, w, b, r, out)
 
 def conv(B, H, W, Cin, Cout, res=False):
     x = torch.randn(B, H, W, Cin, device=dev).half(); w = (torch.randn(Cout, Cin, 3, 3, device=dev) * (9 * Cin) ** -0.5).half()
@@ -43,7 +55,7 @@ def conv(B, H, W, Cin, Cout, res=False):
     r = torch.randn(B, H, W, Cout, device=dev).half() if res else None
     out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=dev)
     d = K.conv3x3_desc(x, wp, out, bias=b, residual=r)
-    return (lambda: K.run_gemm(d)), 2.0 * B * H * W * Cout * 9 * Cin, (x, wp, b, r, out)
+    return prog_of(d), 2.0 * B * H * W * Cout * 9 * Cin, (x, wp, b, r, out)
 
 CASES = {
     "lin320": lambda: lin(65536, 320, 320),

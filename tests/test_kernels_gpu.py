@@ -129,6 +129,26 @@ def test_layer_norm_folded_into_gemm(M, C, N, geglu):
     assert rel(out, ref) < 1.5e-3, rel(out, ref)
 
 
+@pytest.mark.parametrize("Cin,res,silu", [(1280, True, False), (2560, False, False), (640, False, True)])
+def test_conv3x3_split_k(Cin, res, silu):
+    """8x8 maps (M = 1024): the library splits K over CTA-pair groups and reduces fp32 partials in a second
+    launch that also applies bias / timestep row add / residual / SiLU."""
+    B, H, W, Cout = 16, 8, 8, 1280
+    x = h16(rnd(B, H, W, Cin, seed=40))
+    w = h16(rnd(Cout, Cin, 3, 3, seed=41, scale=(9 * Cin) ** -0.5))
+    bias, temb = rnd(Cout, seed=42), rnd(B, Cout, seed=43)
+    r = h16(rnd(B, H, W, Cout, seed=44)) if res else None
+    out = torch.empty(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.conv3x3_desc(x, K.pack_conv3x3(w), out, bias=bias, rowadd=temb, residual=r,
+                              flags=L.EPI_SILU if silu else 0))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + temb[:, :, None, None]
+    if res:
+        ref = ref + r.float().permute(0, 3, 1, 2)
+    if silu:
+        ref = F.silu(ref)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-3
+
+
 def test_rowadd_timestep_broadcast():
     B, H, W, Cin, Cout = 3, 16, 16, 64, 96
     x = h16(rnd(B, H, W, Cin, seed=15))
