@@ -184,7 +184,9 @@ int ldx_euler_ancestral_step(float* x, const float* denoised, const float* noise
 enum {
   LDX_OP_GEMM = 1, LDX_OP_GROUP_NORM = 2, LDX_OP_LAYER_NORM = 3, LDX_OP_ATTENTION = 4,
   LDX_OP_NCHW_TO_NHWC = 5, LDX_OP_TIMESTEP_EMB = 6, LDX_OP_UPSAMPLE2X = 7, LDX_OP_EPS_TO_DENOISED = 8,
-  LDX_OP_CFG_DENOISED = 9, LDX_OP_VAE_POST = 10, LDX_OP_SOFTMAX = 11
+  LDX_OP_CFG_DENOISED = 9, LDX_OP_VAE_POST = 10, LDX_OP_SOFTMAX = 11,
+  LDX_OP_DUP = 12            /* p: src, dst ; l: bytes.  dst[0:bytes] = dst[bytes:2*bytes] = src (device copies): the
+                                [uncond, cond] batch of calc_cond_batch (torch.cat([x] * 2), LD.py:2545-2551) */
 };
 typedef struct {
   int32_t kind;

@@ -122,6 +122,8 @@ extern "C" int ldx_program_add_op(ldx_program_t* prog, const ldx_generic_op_t* g
     if (rc) return rc;
   } else if (gop->kind == LDX_OP_GROUP_NORM) {
     op.launches = group_norm_num_launches(gop->i[0] + gop->i[1], gop->i[3]);
+  } else if (gop->kind == LDX_OP_DUP) {
+    op.launches = 0;             // two device-to-device copies, no kernel of ours
   } else if (gop->kind == LDX_OP_GEMM) {
     set_error("use ldx_program_add_gemm for GEMM ops");
     return LDX_E_INVALID;

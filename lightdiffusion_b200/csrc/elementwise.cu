@@ -643,6 +643,11 @@ int run_generic_op(const ldx_generic_op_t* op, cudaStream_t st) {
       softmax_rows_kernel<<<(unsigned)l[2], 256, 0, st>>>((const float*)p[0], l[0], (__half*)p[1], l[1], i[0], f[0]);
       LDX_CUDA(cudaGetLastError());
       return LDX_OK;
+    case LDX_OP_DUP:
+      // p: src, dst ; l: bytes
+      LDX_CUDA(cudaMemcpyAsync((void*)p[1], p[0], (size_t)l[0], cudaMemcpyDeviceToDevice, st));
+      LDX_CUDA(cudaMemcpyAsync((char*)p[1] + l[0], p[0], (size_t)l[0], cudaMemcpyDeviceToDevice, st));
+      return LDX_OK;
     default:
       set_error("unknown op kind %d", op->kind);
       return LDX_E_INVALID;

@@ -37,6 +37,10 @@ def sigma_tables():
 # UNet; folding the LayerNorm in as well is a small net win (17.27 -> 17.19 ms per UNet step on B200).
 # LDX_FUSE_LN3=0 keeps the separate LayerNorm kernel (A/B measurements).
 FUSE_LN3 = os.environ.get("LDX_FUSE_LN3", "1") == "1"
+# Under classifier-free guidance both halves of the [uncond, cond] batch carry the same latent and timestep
+# (LD.py:2545-2551); the layers before the first cross-attention therefore run once per latent (bit-identical
+# results).  LDX_SHARE_CFG_PREFIX=0 evaluates the full 2b batch everywhere.
+SHARE_CFG_PREFIX = os.environ.get("LDX_SHARE_CFG_PREFIX", "1") == "1"
 
 class _Pool:
     """Size-keyed free list so that dead activations are reused (keeps the working set L2-friendly)."""
@@ -273,7 +277,22 @@ class UNetPlan:
         d.rowstats_out = st.data_ptr()
         return st
 
-    def _attn(self, s: AttnSpec, x):
+    def _rowstats_like(self, st: torch.Tensor, rows: int, slot: int):
+        key = (rows, st.shape[1], slot, "dup")
+        if key not in self._rs_cache:
+            self._rs_cache[key] = torch.empty(rows, st.shape[1], 2, dtype=F32, device=self.eng.dev)
+        return self._rs_cache[key]
+
+    def _dup(self, src: torch.Tensor, dst: torch.Tensor):
+        """dst = cat([src, src]) along the batch axis (two device copies recorded in the program)."""
+        assert src.is_contiguous() and dst.is_contiguous() and dst.numel() == 2 * src.numel() and dst.dtype == src.dtype
+        self.prog.add(K.generic_op(L.OP_DUP, p=[src.data_ptr(), dst.data_ptr()], l=[src.numel() * src.element_size()]))
+
+    def _attn(self, s: AttnSpec, x, expand: bool = False):
+        """SpatialTransformer (LD.py:4242-4262).  expand=True: x holds only the b distinct latents of a CFG pair
+        batch; everything up to and including the self-attention residual is identical for the uncond and cond
+        halves (same x, same timestep; only the context differs), so it runs once on b samples and the
+        activations are duplicated to the [uncond, cond] batch right before the first cross-attention."""
         eng, w, p, pool = self.eng, self.eng.w, s.name, self.pool
         Bn, h, wd, c = x.shape
         n, m = h * wd, Bn * h * wd
@@ -295,6 +314,16 @@ class UNetPlan:
         st2 = self._rowstats(d, m, 1)          # norm2 -> attn2.to_q
         self.prog.add(d)
         pool.free(t)
+        if expand:                             # b -> [uncond, cond] = 2b samples from here on
+            pool.free(a)
+            t2b, xb = pool.alloc(2 * m, c), pool.alloc(2 * Bn, h, wd, c)
+            st2b = self._rowstats_like(st2, 2 * m, 1)
+            self._dup(t2, t2b)
+            self._dup(st2, st2b)
+            self._dup(x, xb)
+            pool.free(t2)
+            t2, st2, x, Bn, m = t2b, st2b, xb, 2 * Bn, 2 * m
+            a = pool.alloc(m, c)
         # attn2 (cross; K/V of the step-invariant context come from the kv_all GEMM)
         q2 = a
         self.prog.add(K.linear_desc(t2, w[p + ".q2.w"], q2, bias=w[p + ".q2.b"], rownorm=(st2, w[p + ".q2.g"], 1e-5, c)))
@@ -324,6 +353,8 @@ class UNetPlan:
         out = pool.alloc(Bn, h, wd, c)
         self.prog.add(K.linear_desc(t4, w[p + ".pout.w"], out, bias=w[p + ".pout.b"], residual=x))
         pool.free(t4)
+        if expand:
+            pool.free(x)                       # the duplicated copy made above
         return out
 
     def _block(self, layers, h, hskip=None):
@@ -379,7 +410,22 @@ class UNetPlan:
 
         hs = []
         h = x0
-        for layers in eng.layout.input_blocks:
+        blocks = list(eng.layout.input_blocks)
+        l1 = blocks[1] if len(blocks) > 1 else []
+        share = (self.cfg_pairs and SHARE_CFG_PREFIX and len(blocks) > 1 and len(l1) == 2 and
+                 isinstance(l1[0], ResSpec) and isinstance(l1[1], AttnSpec))
+        if share:
+            # CFG: conv_in, the first ResBlock and the first self-attention see identical inputs in both halves
+            h0 = self._block(blocks[0], x0[:nb])                 # conv_in on the b distinct latents
+            r1 = self._res(l1[0], h0, None)
+            h = self._attn(l1[1], r1, expand=True)
+            pool.free(r1)
+            h0b = pool.alloc(B, H, W, h0.shape[-1])
+            self._dup(h0, h0b)
+            pool.free(h0)
+            hs += [h0b, h]
+            blocks = blocks[2:]
+        for layers in blocks:
             h = self._block(layers, h)
             hs.append(h)
         h = self._block(eng.layout.middle, h)
