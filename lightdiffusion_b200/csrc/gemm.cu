@@ -426,30 +426,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               // p.bias is never null here (gemm_prepare substitutes a zero vector): no per-load predicates
               const float4* bv = reinterpret_cast<const float4*>(p.bias + nt * p.bn + c);
               const float4* bgp = bv + (p.bn >> 3);
-#pragma unroll
-              if (rownorm) {                   // acc -> rstd * (acc - mean * gsum[n]); the bias is already bias'
-                const float4* gv = reinterpret_cast<const float4*>(p.ln_gsum + nt * p.bn + c);
-                const float4* ggp = gv + (p.bn >> 3);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                  const float4 ga = __ldg(gv + j4), gg = __ldg(ggp + j4);
-                  r[j4 * 4 + 0] = __float_as_uint((__uint_as_float(r[j4 * 4 + 0]) - ln_mean * ga.x) * ln_rstd);
-                  r[j4 * 4 + 1] = __float_as_uint((__uint_as_float(r[j4 * 4 + 1]) - ln_mean * ga.y) * ln_rstd);
-                  r[j4 * 4 + 2] = __float_as_uint((__uint_as_float(r[j4 * 4 + 2]) - ln_mean * ga.z) * ln_rstd);
-                  r[j4 * 4 + 3] = __float_as_uint((__uint_as_float(r[j4 * 4 + 3]) - ln_mean * ga.w) * ln_rstd);
-                  g[j4 * 4 + 0] = __float_as_uint((__uint_as_float(g[j4 * 4 + 0]) - ln_mean * gg.x) * ln_rstd);
-                  g[j4 * 4 + 1] = __float_as_uint((__uint_as_float(g[j4 * 4 + 1]) - ln_mean * gg.y) * ln_rstd);
-                  g[j4 * 4 + 2] = __float_as_uint((__uint_as_float(g[j4 * 4 + 2]) - ln_mean * gg.z) * ln_rstd);
-                  g[j4 * 4 + 3] = __float_as_uint((__uint_as_float(g[j4 * 4 + 3]) - ln_mean * gg.w) * ln_rstd);
-                }
-              }
+              // with the LayerNorm folded in: rstd * (acc - mean * gsum[n]) + bias'[n] = acc * ln_a + (gsum[n] * ln_b + bias')
+              const float ln_a = rownorm ? ln_rstd : 1.0f, ln_b = rownorm ? -ln_mean * ln_rstd : 0.0f;
+              const float4* gv = reinterpret_cast<const float4*>((rownorm ? p.ln_gsum : p.bias) + nt * p.bn + c);
+              const float4* ggp = gv + (p.bn >> 3);
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 ba = __ldg(bv + j4), bg = __ldg(bgp + j4);
-                v[j4 * 4 + 0] = (__uint_as_float(r[j4 * 4 + 0]) + ba.x) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 0]) + bg.x);
-                v[j4 * 4 + 1] = (__uint_as_float(r[j4 * 4 + 1]) + ba.y) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 1]) + bg.y);
-                v[j4 * 4 + 2] = (__uint_as_float(r[j4 * 4 + 2]) + ba.z) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 2]) + bg.z);
-                v[j4 * 4 + 3] = (__uint_as_float(r[j4 * 4 + 3]) + ba.w) * gelu_erf_fast(__uint_as_float(g[j4 * 4 + 3]) + bg.w);
+                float4 ba = __ldg(bv + j4), bg = __ldg(bgp + j4);
+                if (rownorm) {
+                  const float4 ga = __ldg(gv + j4), gg = __ldg(ggp + j4);
+                  ba.x = fmaf(ga.x, ln_b, ba.x); ba.y = fmaf(ga.y, ln_b, ba.y); ba.z = fmaf(ga.z, ln_b, ba.z); ba.w = fmaf(ga.w, ln_b, ba.w);
+                  bg.x = fmaf(gg.x, ln_b, bg.x); bg.y = fmaf(gg.y, ln_b, bg.y); bg.z = fmaf(gg.z, ln_b, bg.z); bg.w = fmaf(gg.w, ln_b, bg.w);
+                }
+                v[j4 * 4 + 0] = fmaf(__uint_as_float(r[j4 * 4 + 0]), ln_a, ba.x) * gelu_erf_fast(fmaf(__uint_as_float(g[j4 * 4 + 0]), ln_a, bg.x));
+                v[j4 * 4 + 1] = fmaf(__uint_as_float(r[j4 * 4 + 1]), ln_a, ba.y) * gelu_erf_fast(fmaf(__uint_as_float(g[j4 * 4 + 1]), ln_a, bg.y));
+                v[j4 * 4 + 2] = fmaf(__uint_as_float(r[j4 * 4 + 2]), ln_a, ba.z) * gelu_erf_fast(fmaf(__uint_as_float(g[j4 * 4 + 2]), ln_a, bg.z));
+                v[j4 * 4 + 3] = fmaf(__uint_as_float(r[j4 * 4 + 3]), ln_a, ba.w) * gelu_erf_fast(fmaf(__uint_as_float(g[j4 * 4 + 3]), ln_a, bg.w));
               }
             } else {
               // bias / rowadd values are fetched while the TMEM load is in flight
