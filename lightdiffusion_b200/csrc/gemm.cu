@@ -13,8 +13,12 @@
 // * B operand: bn x 64 slice of the [N, K] weight matrix, 2-D TMA, same layout.
 // * D: fp32 accumulators in TMEM, double buffered (2 x bn columns) so the epilogue of tile i
 //   overlaps the main loop of tile i+1.
-// * warp 0 = TMA producer, warp 1 = MMA issuer (one thread), warps 2..5 = epilogue
-//   (tcgen05.ld -> bias / timestep-embedding row add / residual / SiLU / GEGLU -> fp16 stores).
+// * warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2..9 = epilogue, each warp an
+//   independent pipeline on its 32 rows (tcgen05.ld -> bias / timestep-embedding row add / folded LayerNorm /
+//   SiLU / GEGLU -> fp16 into its own SWIZZLE_128B staging slot -> its own TMA store).
+// * Residual adds (x + h) are an extra K segment against a 256 x 256 identity: they ride the operand pipeline
+//   and the tensor core adds them into the fp32 accumulator.
+// * Split-K (few output tiles, long K): K slices per CTA-pair group, fp32 partials, splitk_reduce_kernel.
 //
 // Roofline: tensor-pipe bound; algorithmic FLOPs = 2 * M * N * K.
 #include <stdlib.h>
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
   const uint32_t b_stage_bytes = (uint32_t)bn_cta * BK * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)stages * A_STAGE_BYTES;
-  uint8_t* sC = sB + (size_t)stages * b_stage_bytes;          // EPI_NBUF staging buffers (1024-aligned)
+  uint8_t* sC = sB + (size_t)stages * b_stage_bytes;          // per-warp staging slots (1024-aligned)
   GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sC + EPI_SMEM);
 
   if (threadIdx.x == 0) {
