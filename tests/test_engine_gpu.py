@@ -127,6 +127,27 @@ def test_unet_small_cfg_matches_oracle(small_unet):
     assert rel((xs - out) / sigma.view(-1, 1, 1, 1), (xs - ref) / sigma.view(-1, 1, 1, 1)) < 3 * EPS_TOL
 
 
+@pytest.mark.parametrize("nb", [1, 3])
+def test_cfg_shared_prefix_is_bit_identical(small_unet, nb, monkeypatch):
+    """Evaluating the layers before the first cross-attention once per latent and duplicating them to the
+    [uncond, cond] batch must give exactly the result of evaluating all 2b samples (calc_cond_batch feeds both
+    halves the same x and timestep, LD.py:2545-2551)."""
+    from lightdiffusion_b200 import engine as E
+    cfg, sd, eng = small_unet
+    g = torch.Generator().manual_seed(31 + nb)
+    x = (torch.randn(nb, 4, 16, 16, generator=g) * 4).to(DEV)
+    ctx = torch.randn(2 * nb, 77, cfg.context_dim, generator=g).to(DEV)
+    sigma = torch.linspace(0.5, 6.0, nb).to(DEV)
+    outs = []
+    for share in (True, False):
+        monkeypatch.setattr(E, "SHARE_CFG_PREFIX", share)
+        plan = E.UNetPlan(eng, 2 * nb, 16, 16, True)          # fresh plan, not the engine's cache
+        plan.use_graph = False
+        plan.set_context(ctx)
+        outs.append(plan.run(x, sigma, None, cfg_scale=7.0).clone())
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_unet_sd15_eps_parity(sd15_unet):
     cfg, sd, eng = sd15_unet
     x, ctx = _inputs(2, 64, cfg.context_dim, 11)
