@@ -162,6 +162,14 @@ int ldx_cfg_combine(const float* cond, const float* uncond, float scale, float* 
 /* decoded fp16 NHWC [B,H,W,ldc] (first 3 channels) -> clamp((v+1)/2, 0, 1) fp32 NHWC [B,H,W,3]
  * (VAE.process_output + movedim, LD.py:6296-6298, 6377-6380). */
 int ldx_vae_postprocess(const void* dec, int64_t ldc, float* img, int64_t npix, ldx_stream_t stream);
+/* VAE.encode input side: pixels fp32 NHWC [npix, 3] in [0,1] -> 2x - 1, fp16 NHWC [npix, 8] with channels 3..7
+ * zero (VAE.process_input + movedim + cast, LD.py:6295, 6385, 6402-6405). out must be 16-byte aligned. */
+int ldx_vae_preprocess(const float* pixels, void* out, int64_t npix, ldx_stream_t stream);
+/* DiagonalGaussianDistribution.sample (LD.py:166-179): moments fp32 NHWC [b*hw, 2*zc] (mean | logvar), noise
+ * fp32 NCHW [b, zc, hw] or NULL (posterior mean) -> z = mean + exp(0.5 * clamp(logvar, -30, 20)) * noise,
+ * fp32 NCHW. */
+int ldx_vae_sample_posterior(const float* moments, const float* noise, float* z, int b, int zc, int64_t hw,
+                             ldx_stream_t stream);
 /* out[r, :] = softmax(scale * s[r, :]): fp32 scores in, fp16 probabilities out (the VAE AttnBlock's
  * single-head d=512 attention runs as GEMM / softmax / GEMM, LD.py:3591-3602). */
 int ldx_softmax_rows(const float* s, int64_t lds, void* out, int64_t ldo, int64_t rows, int n, float scale,
@@ -185,6 +193,8 @@ enum {
   LDX_OP_GEMM = 1, LDX_OP_GROUP_NORM = 2, LDX_OP_LAYER_NORM = 3, LDX_OP_ATTENTION = 4,
   LDX_OP_NCHW_TO_NHWC = 5, LDX_OP_TIMESTEP_EMB = 6, LDX_OP_UPSAMPLE2X = 7, LDX_OP_EPS_TO_DENOISED = 8,
   LDX_OP_CFG_DENOISED = 9, LDX_OP_VAE_POST = 10, LDX_OP_SOFTMAX = 11,
+  LDX_OP_VAE_PRE = 13,       /* p: pixels, out ; l: npix */
+  LDX_OP_VAE_SAMPLE = 14,    /* p: moments, noise, z ; l: n, hw ; i: zc */
   LDX_OP_DUP = 12            /* p: src, dst ; l: bytes.  dst[0:bytes] = dst[bytes:2*bytes] = src (device copies): the
                                 [uncond, cond] batch of calc_cond_batch (torch.cat([x] * 2), LD.py:2545-2551) */
 };

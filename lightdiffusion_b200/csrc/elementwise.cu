@@ -524,6 +524,83 @@ __global__ void vae_post_kernel(const __half* __restrict__ dec, int64_t ldc, flo
   }
 }
 
+// VAE.encode input side (LD.py:6385, 6295, 6402-6405): pixels fp32 NHWC [npix, 3] in [0,1] -> 2x - 1 as fp16
+// NHWC [npix, 8] (channels 3..7 zero: the 3x3 conv_in reads 16-byte channel groups)
+__global__ void vae_pre_kernel(const float* __restrict__ pix, __half* __restrict__ out, int64_t npix) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+    const float r = pix[i * 3], g = pix[i * 3 + 1], b = pix[i * 3 + 2];
+    const __half2 a = __floats2half2_rn(r * 2.0f - 1.0f, g * 2.0f - 1.0f), c = __floats2half2_rn(b * 2.0f - 1.0f, 0.f);
+    uint4 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&c);
+    u.z = 0u; u.w = 0u;
+    reinterpret_cast<uint4*>(out)[i] = u;
+  }
+}
+
+// DiagonalGaussianDistribution (LD.py:166-179): moments fp32 NHWC [B*hw, 2*zc] (mean | logvar) and noise fp32 NCHW
+// -> z = mean + exp(0.5 * clamp(logvar, -30, 20)) * noise, fp32 NCHW [B, zc, h, w]; noise == NULL gives the mean
+__global__ void vae_sample_kernel(const float* __restrict__ mom, const float* __restrict__ noise, float* __restrict__ z,
+                                  int64_t n, int zc, int64_t hw) {
+  // i indexes z (NCHW)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i % hw, bc = i / hw;
+    const int c = (int)(bc % zc);
+    const int64_t b = bc / zc;
+    const float* m = mom + (b * hw + pix) * (2 * zc);
+    float v = m[c];
+    if (noise) v += expf(0.5f * fminf(fmaxf(m[zc + c], -30.0f), 20.0f)) * noise[i];
+    z[i] = v;
+  }
+}
+
+// row softmax for n = NV * 1024 (the VAE AttnBlock's 4096 / 16384 tokens): the row lives in registers, so the
+// fp32 scores are read once (16-byte loads) and the fp16 probabilities written once (8-byte stores)
+template <int NV>
+__global__ void __launch_bounds__(256) softmax_rows_reg_kernel(const float* __restrict__ s, int64_t lds,
+                                                               __half* __restrict__ out, int64_t ldo, float scale_log2) {
+  __shared__ float red[2][8];
+  const float4* row = reinterpret_cast<const float4*>(s + (int64_t)blockIdx.x * lds);
+  uint2* orow = reinterpret_cast<uint2*>(out + (int64_t)blockIdx.x * ldo);
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = __ldcs(row + j * 256 + threadIdx.x);
+  float m = -3.4e38f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) m = fmaxf(fmaxf(m, fmaxf(v[j].x, v[j].y)), fmaxf(v[j].z, v[j].w));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0][0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[0][w]);
+  const float off = m * scale_log2;     // scale > 0: max(scale * s) = scale * max(s)
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    v[j].x = exp2f(fmaf(v[j].x, scale_log2, -off));
+    v[j].y = exp2f(fmaf(v[j].y, scale_log2, -off));
+    v[j].z = exp2f(fmaf(v[j].z, scale_log2, -off));
+    v[j].w = exp2f(fmaf(v[j].w, scale_log2, -off));
+    sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = red[1][0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) sum += red[1][w];
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const __half2 a = __floats2half2_rn(v[j].x * inv, v[j].y * inv), b = __floats2half2_rn(v[j].z * inv, v[j].w * inv);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t*>(&a);
+    u.y = *reinterpret_cast<const uint32_t*>(&b);
+    orow[j * 256 + threadIdx.x] = u;
+  }
+}
+
 // row softmax(scale * s): fp32 scores in, fp16 probabilities out; one block per row
 __global__ void softmax_rows_kernel(const float* __restrict__ s, int64_t lds, __half* __restrict__ out, int64_t ldo,
                                     int n, float scale) {
@@ -645,9 +722,32 @@ int run_generic_op(const ldx_generic_op_t* op, cudaStream_t st) {
       vae_post_kernel<<<ew_blocks(l[1] * 3), 256, 0, st>>>((const __half*)p[0], l[0], (float*)p[1], l[1]);
       LDX_CUDA(cudaGetLastError());
       return LDX_OK;
+    case LDX_OP_VAE_PRE:
+      // p: pixels, out ; l: npix
+      vae_pre_kernel<<<ew_blocks(l[0]), 256, 0, st>>>((const float*)p[0], (__half*)p[1], l[0]);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
+    case LDX_OP_VAE_SAMPLE:
+      // p: moments, noise, z ; l: n, hw ; i: zc
+      vae_sample_kernel<<<ew_blocks(l[0]), 256, 0, st>>>((const float*)p[0], (const float*)p[1], (float*)p[2], l[0], i[0],
+                                                          l[1]);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
     case LDX_OP_SOFTMAX:
       // p: s (fp32), out (fp16) ; l: lds, ldo, rows ; i: n ; f: scale
-      softmax_rows_kernel<<<(unsigned)l[2], 256, 0, st>>>((const float*)p[0], l[0], (__half*)p[1], l[1], i[0], f[0]);
+      {
+        const float* sp = (const float*)p[0];
+        __half* op = (__half*)p[1];
+        const bool vec = f[0] > 0.f && l[0] % 4 == 0 && l[1] % 4 == 0 && ((uintptr_t)sp & 15) == 0 && ((uintptr_t)op & 7) == 0;
+        const float sl2 = f[0] * 1.4426950408889634f;
+        const unsigned rows = (unsigned)l[2];
+        if (vec && i[0] == 16384) softmax_rows_reg_kernel<16><<<rows, 256, 0, st>>>(sp, l[0], op, l[1], sl2);
+        else if (vec && i[0] == 8192) softmax_rows_reg_kernel<8><<<rows, 256, 0, st>>>(sp, l[0], op, l[1], sl2);
+        else if (vec && i[0] == 4096) softmax_rows_reg_kernel<4><<<rows, 256, 0, st>>>(sp, l[0], op, l[1], sl2);
+        else if (vec && i[0] == 2048) softmax_rows_reg_kernel<2><<<rows, 256, 0, st>>>(sp, l[0], op, l[1], sl2);
+        else if (vec && i[0] == 1024) softmax_rows_reg_kernel<1><<<rows, 256, 0, st>>>(sp, l[0], op, l[1], sl2);
+        else softmax_rows_kernel<<<rows, 256, 0, st>>>(sp, l[0], op, l[1], i[0], f[0]);
+      }
       LDX_CUDA(cudaGetLastError());
       return LDX_OK;
     case LDX_OP_DUP:
@@ -739,6 +839,22 @@ extern "C" int ldx_vae_postprocess(const void* dec, int64_t ldc, float* img, int
   LDX_CHECK_ARG(dec && img, "vae_postprocess: null");
   ldx_generic_op_t op = make_op(LDX_OP_VAE_POST);
   op.p[0] = dec; op.p[1] = img; op.l[0] = ldc; op.l[1] = npix;
+  return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_vae_preprocess(const float* pixels, void* out, int64_t npix, ldx_stream_t stream) {
+  LDX_CHECK_ARG(pixels && out && npix > 0, "vae_preprocess: null / empty");
+  LDX_CHECK_ARG(((uintptr_t)out & 15) == 0, "vae_preprocess: out must be 16-byte aligned");
+  ldx_generic_op_t op = make_op(LDX_OP_VAE_PRE);
+  op.p[0] = pixels; op.p[1] = out; op.l[0] = npix;
+  return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_vae_sample_posterior(const float* moments, const float* noise, float* z, int b, int zc, int64_t hw,
+                                        ldx_stream_t stream) {
+  LDX_CHECK_ARG(moments && z && b > 0 && zc > 0 && hw > 0, "vae_sample_posterior: null / empty");
+  ldx_generic_op_t op = make_op(LDX_OP_VAE_SAMPLE);
+  op.p[0] = moments; op.p[1] = noise; op.p[2] = z; op.l[0] = (int64_t)b * zc * hw; op.l[1] = hw; op.i[0] = zc;
   return run_generic_op(&op, as_stream(stream));
 }
 

@@ -19,7 +19,7 @@ import torch
 from . import _lib as L
 from . import kernels as K
 from .sd15 import (SD15_UNET, SD15_VAE, AttnSpec, ConvSpec, ResSpec, UNetConfig, VAEConfig, unet_layout,
-                   vae_decoder_levels)
+                   vae_decoder_levels, vae_encoder_levels)
 
 F16, F32 = torch.float16, torch.float32
 
@@ -633,20 +633,27 @@ class VAEPlan:
         prog.add(K.group_norm_op(x, None, w[p + ".gn.g"], w[p + ".gn.b"], y, self.stats, 1e-6, False))
         qk = pool.alloc(Bn * n, 2 * c)
         prog.add(K.linear_desc(y, w[p + ".qk.w"], qk, bias=w[p + ".qk.b"]))
-        vt = pool.alloc(Bn, c, n)
+        # P V contracts over the n tokens: its operands' row pitch is padded to a multiple of 64 (the GEMM's K chunk),
+        # with V^T's padding columns zero, so that token counts off the 64 grid (odd image sizes) work too
+        n64 = K.ceil64(n)
+        if n64 == n:
+            vt = pool.alloc(Bn, c, n)
+        else:
+            vt = torch.zeros(Bn, c, n64, dtype=F16, device=x.device)
+            prog.keep(vt)
         s = pool.alloc(n, n, dtype=F32)
-        pm = pool.alloc(n, n)
+        pm = pool.alloc(n, n64)
         o = pool.alloc(Bn * n, c)
         y2, qk3, o3 = y.view(Bn, n, c), qk.view(Bn, n, 2 * c), o.view(Bn, n, c)
         for b in range(Bn):
-            prog.add(K.linear_desc(w[p + ".v.w"], y2[b], vt[b]))                       # V^T = Wv @ hn^T
+            prog.add(K.linear_desc(w[p + ".v.w"], y2[b], vt[b, :, :n]))                # V^T = Wv @ hn^T
             prog.add(K.linear_desc(qk3[b, :, :c], qk3[b, :, c:], s, flags=L.EPI_OUT_F32))  # S = Q K^T
-            prog.add(K.generic_op(L.OP_SOFTMAX, p=[s.data_ptr(), pm.data_ptr()], l=[n, n, n], i=[n],
+            prog.add(K.generic_op(L.OP_SOFTMAX, p=[s.data_ptr(), pm.data_ptr()], l=[n, n64, n], i=[n],
                                   f=[1.0 / math.sqrt(c)]))       # l: lds, ldo, rows
-            prog.add(K.linear_desc(pm, vt[b], o3[b], bias=w[p + ".v.b"]))             # O = P V + b_v
+            prog.add(K.linear_desc(pm[:, :n], vt[b], o3[b], bias=w[p + ".v.b"]))      # O = P V + b_v
         out = pool.alloc(Bn, h, wd, c)
         prog.add(K.linear_desc(o, w[p + ".o.w"], out, bias=w[p + ".o.b"], residual=x))
-        for t in (y, qk, vt, s, pm, o, x):
+        for t in (y, qk, s, pm, o, x) + ((vt,) if n64 == n else ()):
             pool.free(t)
         return out
 
@@ -664,3 +671,140 @@ class VAEPlan:
             self.graph = g
         self.graph.replay()
         return self.img
+
+
+# =============================================================================== VAE encoder
+class VAEEncoderEngine(VAEDecoderEngine):
+    """AutoencoderKL encoder (Encoder + quant_conv + DiagonalGaussianRegularizer, LD.py:3649-3758, 3461-3481,
+    3446-3458) with reference parameter names; shares the ResnetBlock / AttnBlock plans of the decoder."""
+
+    def __init__(self, state_dict, cfg: VAEConfig = SD15_VAE, device="cuda"):
+        L.require_device()
+        self.cfg, self.dev = cfg, torch.device(device)
+        self.w: Dict[str, torch.Tensor] = {}
+        self._plans: Dict[tuple, "VAEEncodePlan"] = {}
+        sd, dev, w = state_dict, self.dev, self.w
+        w["cin.w"] = K.pack_conv3x3(UNetEngine._pad_in(sd["encoder.conv_in.weight"]))
+        w["cin.b"] = _f32(sd, "encoder.conv_in.bias", dev)
+        for i_level, blocks, has_down in vae_encoder_levels(cfg):
+            for j in range(len(blocks)):
+                self._pack_res(sd, f"encoder.down.{i_level}.block.{j}")
+            if has_down:
+                n = f"encoder.down.{i_level}.downsample.conv"
+                w[n + ".w"], w[n + ".b"] = K.pack_conv3x3(sd[n + ".weight"]), _f32(sd, n + ".bias", dev)
+        self._pack_res(sd, "encoder.mid.block_1")
+        self._pack_res(sd, "encoder.mid.block_2")
+        a = "encoder.mid.attn_1"
+        w[a + ".gn.g"], w[a + ".gn.b"] = _f32(sd, a + ".norm.weight", dev), _f32(sd, a + ".norm.bias", dev)
+        w[a + ".qk.w"] = K.pack_linear(torch.cat([sd[a + ".q.weight"], sd[a + ".k.weight"]], 0))
+        w[a + ".qk.b"] = torch.cat([_f32(sd, a + ".q.bias", dev), _f32(sd, a + ".k.bias", dev)]).contiguous()
+        w[a + ".v.w"], w[a + ".v.b"] = K.pack_linear(sd[a + ".v.weight"]), _f32(sd, a + ".v.bias", dev)
+        w[a + ".o.w"], w[a + ".o.b"] = K.pack_linear(sd[a + ".proj_out.weight"]), _f32(sd, a + ".proj_out.bias", dev)
+        w["nout.g"], w["nout.b"] = _f32(sd, "encoder.norm_out.weight", dev), _f32(sd, "encoder.norm_out.bias", dev)
+        w["cout.w"], w["cout.b"] = K.pack_conv3x3(sd["encoder.conv_out.weight"]), _f32(sd, "encoder.conv_out.bias", dev)
+        w["q.w"], w["q.b"] = K.pack_linear(sd["quant_conv.weight"]), _f32(sd, "quant_conv.bias", dev)
+        torch.cuda.synchronize()
+
+    def plan(self, B, H, W) -> "VAEEncodePlan":
+        key = (B, H, W)
+        if key not in self._plans:
+            self._plans[key] = VAEEncodePlan(self, B, H, W)
+        return self._plans[key]
+
+    def decode(self, z):
+        raise L.LdxError("VAEEncoderEngine has no decoder; use VAEDecoderEngine")
+
+    decode_raw = decode
+
+    @torch.no_grad()
+    def encode(self, pixels: torch.Tensor, noise: Optional[torch.Tensor] = None, sample: bool = True) -> torch.Tensor:
+        """VAE.encode (LD.py:6383-6410): pixels fp32 [B, H, W, 3] in [0,1] -> latent fp32 [B, 4, H/8, W/8].
+        The posterior noise defaults to torch.randn(mean.shape) from the global CPU generator, the draw
+        DiagonalGaussianDistribution.sample makes (LD.py:175-179); ``sample=False`` returns the posterior mean."""
+        if pixels.dim() != 4 or pixels.shape[-1] < 3:
+            raise L.LdxError(f"pixels must be [B, H, W, 3], got {tuple(pixels.shape)}")
+        B, H, W, _ = pixels.shape
+        f = 2 ** (len(self.cfg.ch_mult) - 1)
+        if H % f or W % f:
+            raise L.LdxError(f"image size must be a multiple of {f}, got {H}x{W}")
+        pl = self.plan(B, H, W)
+        if sample and noise is None:
+            noise = torch.randn(B, self.cfg.z_channels, H // f, W // f)
+        return pl.run(pixels[..., :3], noise if sample else None).clone()
+
+    @torch.no_grad()
+    def moments(self, pixels: torch.Tensor) -> torch.Tensor:
+        """quant_conv(encoder(x)) as fp32 NCHW [B, 8, H/8, W/8] (mean | logvar), for tests."""
+        B, H, W, _ = pixels.shape
+        pl = self.plan(B, H, W)
+        pl.run(pixels[..., :3], None)
+        return pl.mom.permute(0, 3, 1, 2).contiguous()
+
+
+class VAEEncodePlan(VAEPlan):
+    def __init__(self, eng: VAEEncoderEngine, B, H, W):
+        self.eng, self.B, self.H, self.W = eng, B, H, W
+        dev, cfg, w = eng.dev, eng.cfg, eng.w
+        self.pool = pool = _Pool(dev)
+        self.prog = prog = K.Program()
+        f = 2 ** (len(cfg.ch_mult) - 1)
+        zc = cfg.z_channels
+        self.pix_in = torch.zeros(B, H, W, 3, dtype=F32, device=dev)
+        self.noise_in = torch.zeros(B, zc, H // f, W // f, dtype=F32, device=dev)
+        self.z = torch.zeros(B, zc, H // f, W // f, dtype=F32, device=dev)
+        self.stats = torch.empty(B * L.GN_STATS_FLOATS_PER_BATCH, dtype=F32, device=dev)
+        x0 = torch.zeros(B, H, W, 8, dtype=F16, device=dev)
+        prog.add(K.generic_op(L.OP_VAE_PRE, p=[self.pix_in.data_ptr(), x0.data_ptr()], l=[B * H * W]))
+        h = pool.alloc(B, H, W, cfg.ch)
+        prog.add(K.conv3x3_desc(x0, w["cin.w"], h, bias=w["cin.b"]))
+        prog.keep(x0)
+        for i_level, blocks, has_down in vae_encoder_levels(cfg):
+            for j, (cin, cout) in enumerate(blocks):
+                h = self._res(f"encoder.down.{i_level}.block.{j}", h, cin, cout)
+            if has_down:
+                n = f"encoder.down.{i_level}.downsample.conv"
+                Bn, hh, ww, c = h.shape
+                nh = pool.alloc(Bn, hh // 2, ww // 2, c)
+                prog.add(K.conv3x3_s2_desc(h, w[n + ".w"], nh, pad_end=True, bias=w[n + ".b"]))
+                pool.free(h)
+                h = nh
+        top = cfg.ch * cfg.ch_mult[-1]
+        h = self._res("encoder.mid.block_1", h, top, top)
+        h = self._attn("encoder.mid.attn_1", h)
+        h = self._res("encoder.mid.block_2", h, top, top)
+        Bn, hh, ww, c = h.shape
+        y = pool.alloc(Bn, hh, ww, c)
+        prog.add(K.group_norm_op(h, None, w["nout.g"], w["nout.b"], y, self.stats, 1e-6, True))
+        m0 = torch.zeros(Bn, hh, ww, 2 * zc, dtype=F16, device=dev)
+        prog.add(K.conv3x3_desc(y, w["cout.w"], m0, bias=w["cout.b"]))
+        self.mom = torch.zeros(Bn, hh, ww, 2 * zc, dtype=F32, device=dev)       # mean | logvar, fp32
+        prog.add(K.linear_desc(m0, w["q.w"], self.mom, bias=w["q.b"], flags=L.EPI_OUT_F32))
+        prog.keep(m0)
+        self.mean_prog = K.Program()
+        self.mean_prog.add(K.generic_op(L.OP_VAE_SAMPLE, p=[self.mom.data_ptr(), None, self.z.data_ptr()],
+                                        l=[self.z.numel(), hh * ww], i=[zc]))
+        self.sample_prog = K.Program()
+        self.sample_prog.add(K.generic_op(L.OP_VAE_SAMPLE, p=[self.mom.data_ptr(), self.noise_in.data_ptr(),
+                                                              self.z.data_ptr()],
+                                          l=[self.z.numel(), hh * ww], i=[zc]))
+        self.graph = None
+        self.use_graph = True
+
+    def run(self, pixels, noise=None) -> torch.Tensor:
+        """Returns the plan's latent buffer (fp32 NCHW); valid until the next run."""
+        self.pix_in.copy_(pixels)
+        if noise is not None:
+            self.noise_in.copy_(noise)
+        if not self.use_graph:
+            self.prog.run()
+        else:
+            if self.graph is None:
+                self.prog.run()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.prog.run()
+                self.graph = g
+            self.graph.replay()
+        (self.sample_prog if noise is not None else self.mean_prog).run()
+        return self.z

@@ -161,17 +161,20 @@ def conv3x3_desc(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, **kw) -> 
     return gemm_desc([x], segs, wp, out, wp.shape[0], **kw)
 
 
-def conv3x3_s2_desc(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, **kw) -> L.GemmDesc:
-    """3x3 stride-2 pad-1 conv (Downsample1, LD.py:5173-5186) via four parity-strided views of x."""
+def conv3x3_s2_desc(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, pad_end: bool = False, **kw) -> L.GemmDesc:
+    """3x3 stride-2 conv via four parity-strided views of x: pad 1 on every side (Downsample1, LD.py:5173-5186) or,
+    with ``pad_end``, the VAE encoder's F.pad(x, (0,1,0,1)) + padding-0 conv (Downsample, LD.py:3514-3528), where
+    tap k reads input row 2y + k: parity k & 1, shifted by k >> 1."""
     b, h, w, cin = x.shape
     assert h % 2 == 0 and w % 2 == 0
     nch = ceil64(cin) // 64
     views = [x[:, py::2, px::2, :] for py in range(2) for px in range(2)]
+    taps = ((0, 0), (1, 0), (0, 1)) if pad_end else ((1, -1), (0, 0), (1, 0))
     segs = []
     for ky in range(3):
-        py, dy = ((1, -1), (0, 0), (1, 0))[ky]
+        py, dy = taps[ky]
         for kx in range(3):
-            px, dx = ((1, -1), (0, 0), (1, 0))[kx]
+            px, dx = taps[kx]
             segs.append((py * 2 + px, 0, dx, dy, nch))
     return gemm_desc(views, segs, wp, out, wp.shape[0], **kw)
 

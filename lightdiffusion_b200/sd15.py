@@ -201,6 +201,7 @@ class VAEConfig:
     """The literal AutoencoderKL config of LD.py:6300-6326 (decoder half)."""
     z_channels: int = 4
     out_ch: int = 3
+    in_channels: int = 3
     ch: int = 128
     ch_mult: Tuple[int, ...] = (1, 2, 4, 4)
     num_res_blocks: int = 2
@@ -265,6 +266,52 @@ def vae_decoder_param_shapes(cfg: VAEConfig = SD15_VAE) -> "OrderedDict[str, tup
     out["decoder.norm_out.bias"] = (last,)
     out["decoder.conv_out.weight"] = (cfg.out_ch, last, 3, 3)
     out["decoder.conv_out.bias"] = (cfg.out_ch,)
+    return out
+
+
+# --------------------------------------------------------------------------- VAE encoder
+def vae_encoder_levels(cfg: VAEConfig = SD15_VAE):
+    """[(i_level, [(cin,cout)...], has_downsample)] in execution order (Encoder.__init__, LD.py:3684-3708)."""
+    n = len(cfg.ch_mult)
+    in_mult = (1,) + tuple(cfg.ch_mult)
+    levels = []
+    for i_level in range(n):
+        block_in, block_out = cfg.ch * in_mult[i_level], cfg.ch * cfg.ch_mult[i_level]
+        blocks = []
+        for _ in range(cfg.num_res_blocks):
+            blocks.append((block_in, block_out))
+            block_in = block_out
+        levels.append((i_level, blocks, i_level != n - 1))
+    return levels
+
+
+def vae_encoder_param_shapes(cfg: VAEConfig = SD15_VAE) -> "OrderedDict[str, tuple]":
+    """name -> shape for ``encoder.*`` + ``quant_conv`` (keys of AutoencodingEngine, LD.py:3461-3481;
+    double_z: the encoder emits mean and logvar, 2 * z_channels)."""
+    out: "OrderedDict[str, tuple]" = OrderedDict()
+    out["encoder.conv_in.weight"] = (cfg.ch, cfg.in_channels, 3, 3)
+    out["encoder.conv_in.bias"] = (cfg.ch,)
+    for i_level, blocks, has_down in vae_encoder_levels(cfg):
+        for j, (cin, cout) in enumerate(blocks):
+            _vae_res(out, f"encoder.down.{i_level}.block.{j}", cin, cout)
+        if has_down:
+            c = blocks[-1][1]
+            out[f"encoder.down.{i_level}.downsample.conv.weight"] = (c, c, 3, 3)
+            out[f"encoder.down.{i_level}.downsample.conv.bias"] = (c,)
+    top = cfg.ch * cfg.ch_mult[-1]
+    _vae_res(out, "encoder.mid.block_1", top, top)
+    out["encoder.mid.attn_1.norm.weight"] = (top,)
+    out["encoder.mid.attn_1.norm.bias"] = (top,)
+    for n in ("q", "k", "v", "proj_out"):
+        out[f"encoder.mid.attn_1.{n}.weight"] = (top, top, 1, 1)
+        out[f"encoder.mid.attn_1.{n}.bias"] = (top,)
+    _vae_res(out, "encoder.mid.block_2", top, top)
+    out["encoder.norm_out.weight"] = (top,)
+    out["encoder.norm_out.bias"] = (top,)
+    out["encoder.conv_out.weight"] = (2 * cfg.z_channels, top, 3, 3)
+    out["encoder.conv_out.bias"] = (2 * cfg.z_channels,)
+    out["quant_conv.weight"] = (2 * cfg.z_channels, 2 * cfg.z_channels, 1, 1)
+    out["quant_conv.bias"] = (2 * cfg.z_channels,)
     return out
 
 

@@ -25,7 +25,7 @@ import torch
 import torch.nn.functional as F
 
 from lightdiffusion_b200.sd15 import (AttnSpec, ConvSpec, ResSpec, UNetConfig, VAEConfig,
-                                      unet_layout, vae_decoder_levels)
+                                      unet_layout, vae_decoder_levels, vae_encoder_levels)
 
 SD = Dict[str, torch.Tensor]
 
@@ -332,6 +332,36 @@ def vae_decode(sd: SD, cfg: VAEConfig, z):
     """VAE.decode, LD.py:6357-6381: clamp((x+1)/2, 0, 1), NCHW -> NHWC, fp32."""
     img = vae_decode_raw(sd, cfg, z).float()
     return torch.clamp((img + 1.0) / 2.0, min=0.0, max=1.0).movedim(1, -1)
+
+
+# ----------------------------------------------------------------------------- VAE encoder
+def vae_encode_moments(sd: SD, cfg: VAEConfig, x):
+    """Encoder.forward + quant_conv, LD.py:3733-3758, 3478-3479. x NCHW in [-1, 1]; returns [B, 2*z, h/8, w/8].
+    Downsample (LD.py:3514-3528) pads (0,1,0,1) and convolves with stride 2, padding 0."""
+    h = _conv(sd, "encoder.conv_in", x, padding=1)
+    for i_level, blocks, has_down in vae_encoder_levels(cfg):
+        for j in range(len(blocks)):
+            h = _vae_res(sd, f"encoder.down.{i_level}.block.{j}", h)
+        if has_down:
+            h = _conv(sd, f"encoder.down.{i_level}.downsample.conv", F.pad(h, (0, 1, 0, 1)), stride=2)
+    h = _vae_res(sd, "encoder.mid.block_1", h)
+    h = _vae_attn(sd, "encoder.mid.attn_1", h)
+    h = _vae_res(sd, "encoder.mid.block_2", h)
+    h = F.silu(_gn(sd, "encoder.norm_out", h, 1e-6))
+    return _conv(sd, "quant_conv", _conv(sd, "encoder.conv_out", h, padding=1))
+
+
+def posterior_sample(moments, noise):
+    """DiagonalGaussianDistribution.__init__/sample, LD.py:166-179: mean + exp(0.5 * clamp(logvar, -30, 20)) * noise."""
+    mean, logvar = torch.chunk(moments, 2, dim=1)
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
+
+
+def vae_encode(sd: SD, cfg: VAEConfig, pixels, noise):
+    """VAE.encode, LD.py:6383-6410: NHWC [0,1] pixels -> movedim -> 2x-1 -> encode -> sample -> fp32 latent.
+    ``noise`` stands for the reference's torch.randn(mean.shape) drawn from the global CPU generator."""
+    x = pixels.movedim(-1, 1) * 2.0 - 1.0
+    return posterior_sample(vae_encode_moments(sd, cfg, x), noise).float()
 
 
 # ----------------------------------------------------------------------------- pipeline

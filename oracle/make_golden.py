@@ -136,11 +136,34 @@ def golden_vae(R):
                os.path.join(OUT, "vae_decode.pt"))
 
 
+def golden_vae_encode(R):
+    """Reference VAE.encode (LD.py:6383) on small images; the posterior noise comes from the global CPU generator
+    exactly as DiagonalGaussianDistribution.sample draws it (LD.py:175-179)."""
+    sd = sd15.seeded_state_dict(sd15.vae_encoder_param_shapes(), VAE_SEED + 1, **INIT)
+    vae = ref_loader.build_ref_vae(R, sd)
+    pixels = torch.rand(2, 32, 48, 3, generator=torch.Generator().manual_seed(6))
+    with torch.inference_mode():
+        torch.manual_seed(2024)
+        z = vae.encode(pixels)
+        moments = vae.first_stage_model.quant_conv(vae.first_stage_model.encoder(pixels.movedim(-1, 1) * 2.0 - 1.0))
+    torch.manual_seed(2024)
+    noise = torch.randn(2, 4, 4, 6)
+    n_enc = sum(p.numel() for n, p in vae.first_stage_model.named_parameters() if n.startswith("encoder."))
+    torch.save(dict(pixels=pixels, z=z.clone(), moments=moments.clone(), noise=noise, global_seed=2024,
+                    vae_seed=VAE_SEED + 1, init=INIT, n_encoder_params=n_enc,
+                    source="VAE.encode LD.py:6383 -> Encoder.forward LD.py:3733 -> DiagonalGaussianRegularizer LD.py:3446"),
+               os.path.join(OUT, "vae_encode.pt"))
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     R = ref_loader.load_reference()
+    if len(sys.argv) > 1:                 # e.g. `make_golden.py vae_encode`: regenerate the named fixtures only
+        for name in sys.argv[1:]:
+            globals()["golden_" + name](R)
+        return
     golden_schedules(R)
     golden_sampler_toy(R)
     tiny = sd15.tiny_unet_config()
@@ -148,6 +171,7 @@ def main():
     golden_samplers(R, model, tiny, hw=16)
     del model
     golden_vae(R)
+    golden_vae_encode(R)
     golden_unet(R, "sd15_lat8", sd15.SD15_UNET, hw=8, b=2)   # real SD1.5 dims, small latent
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -100,11 +100,13 @@ def build_ref_model(R, cfg, sd, dtype=torch.float32):
 
 
 def build_ref_vae(R, sd, dtype=torch.float32):
-    """Reference VAE (LD.py:6282) with our seeded decoder weights (encoder left as built)."""
+    """Reference VAE (LD.py:6282) with our seeded decoder and/or encoder weights (the other half left as built)."""
     vae = R.VAE(sd={}, device=torch.device("cpu"), dtype=dtype)
     fsm = vae.first_stage_model
     own = fsm.state_dict()
-    missing = [k for k in own if (k.startswith("decoder.") or k.startswith("post_quant_conv.")) and k not in sd]
+    halves = (("encoder.", "quant_conv.") if any(k.startswith("encoder.") for k in sd) else ()) + \
+             (("decoder.", "post_quant_conv.") if any(k.startswith("decoder.") for k in sd) else ())
+    missing = [k for k in own if k.startswith(halves) and k not in sd]
     extra = [k for k in sd if k not in own]
     assert not missing and not extra, (missing, extra)
     with torch.no_grad():

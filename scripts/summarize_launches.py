@@ -51,5 +51,5 @@ out = {"kernel": "ldx_gemm_kernel", "launches_per_unet_step": n,
        "dram_bytes_per_launch": (sum(a[2] for a in g) + sum(a[3] for a in g)) / n,
        "share_of_step_kernel_time": sum(a[1] for a in g) / tot,
        "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none, scripts/profile_unet.py --eager-only (per launch, cache flushed between kernels by ncu)"}
-json.dump(out, open("profiles/r01_gemm_traffic.json", "w"), indent=1)
+json.dump(out, open(sys.argv[2] if len(sys.argv) > 2 else "profiles/r01_gemm_traffic.json", "w"), indent=1)
 print(json.dumps(out))

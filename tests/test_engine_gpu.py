@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 if torch.cuda.is_available():
     from lightdiffusion_b200 import sd15
-    from lightdiffusion_b200.engine import UNetEngine, VAEDecoderEngine
+    from lightdiffusion_b200.engine import UNetEngine, VAEDecoderEngine, VAEEncoderEngine
     from oracle import ldm_oracle as O
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
@@ -194,7 +194,7 @@ def vae():
 
 
 # (1, 128) is BASELINE.json config 5: a 1024x1024 decode
-@pytest.mark.parametrize("b,hw", [(1, 16), (2, 32), (1, 64), (1, 128)])
+@pytest.mark.parametrize("b,hw", [(1, 16), (2, 12), (2, 32), (1, 64), (1, 128)])
 def test_vae_decode_parity(vae, b, hw):
     sd, eng = vae
     z = torch.randn(b, 4, hw, hw, generator=torch.Generator().manual_seed(5)).to(DEV)
@@ -207,3 +207,60 @@ def test_vae_decode_parity(vae, b, hw):
     print("vae raw rel", rel(raw, ref_raw), "psnr", psnr(img, ref))
     assert rel(raw, ref_raw) < 5e-3
     assert psnr(img, ref) >= PSNR_MIN
+
+
+# ------------------------------------------------------------------------------------ VAE encoder
+LATENT_TOL = 5e-3       # encoded latent / posterior moments, relative L2, fp16 activations vs the fp32 oracle
+
+
+@pytest.fixture(scope="module")
+def vae_enc():
+    sd = rounded(sd15.seeded_state_dict(sd15.vae_encoder_param_shapes(), 100, bias_std=0.05, norm_jitter=0.1))
+    return sd, VAEEncoderEngine(sd)
+
+
+def test_vae_encode_golden(golden):
+    """Against the reference's own VAE.encode output (tests/golden/vae_encode.pt, same seeded weights)."""
+    g = golden("vae_encode.pt")
+    sd = sd15.seeded_state_dict(sd15.vae_encoder_param_shapes(), g["vae_seed"], **g["init"])
+    eng = VAEEncoderEngine({k: v.to(DEV) for k, v in sd.items()})
+    mom = eng.moments(g["pixels"].to(DEV))
+    z = eng.encode(g["pixels"].to(DEV), noise=g["noise"].to(DEV))
+    print("vae encode golden: moments rel", rel(mom.cpu(), g["moments"]), "z rel", rel(z.cpu(), g["z"]))
+    assert z.shape == g["z"].shape and z.dtype == torch.float32
+    assert rel(mom.cpu(), g["moments"]) < LATENT_TOL
+    assert rel(z.cpu(), g["z"]) < LATENT_TOL
+    # default noise: the same global-generator draw the reference makes
+    torch.manual_seed(g["global_seed"])
+    z2 = eng.encode(g["pixels"].to(DEV))
+    assert torch.equal(z2, z)
+    assert rel(eng.encode(g["pixels"].to(DEV), sample=False).cpu(), g["moments"][:, :4]) < LATENT_TOL
+
+
+# (1, 1024, 1024) is BASELINE.json config 5 (img2img at 1024x1024)
+@pytest.mark.parametrize("b,h,w", [(1, 64, 64), (2, 128, 192), (1, 512, 512), (1, 1024, 1024)])
+def test_vae_encode_parity(vae_enc, b, h, w):
+    sd, eng = vae_enc
+    g = torch.Generator().manual_seed(7)
+    # smooth image + noise, in [0,1]
+    pix = (torch.rand(b, h // 8, w // 8, 3, generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2) * 0.8
+           + 0.2 * torch.rand(b, h, w, 3, generator=g)).to(DEV)
+    noise = torch.randn(b, 4, h // 8, w // 8, generator=g).to(DEV)
+    z = eng.encode(pix, noise=noise)
+    mom = eng.moments(pix)
+    with torch.inference_mode():
+        x16 = (pix.movedim(-1, 1) * 2.0 - 1.0).half().float()
+        ref_mom = O.vae_encode_moments(sd, sd15.SD15_VAE, x16)
+        ref = O.posterior_sample(ref_mom, noise)
+    print("vae encode rel: moments", rel(mom, ref_mom), "z", rel(z, ref))
+    assert z.shape == (b, 4, h // 8, w // 8)
+    assert rel(mom, ref_mom) < LATENT_TOL
+    assert rel(z, ref) < LATENT_TOL
+
+
+def test_vae_encode_rejects_bad_sizes(vae_enc):
+    _, eng = vae_enc
+    with pytest.raises(Exception):
+        eng.encode(torch.zeros(1, 60, 64, 3, device=DEV))
+    with pytest.raises(Exception):
+        eng.encode(torch.zeros(64, 64, 3, device=DEV))

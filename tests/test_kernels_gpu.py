@@ -186,6 +186,18 @@ def test_conv3x3_stride2(B, H, W, C):
     assert rel(out.permute(0, 3, 1, 2), ref) < 1e-3
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 64, 48, 128), (1, 32, 32, 256), (2, 16, 24, 512)])
+def test_conv3x3_stride2_pad_end(B, H, W, C):
+    """The VAE encoder's Downsample (LD.py:3514-3528): F.pad(x, (0,1,0,1)) then a stride-2, padding-0 conv."""
+    x = h16(rnd(B, H, W, C, seed=124))
+    w = h16(rnd(C, C, 3, 3, seed=125, scale=(9 * C) ** -0.5))
+    bias = rnd(C, seed=126)
+    out = torch.empty(B, H // 2, W // 2, C, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.conv3x3_s2_desc(x, K.pack_conv3x3(w), out, pad_end=True, bias=bias))
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.float(), bias, stride=2)
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-3
+
+
 @pytest.mark.parametrize("B,H,W,C", [(2, 8, 8, 1280), (2, 16, 16, 1280), (2, 32, 32, 640), (1, 64, 64, 128)])
 def test_upsample_conv_folded(B, H, W, C):
     x = h16(rnd(B, H, W, C, seed=27))
@@ -311,11 +323,38 @@ def test_vae_post_and_softmax():
     img = torch.empty(2 * 32 * 32, 3, device=DEV)
     L.check(L.lib().ldx_vae_postprocess(dec.data_ptr(), 8, img.data_ptr(), dec.shape[0], 0))
     assert torch.equal(img, torch.clamp((dec[:, :3].float() + 1.0) / 2.0, 0.0, 1.0))
-    s = rnd(300, 4096, seed=63) * 20
-    ref = torch.softmax(s * 0.0442, -1)
-    pm = torch.empty(300, 4096, dtype=torch.float16, device=DEV)
-    L.check(L.lib().ldx_softmax_rows(s.data_ptr(), 4096, pm.data_ptr(), 4096, 300, 4096, 0.0442, 0))
-    assert rel(pm, ref) < 1e-3
+    # 1024 .. 16384 take the register-resident kernel, 1000 / 4100 the generic one; ld > n checks the row strides
+    for rows, n, ld in ((300, 4096, 4096), (37, 16384, 16384), (50, 1024, 2048), (20, 8192, 8192), (33, 1000, 1000),
+                        (9, 4100, 4104)):
+        s = rnd(rows, ld, seed=63 + rows) * 20
+        s[:, 3] += 40.0                      # a dominant score per row
+        ref = torch.softmax(s[:, :n] * 0.0442, -1)
+        pm = torch.zeros(rows, ld, dtype=torch.float16, device=DEV)
+        L.check(L.lib().ldx_softmax_rows(s.data_ptr(), ld, pm.data_ptr(), ld, rows, n, 0.0442, 0))
+        assert rel(pm[:, :n], ref) < 1e-3, (rows, n)
+        assert (pm[:, :n].float().sum(-1) - 1).abs().max() < 2e-3
+        assert not pm[:, n:].any()
+
+
+def test_vae_preprocess_and_posterior_sample():
+    from oracle import ldm_oracle as O
+    for npix in (2 * 24 * 40, 1024 * 1024 + 3):       # the second exceeds one wave of the capped grid
+        pix = torch.rand(npix, 3, device=DEV)
+        out = torch.full((npix, 8), 7.0, dtype=torch.float16, device=DEV)
+        L.check(L.lib().ldx_vae_preprocess(pix.data_ptr(), out.data_ptr(), npix, 0))
+        assert torch.equal(out[:, :3], (pix * 2.0 - 1.0).half())
+        assert not out[:, 3:].any()
+    assert L.lib().ldx_vae_preprocess(None, out.data_ptr(), 4, 0) != 0
+    for b, zc, h, w in ((3, 4, 5, 7), (2, 4, 256, 320)):
+        mom = rnd(b, h, w, 2 * zc, seed=64) * 3
+        mom[0, 0, 0, zc:] = torch.tensor([-50.0, 50.0, 0.0, 1.0], device=DEV)     # exercises the logvar clamp
+        noise = rnd(b, zc, h, w, seed=65)
+        z = torch.empty(b, zc, h, w, device=DEV)
+        L.check(L.lib().ldx_vae_sample_posterior(mom.data_ptr(), noise.data_ptr(), z.data_ptr(), b, zc, h * w, 0))
+        ref = O.posterior_sample(mom.permute(0, 3, 1, 2), noise)
+        assert torch.allclose(z, ref, rtol=1e-5, atol=1e-6)
+        L.check(L.lib().ldx_vae_sample_posterior(mom.data_ptr(), None, z.data_ptr(), b, zc, h * w, 0))
+        assert torch.equal(z, mom.permute(0, 3, 1, 2)[:, :zc])
 
 
 def test_sampler_step_kernels():

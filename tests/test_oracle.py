@@ -92,3 +92,21 @@ def test_vae_decode(golden):
         img = O.vae_decode(sd, sd15.SD15_VAE, g["z"])
     assert img.shape == g["image"].shape == (2, 64, 64, 3)
     assert rel(img, g["image"]) < 2e-5
+
+
+def test_vae_encode(golden):
+    """The encoder restatement against the reference's VAE.encode output (fixture from oracle/make_golden.py)."""
+    g = golden("vae_encode.pt")
+    shapes = sd15.vae_encoder_param_shapes()
+    assert sum(torch.Size(s).numel() for k, s in shapes.items() if k.startswith("encoder.")) == g["n_encoder_params"]
+    sd = sd15.seeded_state_dict(shapes, g["vae_seed"], **g["init"])
+    with torch.inference_mode():
+        mom = O.vae_encode_moments(sd, sd15.SD15_VAE, g["pixels"].movedim(-1, 1) * 2.0 - 1.0)
+        z = O.vae_encode(sd, sd15.SD15_VAE, g["pixels"], g["noise"])
+    assert mom.shape == g["moments"].shape == (2, 8, 4, 6)
+    assert rel(mom, g["moments"]) < 2e-5
+    assert z.shape == g["z"].shape == (2, 4, 4, 6)
+    assert rel(z, g["z"]) < 2e-5
+    # the reference draws the posterior noise from the global CPU generator (LD.py:175-179)
+    torch.manual_seed(g["global_seed"])
+    assert torch.equal(torch.randn(2, 4, 4, 6), g["noise"])
