@@ -170,6 +170,13 @@ int ldx_vae_preprocess(const float* pixels, void* out, int64_t npix, ldx_stream_
  * fp32 NCHW. */
 int ldx_vae_sample_posterior(const float* moments, const float* noise, float* z, int b, int zc, int64_t hw,
                              ldx_stream_t stream);
+/* One axis of bislerp (LD.py:429-518, the hires-fix latent upscale of LatentUpscale, LD.py:6639-6654): for the
+ * fp32 tensor viewed as [n, c, outer, len_old, inner], out[n, :, o, j, i] = slerp(in[n, :, o, idx1[j], i],
+ * in[n, :, o, idx2[j], i], ratio[j]) over the channel vectors, j < len_new, with the reference's edge cases (zero
+ * norms, dot > 1 - 1e-5 -> first vector, dot < -1 + 1e-5 -> lerp).  ratio / idx1 / idx2 are device arrays of
+ * len_new entries (generate_bilinear_data, LD.py:464-485).  1 <= c <= 16. */
+int ldx_bislerp_axis(const float* in, float* out, const float* ratio, const int32_t* idx1, const int32_t* idx2,
+                     int n, int c, int64_t outer, int len_old, int len_new, int64_t inner, ldx_stream_t stream);
 /* out[r, :] = softmax(scale * s[r, :]): fp32 scores in, fp16 probabilities out (the VAE AttnBlock's
  * single-head d=512 attention runs as GEMM / softmax / GEMM, LD.py:3591-3602). */
 int ldx_softmax_rows(const float* s, int64_t lds, void* out, int64_t ldo, int64_t rows, int n, float scale,

@@ -554,6 +554,61 @@ __global__ void vae_sample_kernel(const float* __restrict__ mom, const float* __
   }
 }
 
+// One axis of bislerp (LD.py:429-518): spherical interpolation of the C-channel vectors at positions i1[j], i2[j]
+// of the `len_old` axis with ratio r[j], for the tensor viewed as [n, C, outer, len, inner] (fp32).  The width pass
+// has inner = 1, the height pass outer = 1.  One thread per output vector; C <= BISLERP_MAX_C in registers.
+static constexpr int BISLERP_MAX_C = 16;
+__global__ void bislerp_axis_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ ratio,
+                                    const int* __restrict__ i1, const int* __restrict__ i2, int64_t total, int C,
+                                    int64_t outer, int len_old, int len_new, int64_t inner) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t in_ = t % inner;
+    const int j = (int)((t / inner) % len_new);
+    const int64_t o = (t / (inner * len_new)) % outer;
+    const int64_t n = t / (inner * len_new * outer);
+    const int64_t cs_in = outer * len_old * inner, cs_out = outer * len_new * inner;
+    const float* a = in + n * C * cs_in + (o * len_old + i1[j]) * inner + in_;
+    const float* b = in + n * C * cs_in + (o * len_old + i2[j]) * inner + in_;
+    float* d = out + n * C * cs_out + (o * len_new + j) * inner + in_;
+    const float r = ratio[j];
+    float v1[BISLERP_MAX_C], v2[BISLERP_MAX_C];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int c = 0; c < BISLERP_MAX_C; ++c)
+      if (c < C) {
+        v1[c] = a[c * cs_in];
+        v2[c] = b[c * cs_in];
+        s1 = fmaf(v1[c], v1[c], s1);
+        s2 = fmaf(v2[c], v2[c], s2);
+      }
+    const float n1 = sqrtf(s1), n2 = sqrtf(s2);
+    // zero vectors normalise to zero (LD.py:444-446)
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < BISLERP_MAX_C; ++c)
+      if (c < C) dot += (n1 == 0.f ? 0.f : v1[c] / n1) * (n2 == 0.f ? 0.f : v2[c] / n2);
+    if (dot > 1.0f - 1e-5f) {                       // same direction: the first vector
+#pragma unroll
+      for (int c = 0; c < BISLERP_MAX_C; ++c)
+        if (c < C) d[c * cs_out] = v1[c];
+    } else if (dot < 1e-5f - 1.0f) {                // polar opposites: plain lerp
+#pragma unroll
+      for (int c = 0; c < BISLERP_MAX_C; ++c)
+        if (c < C) d[c * cs_out] = v1[c] * (1.0f - r) + v2[c] * r;
+    } else {
+      const float omega = acosf(dot), so = sinf(omega);
+      const float w1 = sinf((1.0f - r) * omega) / so, w2 = sinf(r * omega) / so;
+      const float nm = n1 * (1.0f - r) + n2 * r;
+#pragma unroll
+      for (int c = 0; c < BISLERP_MAX_C; ++c)
+        if (c < C) {
+          const float u1 = n1 == 0.f ? 0.f : v1[c] / n1, u2 = n2 == 0.f ? 0.f : v2[c] / n2;
+          d[c * cs_out] = (w1 * u1 + w2 * u2) * nm;
+        }
+    }
+  }
+}
+
 // row softmax for n = NV * 1024 (the VAE AttnBlock's 4096 / 16384 tokens): the row lives in registers, so the
 // fp32 scores are read once (16-byte loads) and the fp16 probabilities written once (8-byte stores)
 template <int NV>
@@ -856,6 +911,18 @@ extern "C" int ldx_vae_sample_posterior(const float* moments, const float* noise
   ldx_generic_op_t op = make_op(LDX_OP_VAE_SAMPLE);
   op.p[0] = moments; op.p[1] = noise; op.p[2] = z; op.l[0] = (int64_t)b * zc * hw; op.l[1] = hw; op.i[0] = zc;
   return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_bislerp_axis(const float* in, float* out, const float* ratio, const int32_t* idx1, const int32_t* idx2,
+                                int n, int c, int64_t outer, int len_old, int len_new, int64_t inner, ldx_stream_t stream) {
+  LDX_CHECK_ARG(in && out && ratio && idx1 && idx2, "bislerp_axis: null");
+  LDX_CHECK_ARG(n > 0 && c > 0 && c <= BISLERP_MAX_C && outer > 0 && len_old > 0 && len_new > 0 && inner > 0,
+                "bislerp_axis: bad shape (1 <= C <= 16)");
+  const int64_t total = (int64_t)n * outer * len_new * inner;
+  bislerp_axis_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(in, out, ratio, idx1, idx2, total, c, outer, len_old,
+                                                                      len_new, inner);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
 }
 
 extern "C" int ldx_softmax_rows(const float* s, int64_t lds, void* out, int64_t ldo, int64_t rows, int n, float scale,

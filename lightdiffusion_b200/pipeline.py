@@ -13,7 +13,8 @@ from typing import Optional
 import torch
 
 from . import _lib as L
-from .engine import UNetEngine, VAEDecoderEngine, sigma_tables
+from .engine import UNetEngine, VAEDecoderEngine, VAEEncoderEngine, sigma_tables
+from .upscale import bislerp
 from .samplers import dpmpp2m_coefficients, get_ancestral_step, get_sigmas_karras
 
 LATENT_SCALE = 0.18215          # SD15 latent format (LD.py:137-139)
@@ -48,8 +49,8 @@ class Txt2ImgPipeline:
     """Resident UNet + VAE decoder on one GPU.  ``sample`` returns the latent (already / 0.18215, like
     the reference's sample()); ``generate`` also decodes to [b, 8h, 8w, 3] fp32 images in [0, 1]."""
 
-    def __init__(self, unet: UNetEngine, vae: Optional[VAEDecoderEngine]):
-        self.unet, self.vae = unet, vae
+    def __init__(self, unet: UNetEngine, vae: Optional[VAEDecoderEngine], vae_encoder: Optional[VAEEncoderEngine] = None):
+        self.unet, self.vae, self.vae_encoder = unet, vae, vae_encoder
         self.sigma_max = float(unet.sigmas[-1])
         self.gpu_launches = 0            # kernels of ours launched by the last call
 
@@ -111,6 +112,39 @@ class Txt2ImgPipeline:
         img = self.vae.decode(z)
         self.gpu_launches += self.vae.plan(*[z.shape[0], z.shape[2], z.shape[3]]).prog.num_launches
         return z, img
+
+
+    @torch.no_grad()
+    def img2img(self, pixels, noise, cond, uncond, cfg_scale, steps: int, denoise: float, scheduler="normal",
+                sampler="euler_ancestral", posterior_noise=None, noise_sampler=None):
+        """VAEEncode (VAE.encode, LD.py:6383-6410) -> common_ksampler with denoise < 1 (KSampler1.set_steps,
+        LD.py:3097-3104: the last steps+1 sigmas of int(steps/denoise)) -> VAEDecode: the img2img / hires-fix second
+        pass.  pixels fp32 [b, H, W, 3] in [0,1]; returns (latent, image)."""
+        if self.vae_encoder is None:
+            raise L.LdxError("img2img needs a VAEEncoderEngine")
+        latent = self.vae_encoder.encode(pixels.to(self.unet.dev, torch.float32), noise=posterior_noise)
+        enc_launches = self.vae_encoder.plan(*pixels.shape[:3]).prog.num_launches + 1
+        sig = sigmas_for_denoise(scheduler, steps, denoise)
+        z, img = self.generate(noise, cond, uncond, cfg_scale, sig, sampler, latent, noise_sampler)
+        self.gpu_launches += enc_launches
+        return z, img
+
+
+    @torch.no_grad()
+    def hires_fix(self, noise, noise2, cond, uncond, cfg_scale, sigmas, sampler="dpmpp_2m", scale: int = 2,
+                  steps2: int = 10, cfg2: float = 8.0, denoise2: float = 0.45, scheduler2="normal",
+                  sampler2="euler_ancestral", noise_sampler=None):
+        """The reference's two-pass flow (LD.py:10048-10080): base-resolution sample -> LatentUpscale with bislerp to
+        ``scale`` x (LD.py:6639-6654) -> second KSampler pass (10 Euler-ancestral steps, 'normal' schedule, denoise
+        0.45, cfg 8) seeded by ``noise2`` -> VAE decode.  Returns (base latent, final latent, image)."""
+        z1 = self.sample(noise, cond, uncond, cfg_scale, sigmas, sampler)
+        launches = self.gpu_launches
+        up = bislerp(z1, z1.shape[3] * scale, z1.shape[2] * scale)
+        launches += 2
+        z2, img = self.generate(noise2, cond, uncond, cfg2, sigmas_for_denoise(scheduler2, steps2, denoise2), sampler2,
+                                up, noise_sampler)
+        self.gpu_launches += launches
+        return z1, z2, img
 
 
 def shard_range(n_items: int, rank: int, world: int):

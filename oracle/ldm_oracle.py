@@ -364,6 +364,48 @@ def vae_encode(sd: SD, cfg: VAEConfig, pixels, noise):
     return posterior_sample(vae_encode_moments(sd, cfg, x), noise).float()
 
 
+# ----------------------------------------------------------------------------- latent upscale
+def _slerp(b1, b2, r):
+    """slerp of LD.py:430-461 on [N, C] batches with ratio r [N, 1]."""
+    n1, n2 = torch.norm(b1, dim=-1, keepdim=True), torch.norm(b2, dim=-1, keepdim=True)
+    u1 = torch.where(n1 == 0.0, torch.zeros_like(b1), b1 / n1)
+    u2 = torch.where(n2 == 0.0, torch.zeros_like(b2), b2 / n2)
+    dot = (u1 * u2).sum(1)
+    omega = torch.acos(dot)
+    so = torch.sin(omega)
+    res = (torch.sin((1.0 - r.squeeze(1)) * omega) / so).unsqueeze(1) * u1 + (torch.sin(r.squeeze(1) * omega) / so).unsqueeze(1) * u2
+    res = res * (n1 * (1.0 - r) + n2 * r)
+    res = torch.where((dot > 1 - 1e-5).unsqueeze(1), b1, res)
+    return torch.where((dot < 1e-5 - 1).unsqueeze(1), b1 * (1.0 - r) + b2 * r, res)
+
+
+def _bilinear_table(length_old: int, length_new: int):
+    """generate_bilinear_data, LD.py:464-485."""
+    c1 = F.interpolate(torch.arange(length_old, dtype=torch.float32).reshape(1, 1, 1, -1), size=(1, length_new), mode="bilinear")
+    ratios = (c1 - c1.floor()).reshape(-1)
+    c2 = torch.arange(length_old, dtype=torch.float32).reshape(1, 1, 1, -1) + 1
+    c2[:, :, :, -1] -= 1
+    c2 = F.interpolate(c2, size=(1, length_new), mode="bilinear")
+    return ratios, c1.to(torch.int64).reshape(-1), c2.to(torch.int64).reshape(-1)
+
+
+def bislerp(samples, width: int, height: int):
+    """bislerp, LD.py:429-518: slerp of the channel vectors along the width, then the height."""
+    x = samples.float()
+    n, c, h, w = x.shape
+    r, i1, i2 = (t.to(x.device) for t in _bilinear_table(w, width))
+    a = x[:, :, :, i1].movedim(1, -1).reshape(-1, c)
+    b = x[:, :, :, i2].movedim(1, -1).reshape(-1, c)
+    rr = r.reshape(1, 1, -1).expand(n, h, -1).reshape(-1, 1)
+    x = _slerp(a, b, rr).reshape(n, h, width, c).movedim(-1, 1)
+    r, i1, i2 = (t.to(x.device) for t in _bilinear_table(h, height))
+    a = x[:, :, i1, :].movedim(1, -1).reshape(-1, c)
+    b = x[:, :, i2, :].movedim(1, -1).reshape(-1, c)
+    rr = r.reshape(1, -1, 1).expand(n, -1, width).reshape(-1, 1)
+    x = _slerp(a, b, rr).reshape(n, height, width, c).movedim(-1, 1)
+    return x.to(samples.dtype)
+
+
 # ----------------------------------------------------------------------------- pipeline
 LATENT_SCALE = 0.18215      # SD15 latent format, LD.py:137-139
 
@@ -392,3 +434,19 @@ def txt2img(unet_sd: SD, ucfg: UNetConfig, vae_sd: SD, vcfg: VAEConfig, noise, c
     """common_ksampler (LD.py:6657) followed by VAEDecode (LD.py:6581). Returns (latent, image NHWC)."""
     z = sample_latent(unet_sd, ucfg, noise, cond, uncond, cfg_scale, sigmas, sampler, latent, noise_sampler)
     return z, vae_decode(vae_sd, vcfg, z)
+
+
+def img2img(unet_sd: SD, ucfg: UNetConfig, enc_sd: SD, dec_sd: SD, vcfg: VAEConfig, pixels, posterior_noise, noise,
+            cond, uncond, cfg_scale: float, sigmas, sampler: str = "euler_ancestral", noise_sampler=None):
+    """VAEEncode (LD.py:6383) -> common_ksampler with a non-empty latent (LD.py:6657) -> VAEDecode (LD.py:6581)."""
+    latent = vae_encode(enc_sd, vcfg, pixels, posterior_noise)
+    return txt2img(unet_sd, ucfg, dec_sd, vcfg, noise, cond, uncond, cfg_scale, sigmas, sampler, latent, noise_sampler)
+
+
+def hires_fix(unet_sd: SD, ucfg: UNetConfig, dec_sd: SD, vcfg: VAEConfig, noise, noise2, cond, uncond, cfg_scale: float,
+              sigmas, sigmas2, cfg2: float = 8.0, scale: int = 2, noise_sampler=None):
+    """LD.py:10048-10080: sample -> LatentUpscale(bislerp, 2x) -> euler_ancestral second pass -> VAEDecode."""
+    z1 = sample_latent(unet_sd, ucfg, noise, cond, uncond, cfg_scale, sigmas, "dpmpp_2m")
+    up = bislerp(z1, z1.shape[3] * scale, z1.shape[2] * scale)
+    z2, img = txt2img(unet_sd, ucfg, dec_sd, vcfg, noise2, cond, uncond, cfg2, sigmas2, "euler_ancestral", up, noise_sampler)
+    return z1, z2, img

@@ -155,6 +155,24 @@ def golden_vae_encode(R):
                os.path.join(OUT, "vae_encode.pt"))
 
 
+def golden_bislerp(R):
+    """Reference bislerp (LD.py:429) on small latents: 2x, a non-integer ratio, a downscale, and the slerp edge cases
+    (zero vectors, parallel and opposite neighbours)."""
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 4, 8, 12, generator=g)
+    x[0, :, 0, 0] = 0.0                              # zero-norm vector
+    x[0, :, 1, 1] = x[0, :, 1, 0] * 2.5              # parallel neighbours along w
+    x[0, :, 2, 3] = -x[0, :, 2, 2]                   # opposite neighbours along w
+    x[1, :, 4, 5] = x[1, :, 3, 5] * 0.5              # parallel neighbours along h
+    x[1, :, 6, 7] = -1.5 * x[1, :, 5, 7]             # opposite neighbours along h
+    cases = {}
+    for name, (w, h) in dict(x2=(24, 16), x1p5=(18, 12), odd=(17, 11), down=(6, 4), same=(12, 8)).items():
+        cases[name] = dict(width=w, height=h, out=R.bislerp(x.clone(), w, h).clone())
+    x16 = torch.randn(1, 16, 5, 6, generator=g)
+    cases["c16"] = dict(width=9, height=10, out=R.bislerp(x16.clone(), 9, 10).clone(), x=x16)
+    torch.save(dict(x=x, cases=cases, source="bislerp LD.py:429-518"), os.path.join(OUT, "bislerp.pt"))
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -172,6 +190,7 @@ def main():
     del model
     golden_vae(R)
     golden_vae_encode(R)
+    golden_bislerp(R)
     golden_unet(R, "sd15_lat8", sd15.SD15_UNET, hw=8, b=2)   # real SD1.5 dims, small latent
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

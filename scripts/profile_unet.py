@@ -4,17 +4,25 @@ import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from lightdiffusion_b200 import sd15
-from lightdiffusion_b200.engine import UNetEngine, VAEDecoderEngine
+from lightdiffusion_b200.engine import UNetEngine, VAEDecoderEngine, VAEEncoderEngine
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=8)
 ap.add_argument("--latent", type=int, default=64)
 ap.add_argument("--eager-only", action="store_true")
 ap.add_argument("--vae", action="store_true")
+ap.add_argument("--vae-encode", action="store_true", help="--latent is the latent size; the image is 8x larger")
 ap.add_argument("--out", default="gpurun_out/unet_ops.json")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
-if args.vae:
+if args.vae_encode:
+    sd = sd15.seeded_state_dict(sd15.vae_encoder_param_shapes(), 100, dtype=torch.float16, device=dev)
+    eng = VAEEncoderEngine(sd, device=dev)
+    plan = eng.plan(args.batch, args.latent * 8, args.latent * 8)
+    plan.use_graph = False
+    plan.run(torch.rand(args.batch, args.latent * 8, args.latent * 8, 3, device=dev),
+             torch.randn(args.batch, 4, args.latent, args.latent, device=dev))
+elif args.vae:
     sd = sd15.seeded_state_dict(sd15.vae_decoder_param_shapes(), 99, dtype=torch.float16, device=dev)
     eng = VAEDecoderEngine(sd, device=dev)
     plan = eng.plan(args.batch, args.latent, args.latent)

@@ -357,6 +357,30 @@ def test_vae_preprocess_and_posterior_sample():
         assert torch.equal(z, mom.permute(0, 3, 1, 2)[:, :zc])
 
 
+def test_bislerp_matches_reference_golden(golden):
+    """ldx_bislerp_axis through the reference-signature wrapper, against the reference's outputs (LD.py:429)."""
+    from lightdiffusion_b200 import upscale as U
+    g = golden("bislerp.pt")
+    for name, c in g["cases"].items():
+        x = c.get("x", g["x"]).to(DEV)
+        out = U.common_upscale(x, c["width"], c["height"], "bislerp", "disabled")
+        assert out.shape == c["out"].shape and out.dtype == x.dtype, name
+        assert torch.allclose(out.cpu(), c["out"], rtol=1e-4, atol=1e-5), (name, (out.cpu() - c["out"]).abs().max())
+    # hires-fix bridge shape: 64x64 -> 128x128 latents, against the restatement
+    from oracle import ldm_oracle as O
+    x = rnd(3, 4, 64, 64, seed=90)
+    got, ref = U.bislerp(x, 128, 128), O.bislerp(x, 128, 128)
+    bad = ((got - ref).abs() > 1e-5 + 1e-4 * ref.abs()).float().mean().item()
+    print("bislerp 64->128: rel", rel(got, ref), "max abs", (got - ref).abs().max().item(), "outside tol", bad)
+    # near-opposite neighbours (sin(omega) -> 0) amplify the last-ulp differences of acos/sin between CUDA and ATen
+    assert rel(got, ref) < 1e-5 and bad < 1e-4
+    assert U.bislerp(x.half(), 96, 80).dtype == torch.float16
+    with pytest.raises(Exception):
+        U.bislerp(x.cpu(), 128, 128)          # no CPU fallback
+    with pytest.raises(Exception):
+        U.bislerp(rnd(1, 17, 4, 4, seed=91), 8, 8)   # more than 16 channels
+
+
 def test_sampler_step_kernels():
     n = 8 * 4 * 64 * 64
     x, d, od, nz = (rnd(n, seed=70 + i) for i in range(4))

@@ -110,3 +110,13 @@ def test_vae_encode(golden):
     # the reference draws the posterior noise from the global CPU generator (LD.py:175-179)
     torch.manual_seed(g["global_seed"])
     assert torch.equal(torch.randn(2, 4, 4, 6), g["noise"])
+
+
+def test_bislerp(golden):
+    """The bislerp restatement against the reference's own outputs, edge cases included."""
+    g = golden("bislerp.pt")
+    for name, c in g["cases"].items():
+        x = c.get("x", g["x"])
+        out = O.bislerp(x, c["width"], c["height"])
+        assert out.shape == c["out"].shape, name
+        assert torch.allclose(out, c["out"], rtol=1e-5, atol=1e-6), name

@@ -11,7 +11,7 @@ if torch.cuda.is_available():
     from lightdiffusion_b200 import ops as X
     from lightdiffusion_b200 import samplers as S
     from lightdiffusion_b200 import sd15
-    from lightdiffusion_b200.engine import UNetEngine, VAEDecoderEngine
+    from lightdiffusion_b200.engine import UNetEngine, VAEDecoderEngine, VAEEncoderEngine
     from lightdiffusion_b200.pipeline import Txt2ImgPipeline, calculate_sigmas, sigmas_for_denoise
     from oracle import ldm_oracle as O
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -147,6 +147,56 @@ def test_small_pipeline_matches_oracle(small_pipe, sampler, sched, steps, denois
                              sig.to(DEV), sampler, latent, noise_sampler=lambda s, sn: next(it2))
     print(sampler, "latent rel", rel(z, zr), "psnr", psnr(img, imgr))
     assert rel(z, zr) < 2e-2          # fp16 per-step errors (<= 2e-3 each, x7 CFG) compound over the trajectory
+    assert psnr(img, imgr) >= 40.0
+
+
+def test_small_img2img_matches_oracle(small_pipe):
+    """encode -> 0.45-denoise Euler-ancestral pass -> decode (the hires-fix / img2img second pass, config 4/5 shape)."""
+    cfg, usd, vsd, pipe0 = small_pipe
+    esd = rounded(sd15.seeded_state_dict(sd15.vae_encoder_param_shapes(), 100, bias_std=0.05, norm_jitter=0.1))
+    pipe = Txt2ImgPipeline(pipe0.unet, pipe0.vae, VAEEncoderEngine(esd))
+    b, hw, steps = 2, 16, 4
+    g = torch.Generator().manual_seed(21)
+    pixels = torch.rand(b, hw * 8, hw * 8, 3, generator=g).to(DEV)
+    pnoise = torch.randn(b, 4, hw, hw, generator=g).to(DEV)
+    noise = torch.randn(b, 4, hw, hw, generator=g).to(DEV)
+    cond, uncond = _conds(b, cfg.context_dim, 6)
+    noises = [torch.randn(b, 4, hw, hw, generator=torch.Generator().manual_seed(200 + i)).to(DEV) for i in range(steps)]
+    it1, it2 = iter(noises), iter(noises)
+    z, img = pipe.img2img(pixels, noise, cond, uncond, 8.0, steps, 0.45, posterior_noise=pnoise,
+                          noise_sampler=lambda s, sn: next(it1))
+    assert pipe.gpu_launches > 0
+    sig = sigmas_for_denoise("normal", steps, 0.45)
+    with torch.inference_mode():
+        zr, imgr = O.img2img(usd, cfg, esd, vsd, sd15.SD15_VAE, pixels, pnoise, noise, cond.half().float(),
+                             uncond.half().float(), 8.0, sig.to(DEV), "euler_ancestral",
+                             noise_sampler=lambda s, sn: next(it2))
+    print("img2img latent rel", rel(z, zr), "psnr", psnr(img, imgr))
+    assert rel(z, zr) < 2e-2
+    assert psnr(img, imgr) >= 40.0
+    with pytest.raises(Exception):
+        pipe0.img2img(pixels, noise, cond, uncond, 8.0, steps, 0.45)     # no encoder attached
+
+
+def test_small_hires_fix_matches_oracle(small_pipe):
+    """base pass -> bislerp 2x -> Euler-ancestral second pass -> decode (BASELINE config 4's flow) on the small UNet."""
+    cfg, usd, vsd, pipe = small_pipe
+    b, hw, steps2 = 1, 8, 4
+    g = torch.Generator().manual_seed(33)
+    noise = torch.randn(b, 4, hw, hw, generator=g).to(DEV)
+    noise2 = torch.randn(b, 4, 2 * hw, 2 * hw, generator=g).to(DEV)
+    cond, uncond = _conds(b, cfg.context_dim, 8)
+    sig = calculate_sigmas("karras", 5)
+    noises = [torch.randn(b, 4, 2 * hw, 2 * hw, generator=torch.Generator().manual_seed(300 + i)).to(DEV) for i in range(steps2)]
+    it1, it2 = iter(noises), iter(noises)
+    z1, z2, img = pipe.hires_fix(noise, noise2, cond, uncond, 7.0, sig, steps2=steps2, noise_sampler=lambda s, sn: next(it1))
+    assert img.shape == (b, 16 * hw, 16 * hw, 3) and pipe.gpu_launches > 0
+    with torch.inference_mode():
+        r1, r2, imgr = O.hires_fix(usd, cfg, vsd, sd15.SD15_VAE, noise, noise2, cond.half().float(), uncond.half().float(),
+                                   7.0, sig.to(DEV), sigmas_for_denoise("normal", steps2, 0.45).to(DEV),
+                                   noise_sampler=lambda s, sn: next(it2))
+    print("hires-fix latent rel", rel(z1, r1), rel(z2, r2), "psnr", psnr(img, imgr))
+    assert rel(z1, r1) < 2e-2 and rel(z2, r2) < 2e-2
     assert psnr(img, imgr) >= 40.0
 
 
