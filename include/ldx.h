@@ -64,6 +64,7 @@ typedef struct {
 #define LDX_EPI_GEGLU 2     /* out[:, j] = a * gelu_erf(gate)     (GEGLU.forward, LD.py:4513-4515);
                                weight rows must be interleaved by ldx_pack_geglu; out has N/2 columns */
 #define LDX_EPI_OUT_F32 4   /* store fp32 instead of fp16 */
+#define LDX_EPI_QUICK_GELU 16 /* out = x * sigmoid(1.702 x), x = acc + bias  (CLIPMLP quick_gelu, LD.py:4296-4321) */
 #define LDX_EPI_ROWNORM 8   /* LayerNorm of the A rows folded into the GEMM (F.layer_norm LD.py:2403 followed by
                                F.linear LD.py:2368): with w' = w * gamma (caller-folded), gsum[n] = sum_k w'[n,k] and
                                bias' = bias + w @ beta,  out = rstd_r * (acc - mean_r * gsum[n]) + bias'[n], where
@@ -136,6 +137,11 @@ int ldx_layer_norm(const void* x, int64_t ldx_, int rows, int C, float eps, cons
 int ldx_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                   void* o, int64_t ldo, int B, int Nq, int Nk, int heads, int d, ldx_stream_t stream);
 
+/* The same with the CLIP text tower's causal mask (CLIPTextModel_.forward, LD.py:4443-4449: -inf above the
+ * diagonal, i.e. key j attends to query i only for j <= i), self-attention over N tokens; d = 64, N <= 256. */
+int ldx_attention_causal(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                         void* o, int64_t ldo, int B, int N, int heads, int d, ldx_stream_t stream);
+
 /* ------------------------------------------------------------------ data movement / small ops */
 /* x fp32 NCHW [B,C,H,W] * (1/sqrt(sigma_b^2+1)) -> fp16 NHWC [B,H,W,Cpad], extra channels zero
  * (EPS.calculate_input LD.py:1259-1261 + the .to(dtype) of apply_model LD.py:5842). sigma may be NULL. */
@@ -177,6 +183,10 @@ int ldx_vae_sample_posterior(const float* moments, const float* noise, float* z,
  * len_new entries (generate_bilinear_data, LD.py:464-485).  1 <= c <= 16. */
 int ldx_bislerp_axis(const float* in, float* out, const float* ratio, const int32_t* idx1, const int32_t* idx2,
                      int n, int c, int64_t outer, int len_old, int len_new, int64_t inner, ldx_stream_t stream);
+/* CLIPEmbeddings.forward (LD.py:4409-4410): out[r, :] = token_embedding[tokens[r], :] + position_embedding[r % T, :];
+ * fp32 tables [vocab, C] / [T, C], int32 token ids (the caller guarantees 0 <= id < vocab), fp16 out [rows, ldo]. */
+int ldx_clip_embed(const int32_t* tokens, const float* tok_emb, const float* pos_emb, void* out, int64_t ldo,
+                   int rows, int T, int C, ldx_stream_t stream);
 /* out[r, :] = softmax(scale * s[r, :]): fp32 scores in, fp16 probabilities out (the VAE AttnBlock's
  * single-head d=512 attention runs as GEMM / softmax / GEMM, LD.py:3591-3602). */
 int ldx_softmax_rows(const float* s, int64_t lds, void* out, int64_t ldo, int64_t rows, int n, float scale,
@@ -200,6 +210,8 @@ enum {
   LDX_OP_GEMM = 1, LDX_OP_GROUP_NORM = 2, LDX_OP_LAYER_NORM = 3, LDX_OP_ATTENTION = 4,
   LDX_OP_NCHW_TO_NHWC = 5, LDX_OP_TIMESTEP_EMB = 6, LDX_OP_UPSAMPLE2X = 7, LDX_OP_EPS_TO_DENOISED = 8,
   LDX_OP_CFG_DENOISED = 9, LDX_OP_VAE_POST = 10, LDX_OP_SOFTMAX = 11,
+  /* LDX_OP_ATTENTION takes i[5] = 1 for the causal variant (ldx_attention_causal) */
+  LDX_OP_CLIP_EMBED = 15,    /* p: tokens, tok_emb, pos_emb, out ; l: ldo ; i: rows, T, C */
   LDX_OP_VAE_PRE = 13,       /* p: pixels, out ; l: npix */
   LDX_OP_VAE_SAMPLE = 14,    /* p: moments, noise, z ; l: n, hw ; i: zc */
   LDX_OP_DUP = 12            /* p: src, dst ; l: bytes.  dst[0:bytes] = dst[bytes:2*bytes] = src (device copies): the

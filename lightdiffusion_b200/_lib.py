@@ -15,11 +15,12 @@ EPI_SILU = 1
 EPI_GEGLU = 2
 EPI_OUT_F32 = 4
 EPI_ROWNORM = 8
+EPI_QUICK_GELU = 16
 
 OP_GEMM, OP_GROUP_NORM, OP_LAYER_NORM, OP_ATTENTION = 1, 2, 3, 4
 OP_NCHW_TO_NHWC, OP_TIMESTEP_EMB, OP_UPSAMPLE2X, OP_EPS_TO_DENOISED = 5, 6, 7, 8
 OP_CFG_DENOISED, OP_VAE_POST, OP_SOFTMAX = 9, 10, 11
-OP_DUP, OP_VAE_PRE, OP_VAE_SAMPLE = 12, 13, 14
+OP_DUP, OP_VAE_PRE, OP_VAE_SAMPLE, OP_CLIP_EMBED = 12, 13, 14, 15
 
 GN_STATS_FLOATS_PER_BATCH = 64 * 32 * 2      # ldx_group_norm workspace: B * this many floats
 
@@ -88,6 +89,10 @@ _SIGS = {
     "ldx_vae_sample_posterior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
     "ldx_bislerp_axis": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64,
                                    C.c_int, C.c_int, C.c_int64, C.c_void_p]),
+    "ldx_clip_embed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p]),
+    "ldx_attention_causal": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                       C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldx_vae_postprocess": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "ldx_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float,
                                    C.c_void_p]),

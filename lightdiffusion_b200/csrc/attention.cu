@@ -93,6 +93,7 @@ struct alignas(64) AttnParams {
   int64_t ldo;
   int32_t B, Nq, Nk, heads;
   float scale_log2;   // log2(e) / sqrt(d)
+  int32_t causal;
 };
 
 // 2^x for x <= 0 on the FMA/ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative
@@ -107,7 +108,9 @@ LDX_DEVICE float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-template <int D, int NG_>
+// CAUSAL (the CLIP text tower's mask, LD.py:4443-4449: -inf above the diagonal) is a compile-time variant so
+// that the unmasked kernels keep their instruction stream; key j contributes to query i only when j <= i.
+template <int D, int NG_, bool CAUSAL = false>
 __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN_BLOCKS) ldx_attention_kernel(
     const __grid_constant__ AttnParams p) {
   using C = AttnCfg<D, NG_>;
@@ -306,6 +309,14 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
           for (int i = 0; i < 32; ++i)
             if (hf * 32 + i >= kv_left) s[i] = -INFINITY;
         }
+        if constexpr (CAUSAL) {
+          const int k0 = j * BKV + hf * 32, qi = q_cta + g * BQ + row;
+          if (k0 + 31 > qi) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (k0 + i > qi) s[i] = -INFINITY;
+          }
+        }
         float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
 #pragma unroll
         for (int i = 4; i < 32; i += 4) {
@@ -442,7 +453,7 @@ struct AttnLaunch {
 static int attention_groups(int d, int Nk) { return (d <= 64 && Nk > 256) ? LDX_ATT_NG_SMALL : 1; }
 
 static int attention_prepare(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                             void* o, int64_t ldo, int B, int Nq, int Nk, int heads, int d, AttnLaunch* L) {
+                             void* o, int64_t ldo, int B, int Nq, int Nk, int heads, int d, AttnLaunch* L, int causal = 0) {
   LDX_CHECK_ARG(q && k && v && o, "attention: null pointer");
   LDX_CHECK_ARG(d == 40 || d == 64 || d == 80 || d == 128 || d == 160, "attention: head dim %d unsupported", d);
   LDX_CHECK_ARG(B >= 1 && Nq >= 1 && Nk >= 1 && heads >= 1, "attention: bad extents");
@@ -462,25 +473,34 @@ static int attention_prepare(const void* q, int64_t ldq, const void* k, int64_t 
   L->p.ldo = ldo;
   L->p.B = B; L->p.Nq = Nq; L->p.Nk = Nk; L->p.heads = heads;
   L->p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
+  L->p.causal = causal;
+  LDX_CHECK_ARG(!causal || Nq == Nk, "attention: the causal mask needs Nq == Nk");
   L->d = d;
   L->ng = attention_groups(d, Nk);
   L->grid = dim3((Nq + L->ng * BQ - 1) / (L->ng * BQ), heads, B);
   return LDX_OK;
 }
 
-template <int D, int NG_>
+template <int D, int NG_, bool CAUSAL = false>
 static int attention_launch_t(const AttnLaunch* L, cudaStream_t st) {
   using C = AttnCfg<D, NG_>;
   static bool attr = false;
   if (!attr) {
-    LDX_CUDA(cudaFuncSetAttribute(ldx_attention_kernel<D, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    LDX_CUDA(cudaFuncSetAttribute(ldx_attention_kernel<D, NG_, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::SMEM));
     attr = true;
   }
-  LDX_CUDA(launch_k(ldx_attention_kernel<D, NG_>, L->grid, dim3(C::THREADS), (size_t)C::SMEM, st, 1, L->p));
+  LDX_CUDA(launch_k(ldx_attention_kernel<D, NG_, CAUSAL>, L->grid, dim3(C::THREADS), (size_t)C::SMEM, st, 1, L->p));
   return LDX_OK;
 }
 
 static int attention_launch(const AttnLaunch* L, cudaStream_t st) {
+  if (L->p.causal) {
+    if (L->d == 64 && L->ng == 1) return attention_launch_t<64, 1, true>(L, st);
+    set_error("attention: the causal variant exists for d = 64 and Nk <= 256 (CLIP text tower), got d = %d, Nk = %d", L->d,
+              L->p.Nk);
+    return LDX_E_INVALID;
+  }
   switch (L->d) {
     case 40: return L->ng == 1 ? attention_launch_t<40, 1>(L, st) : attention_launch_t<40, LDX_ATT_NG_SMALL>(L, st);
     case 64: return L->ng == 1 ? attention_launch_t<64, 1>(L, st) : attention_launch_t<64, LDX_ATT_NG_SMALL>(L, st);
@@ -495,9 +515,9 @@ static int attention_launch(const AttnLaunch* L, cudaStream_t st) {
 // program support (api.cu)
 int attention_prepare_op(const ldx_generic_op_t* op, void** handle) {
   AttnLaunch* L = new AttnLaunch;
-  // p: q, k, v, o ; l: ldq, ldk, ldv, ldo ; i: B, Nq, Nk, heads, d
+  // p: q, k, v, o ; l: ldq, ldk, ldv, ldo ; i: B, Nq, Nk, heads, d, causal
   int rc = attention_prepare(op->p[0], op->l[0], op->p[1], op->l[1], op->p[2], op->l[2], (void*)op->p[3], op->l[3],
-                             op->i[0], op->i[1], op->i[2], op->i[3], op->i[4], L);
+                             op->i[0], op->i[1], op->i[2], op->i[3], op->i[4], L, op->i[5]);
   if (rc) {
     delete L;
     return rc;
@@ -516,6 +536,14 @@ extern "C" int ldx_attention(const void* q, int64_t ldq, const void* k, int64_t 
                              void* o, int64_t ldo, int B, int Nq, int Nk, int heads, int d, ldx_stream_t stream) {
   AttnLaunch L;
   int rc = attention_prepare(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, heads, d, &L);
+  if (rc) return rc;
+  return attention_launch(&L, as_stream(stream));
+}
+
+extern "C" int ldx_attention_causal(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                    void* o, int64_t ldo, int B, int N, int heads, int d, ldx_stream_t stream) {
+  AttnLaunch L;
+  int rc = attention_prepare(q, ldq, k, ldk, v, ldv, o, ldo, B, N, N, heads, d, &L, 1);
   if (rc) return rc;
   return attention_launch(&L, as_stream(stream));
 }

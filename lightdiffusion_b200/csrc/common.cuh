@@ -327,6 +327,12 @@ LDX_DEVICE float silu_f(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(-1.4426950408889634f * x)));
   return x * r;
 }
+// x * sigmoid(k x): k = 1 is SiLU, k = 1.702 the CLIP text tower's quick_gelu (LD.py:4296-4299)
+LDX_DEVICE float sigmoid_gate_f(float x, float neg_k_log2e) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + ex2_approx(neg_k_log2e * x)));
+  return x * r;
+}
 LDX_DEVICE float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 // exact-erf GELU, x * Phi(x), as x * sigmoid(q(x)) with q = logit(Phi) fitted by an odd degree-9 polynomial
 // (max abs error 3.7e-6 over all x, below fp16 output rounding wherever |gelu| > 1e-2; the tails saturate

@@ -609,6 +609,17 @@ __global__ void bislerp_axis_kernel(const float* __restrict__ in, float* __restr
   }
 }
 
+// CLIPEmbeddings.forward (LD.py:4409-4410): out[r, :] = token_embedding[tokens[r], :] + position_embedding[r % T, :],
+// fp32 tables (the reference keeps them fp32, LD.py:4423), fp16 out; one block per row
+__global__ void clip_embed_kernel(const int* __restrict__ tokens, const float* __restrict__ tok_emb,
+                                  const float* __restrict__ pos_emb, __half* __restrict__ out, int64_t ldo, int T, int C) {
+  const int r = blockIdx.x;
+  const float* te = tok_emb + (int64_t)tokens[r] * C;
+  const float* pe = pos_emb + (int64_t)(r % T) * C;
+  __half* o = out + (int64_t)r * ldo;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = __float2half_rn(te[c] + pe[c]);
+}
+
 // row softmax for n = NV * 1024 (the VAE AttnBlock's 4096 / 16384 tokens): the row lives in registers, so the
 // fp32 scores are read once (16-byte loads) and the fp16 probabilities written once (8-byte stores)
 template <int NV>
@@ -788,6 +799,12 @@ int run_generic_op(const ldx_generic_op_t* op, cudaStream_t st) {
                                                           l[1]);
       LDX_CUDA(cudaGetLastError());
       return LDX_OK;
+    case LDX_OP_CLIP_EMBED:
+      // p: tokens, tok_emb, pos_emb, out ; l: ldo ; i: rows, T, C
+      clip_embed_kernel<<<(unsigned)i[0], 256, 0, st>>>((const int*)p[0], (const float*)p[1], (const float*)p[2],
+                                                       (__half*)p[3], l[0], i[1], i[2]);
+      LDX_CUDA(cudaGetLastError());
+      return LDX_OK;
     case LDX_OP_SOFTMAX:
       // p: s (fp32), out (fp16) ; l: lds, ldo, rows ; i: n ; f: scale
       {
@@ -923,6 +940,16 @@ extern "C" int ldx_bislerp_axis(const float* in, float* out, const float* ratio,
                                                                       len_new, inner);
   LDX_CUDA(cudaGetLastError());
   return LDX_OK;
+}
+
+extern "C" int ldx_clip_embed(const int32_t* tokens, const float* tok_emb, const float* pos_emb, void* out, int64_t ldo,
+                              int rows, int T, int C, ldx_stream_t stream) {
+  LDX_CHECK_ARG(tokens && tok_emb && pos_emb && out, "clip_embed: null");
+  LDX_CHECK_ARG(rows > 0 && T > 0 && C > 0 && ldo >= C, "clip_embed: bad shape");
+  ldx_generic_op_t op = make_op(LDX_OP_CLIP_EMBED);
+  op.p[0] = tokens; op.p[1] = tok_emb; op.p[2] = pos_emb; op.p[3] = out; op.l[0] = ldo;
+  op.i[0] = rows; op.i[1] = T; op.i[2] = C;
+  return run_generic_op(&op, as_stream(stream));
 }
 
 extern "C" int ldx_softmax_rows(const float* s, int64_t lds, void* out, int64_t ldo, int64_t rows, int n, float scale,

@@ -125,9 +125,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, uint32_t tm
   }
   if (!row_valid) return;
   const int n_out_total = kGeglu ? p.N / 2 : p.N;
-  if (p.flags & LDX_EPI_SILU) {
+  if (p.flags & (LDX_EPI_SILU | LDX_EPI_QUICK_GELU)) {
+    const float nk = (p.flags & LDX_EPI_QUICK_GELU) ? -1.702f * 1.4426950408889634f : -1.4426950408889634f;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = sigmoid_gate_f(v[j], nk);
   }
   if (p.vec_ok) {
 #pragma unroll
@@ -492,9 +493,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               __syncwarp();
               if (lane == 0) release_tmem(as);
             }
-            if (p.flags & LDX_EPI_SILU) {
+            if (p.flags & (LDX_EPI_SILU | LDX_EPI_QUICK_GELU)) {
+              const float nk = (p.flags & LDX_EPI_QUICK_GELU) ? -1.702f * 1.4426950408889634f : -1.4426950408889634f;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = silu_f(v[j]);
+              for (int j = 0; j < 32; ++j) v[j] = sigmoid_gate_f(v[j], nk);
             }
             if (rowstats) {                    // row statistics for a LayerNorm folded into the consumer GEMM
 #pragma unroll
@@ -594,7 +596,11 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitReduce r)
       const float2 a0 = unpack_h2(rr.x), a1 = unpack_h2(rr.y);
       acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
     }
-    if (r.silu) { acc.x = silu_f(acc.x); acc.y = silu_f(acc.y); acc.z = silu_f(acc.z); acc.w = silu_f(acc.w); }
+    if (r.silu) {                 // 1 = SiLU, 2 = quick_gelu
+      const float nk = r.silu == 2 ? -1.702f * 1.4426950408889634f : -1.4426950408889634f;
+      acc.x = sigmoid_gate_f(acc.x, nk); acc.y = sigmoid_gate_f(acc.y, nk);
+      acc.z = sigmoid_gate_f(acc.z, nk); acc.w = sigmoid_gate_f(acc.w, nk);
+    }
     __half* o = reinterpret_cast<__half*>(r.out) + r.o_off + (int64_t)b * r.o_sb + (int64_t)y * r.o_sy + (int64_t)x * r.o_sx + n;
     *reinterpret_cast<uint2*>(o) = make_uint2(pack_h2(acc.x, acc.y), pack_h2(acc.z, acc.w));
   }
@@ -926,7 +932,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     p.split_stride = rows * d->N;
     g->ws_bytes = (size_t)nsplit * (size_t)p.split_stride * sizeof(float);
     g->red = SplitReduce{nullptr, nsplit, p.split_stride, (int)rows, d->N, d->W, d->H, d->bias, d->rowadd, d->ld_rowadd,
-                         d->residual, d->ldr, (d->flags & LDX_EPI_SILU) ? 1 : 0, d->out, d->o_sx,
+                         d->residual, d->ldr, (d->flags & LDX_EPI_SILU) ? 1 : ((d->flags & LDX_EPI_QUICK_GELU) ? 2 : 0), d->out, d->o_sx,
                          d->o_sy > 0 ? d->o_sy : d->o_sx * d->W,
                          d->o_sb > 0 ? d->o_sb : (d->o_sy > 0 ? d->o_sy : d->o_sx * d->W) * d->H, d->o_off};
     p.out = nullptr;                        // bound by gemm_bind_workspace()

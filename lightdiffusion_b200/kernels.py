@@ -273,7 +273,7 @@ def layer_norm_op(x2, gamma, beta, y2, eps=1e-5) -> L.GenericOp:
                       i=[rows, c], l=[x2.stride(0), y2.stride(0)], f=[eps])
 
 
-def attention_op(q, k, v, o, heads: int) -> L.GenericOp:
+def attention_op(q, k, v, o, heads: int, causal: bool = False) -> L.GenericOp:
     """q [B,Nq,heads*d], k/v [B,Nk,heads*d] (row pitch free, batch stride = N * pitch), o like q."""
     b, nq, c = q.shape
     nk = k.shape[1]
@@ -281,7 +281,7 @@ def attention_op(q, k, v, o, heads: int) -> L.GenericOp:
         _check_act(t)
         assert t.stride(0) == t.stride(1) * n, "batch stride must equal N * row pitch"
     return generic_op(L.OP_ATTENTION, p=[q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()],
-                      l=[q.stride(1), k.stride(1), v.stride(1), o.stride(1)], i=[b, nq, nk, heads, c // heads])
+                      l=[q.stride(1), k.stride(1), v.stride(1), o.stride(1)], i=[b, nq, nk, heads, c // heads, 1 if causal else 0])
 
 
 def run_op(op: L.GenericOp):

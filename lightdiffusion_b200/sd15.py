@@ -315,6 +315,46 @@ def vae_encoder_param_shapes(cfg: VAEConfig = SD15_VAE) -> "OrderedDict[str, tup
     return out
 
 
+# --------------------------------------------------------------------------- CLIP text tower
+@dataclass(frozen=True)
+class CLIPTextConfig:
+    """_internal/clip/sd1_clip_config.json (CLIP ViT-L/14 text model), read by SDClipModel (LD.py:4596-4602)."""
+    vocab_size: int = 49408
+    max_positions: int = 77
+    hidden_size: int = 768
+    num_layers: int = 12
+    num_heads: int = 12
+    intermediate_size: int = 3072
+
+
+SD15_CLIP = CLIPTextConfig()
+
+
+def clip_text_param_shapes(cfg: CLIPTextConfig = SD15_CLIP) -> "OrderedDict[str, tuple]":
+    """name -> shape of CLIPTextModel (LD.py:4456-4467: ``text_model.*`` + ``text_projection``)."""
+    out: "OrderedDict[str, tuple]" = OrderedDict()
+    c, f = cfg.hidden_size, cfg.intermediate_size
+    out["text_model.embeddings.token_embedding.weight"] = (cfg.vocab_size, c)
+    out["text_model.embeddings.position_embedding.weight"] = (cfg.max_positions, c)
+    for i in range(cfg.num_layers):
+        p = f"text_model.encoder.layers.{i}"
+        out[f"{p}.layer_norm1.weight"] = (c,)
+        out[f"{p}.layer_norm1.bias"] = (c,)
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            out[f"{p}.self_attn.{n}.weight"] = (c, c)
+            out[f"{p}.self_attn.{n}.bias"] = (c,)
+        out[f"{p}.layer_norm2.weight"] = (c,)
+        out[f"{p}.layer_norm2.bias"] = (c,)
+        out[f"{p}.mlp.fc1.weight"] = (f, c)
+        out[f"{p}.mlp.fc1.bias"] = (f,)
+        out[f"{p}.mlp.fc2.weight"] = (c, f)
+        out[f"{p}.mlp.fc2.bias"] = (c,)
+    out["text_model.final_layer_norm.weight"] = (c,)
+    out["text_model.final_layer_norm.bias"] = (c,)
+    out["text_projection.weight"] = (c, c)
+    return out
+
+
 # --------------------------------------------------------------------------- weights
 def seeded_state_dict(shapes: "OrderedDict[str, tuple]", seed: int, dtype=torch.float32,
                       device="cpu", bias_std: float = 0.0, norm_jitter: float = 0.0):

@@ -406,6 +406,61 @@ def bislerp(samples, width: int, height: int):
     return x.to(samples.dtype)
 
 
+# ----------------------------------------------------------------------------- CLIP text tower
+def clip_text_forward(sd: SD, cfg, tokens, intermediate_output: Optional[int] = None,
+                      final_layer_norm_intermediate: bool = True):
+    """CLIPTextModel.forward, LD.py:4437-4486 over CLIPEncoder / CLIPLayer / CLIPAttention / CLIPMLP (LD.py:4268-4396):
+    token + position embeddings, causal mask, pre-LN layers with quick_gelu, final LayerNorm, pooled = the row at the
+    arg-max token id (EOS), text_projection.  Returns (last, intermediate or None, projected pooled, pooled)."""
+    tokens = tokens.long()
+    x = sd["text_model.embeddings.token_embedding.weight"][tokens] + sd["text_model.embeddings.position_embedding.weight"]
+    n = x.shape[1]
+    mask = torch.full((n, n), float("-inf"), dtype=x.dtype, device=x.device).triu_(1)
+    if intermediate_output is not None and intermediate_output < 0:
+        intermediate_output = cfg.num_layers + intermediate_output
+    inter = None
+    for i in range(cfg.num_layers):
+        p = f"text_model.encoder.layers.{i}"
+        y = _ln(sd, p + ".layer_norm1", x)
+        q, k, v = (_lin(sd, f"{p}.self_attn.{nm}_proj", y) for nm in ("q", "k", "v"))
+        b, t, c = q.shape
+        h = cfg.num_heads
+        qh, kh, vh = (z.view(b, t, h, c // h).transpose(1, 2) for z in (q, k, v))
+        a = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=mask).transpose(1, 2).reshape(b, t, c)
+        x = x + _lin(sd, p + ".self_attn.out_proj", a)
+        y = _lin(sd, p + ".mlp.fc1", _ln(sd, p + ".layer_norm2", x))
+        x = x + _lin(sd, p + ".mlp.fc2", y * torch.sigmoid(1.702 * y))
+        if i == intermediate_output:
+            inter = x.clone()
+    x = _ln(sd, "text_model.final_layer_norm", x)
+    if inter is not None and final_layer_norm_intermediate:
+        inter = _ln(sd, "text_model.final_layer_norm", inter)
+    pooled = x[torch.arange(x.shape[0], device=x.device), tokens.to(torch.int).argmax(dim=-1)]
+    return x, inter, F.linear(pooled, sd["text_projection.weight"]), pooled
+
+
+def clip_encode_token_weights(sd: SD, cfg, token_weight_pairs, layer_idx: Optional[int] = -2, empty_tokens=None):
+    """ClipTokenWeightEncoder.encode_token_weights (LD.py:4539-4569) over SDClipModel.forward (LD.py:4689-4724) with
+    layer = "hidden": one 77-token section per entry; weighted tokens are pushed away from the empty prompt's
+    embedding, z = (z - z_empty) * w + z_empty; sections are concatenated along the token axis."""
+    to_encode = [[t for t, _ in sec] for sec in token_weight_pairs]
+    has_weights = any(w != 1.0 for sec in token_weight_pairs for _, w in sec)
+    sections = len(to_encode)
+    if has_weights or sections == 0:
+        to_encode.append(list(empty_tokens))
+    dev = sd["text_projection.weight"].device
+    last, inter, pooled, _ = clip_text_forward(sd, cfg, torch.tensor(to_encode, device=dev), layer_idx)
+    out = (last if layer_idx is None else inter).float()
+    zs = []
+    for k in range(sections):
+        z = out[k:k + 1].clone()
+        if has_weights:
+            w = torch.tensor([wt for _, wt in token_weight_pairs[k]], device=dev, dtype=z.dtype).view(1, -1, 1)
+            z = torch.where(w != 1.0, (z - out[-1]) * w + out[-1], z)
+        zs.append(z)
+    return torch.cat(zs, dim=-2), pooled[0:1].float()
+
+
 # ----------------------------------------------------------------------------- pipeline
 LATENT_SCALE = 0.18215      # SD15 latent format, LD.py:137-139
 

@@ -173,6 +173,50 @@ def golden_bislerp(R):
     torch.save(dict(x=x, cases=cases, source="bislerp LD.py:429-518"), os.path.join(OUT, "bislerp.pt"))
 
 
+CLIP_SEED = 77
+
+
+def _clip_tokens(g, n_words, weights=None):
+    """One 77-token section in the tokenizer's layout (SDTokenizer.tokenize_with_weights, LD.py:4960-5031):
+    start, words, end, pad (= end for SD1), each paired with a weight."""
+    ids = torch.randint(1000, 40000, (n_words,), generator=g).tolist()
+    toks = [49406] + ids + [49407] * (77 - 1 - n_words)
+    w = [1.0] * 77
+    for pos, val in (weights or {}).items():
+        w[pos] = val
+    return list(zip(toks, w))
+
+
+def golden_clip(R):
+    """Reference SDClipModel (LD.py:4572) with the SD1 text config and seeded weights: raw CLIPTextModel.forward
+    outputs, and encode_token_weights with clip-skip -2 (CLIPSetLastLayer, LD.py:10032-10035) on weighted prompts."""
+    import json
+    sd = sd15.seeded_state_dict(sd15.clip_text_param_shapes(), CLIP_SEED, **INIT)
+    with torch.no_grad():          # CLIPTextModel.__init__ writes text_projection in place (LD.py:4475)
+        clip = R.SDClipModel(device="cpu", dtype=torch.float32, textmodel_json_config=os.path.join(
+            ref_loader.REF_DIR, "_internal", "clip", "sd1_clip_config.json"))
+    missing, unexpected = clip.transformer.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    g = torch.Generator().manual_seed(12)
+    secs = [_clip_tokens(g, 9), _clip_tokens(g, 30, {3: 1.4, 4: 1.4, 10: 0.6}), _clip_tokens(g, 75)]
+    tokens = torch.tensor([[t for t, _ in s_] for s_ in secs])
+    with torch.inference_mode():
+        last, inter, pooled_proj, pooled = clip.transformer(tokens, None, intermediate_output=-2,
+                                                            final_layer_norm_intermediate=True)
+        last_only = clip.transformer(tokens[:1], None)[0]
+        clip.set_clip_options({"layer": -2})
+        cond_w, pooled_w = clip.encode_token_weights([secs[1]])             # weighted: appends the empty prompt
+        cond_2, pooled_2 = clip.encode_token_weights([secs[0], secs[2]])    # two unweighted sections -> 154 tokens
+        clip.reset_clip_options()
+        cond_last, _ = clip.encode_token_weights([secs[0]])                 # layer = "last"
+    torch.save(dict(secs=secs, tokens=tokens, last=last.clone(), inter=inter.clone(), pooled_proj=pooled_proj.clone(),
+                    pooled=pooled.clone(), last_only=last_only.clone(), cond_w=cond_w.clone(), pooled_w=pooled_w.clone(),
+                    cond_2=cond_2.clone(), pooled_2=pooled_2.clone(), cond_last=cond_last.clone(),
+                    empty=R.gen_empty_tokens(clip.special_tokens, 77), clip_seed=CLIP_SEED, init=INIT,
+                    source="SDClipModel LD.py:4572, CLIPTextModel.forward LD.py:4480, encode_token_weights LD.py:4540"),
+               os.path.join(OUT, "clip_text.pt"))
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -191,6 +235,7 @@ def main():
     golden_vae(R)
     golden_vae_encode(R)
     golden_bislerp(R)
+    golden_clip(R)
     golden_unet(R, "sd15_lat8", sd15.SD15_UNET, hw=8, b=2)   # real SD1.5 dims, small latent
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -264,3 +264,70 @@ def test_vae_encode_rejects_bad_sizes(vae_enc):
         eng.encode(torch.zeros(1, 60, 64, 3, device=DEV))
     with pytest.raises(Exception):
         eng.encode(torch.zeros(64, 64, 3, device=DEV))
+
+
+# ------------------------------------------------------------------------------------ CLIP text tower
+COND_TOL = 5e-3         # conditioning (LayerNorm'd hidden states) relative L2, fp16 activations vs fp32 reference
+
+
+@pytest.fixture(scope="module")
+def clip_eng(golden):
+    from lightdiffusion_b200.clip import CLIPTextEngine
+    g = golden("clip_text.pt")
+    sd = rounded(sd15.seeded_state_dict(sd15.clip_text_param_shapes(), g["clip_seed"], **g["init"]))
+    return g, sd, CLIPTextEngine(sd)
+
+
+def test_clip_text_forward_matches_reference_golden(clip_eng):
+    """CLIPTextModel.forward outputs of the real reference (unrounded fp32 weights) vs the engine (fp16 weights)."""
+    g, sd, eng = clip_eng
+    last, inter, proj, pooled = eng.forward(g["tokens"], intermediate_output=-2)
+    errs = dict(last=rel(last.cpu(), g["last"]), inter=rel(inter.cpu(), g["inter"]), proj=rel(proj.cpu(), g["pooled_proj"]),
+                pooled=rel(pooled.cpu(), g["pooled"]))
+    print("clip vs reference golden", errs)
+    assert max(errs.values()) < COND_TOL
+    assert last.dtype == torch.float32 and last.shape == (3, 77, 768)
+    assert eng.forward(g["tokens"][:1])[1] is None
+    assert rel(eng.forward(g["tokens"][:1])[0].cpu(), g["last_only"]) < COND_TOL
+
+
+def test_clip_text_parity_with_oracle(clip_eng):
+    """Same fp16-rounded weights on both sides; other batch sizes and intermediate layers."""
+    g, sd, eng = clip_eng
+    gen = torch.Generator().manual_seed(3)
+    for B, T, inter in ((1, 77, -2), (4, 77, None), (2, 77, 5), (7, 77, -1)):
+        tok = torch.randint(0, 49408, (B, T), generator=gen)
+        tok[:, 0] = 49406
+        last, mid, proj, pooled = eng.forward(tok, intermediate_output=inter)
+        with torch.inference_mode():
+            rl, rm, rp, rpo = O.clip_text_forward(sd, sd15.SD15_CLIP, tok.to(DEV), inter)
+        e = [rel(last, rl), rel(proj, rp), rel(pooled, rpo)] + ([] if inter is None else [rel(mid, rm)])
+        print("clip parity", (B, T, inter), e)
+        assert max(e) < 3e-3
+    raw = eng.forward(g["tokens"], intermediate_output=-2, final_layer_norm_intermediate=False)[1]
+    with torch.inference_mode():
+        rr = O.clip_text_forward(sd, sd15.SD15_CLIP, g["tokens"].to(DEV), -2, False)[1]
+    assert rel(raw, rr) < 3e-3
+    with pytest.raises(Exception):
+        eng.forward(torch.full((1, 77), 49408))          # id outside the vocabulary
+    with pytest.raises(Exception):
+        eng.forward(torch.zeros(1, 78, dtype=torch.long))
+    with pytest.raises(Exception):
+        eng.forward(torch.zeros(1, 20, dtype=torch.long))   # the reference adds all 77 position rows (LD.py:4410)
+
+
+def test_clip_encode_token_weights_matches_reference_golden(clip_eng):
+    """SDClipModel.encode_token_weights with clip skip -2: weighted prompt, two sections, and layer = last."""
+    from lightdiffusion_b200.clip import SD1ClipEncoder
+    g, sd, eng = clip_eng
+    enc = SD1ClipEncoder(eng)
+    enc.set_clip_options({"layer": -2})
+    cw, pw = enc.encode_token_weights([g["secs"][1]])
+    c2, p2 = enc.encode_token_weights([g["secs"][0], g["secs"][2]])
+    enc.reset_clip_options()
+    cl, _ = enc.encode_token_weights([g["secs"][0]])
+    errs = [rel(cw.cpu(), g["cond_w"]), rel(pw.cpu(), g["pooled_w"]), rel(c2.cpu(), g["cond_2"]), rel(p2.cpu(), g["pooled_2"]),
+            rel(cl.cpu(), g["cond_last"])]
+    print("clip token weights vs reference golden", errs)
+    assert cw.shape == (1, 77, 768) and c2.shape == (1, 154, 768) and pw.shape == (1, 768)
+    assert max(errs) < COND_TOL

@@ -284,6 +284,47 @@ def test_attention_peaked_scores_rescale_path():
     assert rel(o, ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,N,heads", [(1, 77, 12), (3, 77, 12), (2, 64, 4), (2, 130, 2), (1, 256, 1)])
+def test_attention_causal(B, N, heads):
+    """The CLIP text tower's attention (LD.py:4443-4449, 4291): -inf above the diagonal, d = 64."""
+    d = 64
+    q, k, v = (h16(rnd(B, N, heads * d, seed=140 + i) * (2.0 if i < 2 else 1.0)) for i in range(3))
+    o = torch.zeros_like(q)
+    L.check(L.lib().ldx_attention_causal(q.data_ptr(), heads * d, k.data_ptr(), heads * d, v.data_ptr(), heads * d,
+                                         o.data_ptr(), heads * d, B, N, heads, d, 0))
+    qf, kf, vf = (t.float().view(B, N, heads, d).transpose(1, 2) for t in (q, k, v))
+    mask = torch.full((N, N), float("-inf"), device=DEV).triu_(1)
+    ref = F.scaled_dot_product_attention(qf, kf, vf, attn_mask=mask).transpose(1, 2).reshape(B, N, heads * d)
+    assert rel(o, ref) < 2e-3
+    # the first token attends to itself only
+    assert rel(o[:, 0], v[:, 0].float()) < 1e-3
+    # strided q/k/v (views of one fused projection), through a recorded program
+    qkv = h16(rnd(B, N, 3 * heads * d, seed=150))
+    o2 = torch.zeros(B, N, heads * d, dtype=torch.float16, device=DEV)
+    c = heads * d
+    K.run_op(K.attention_op(qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:], o2, heads, causal=True))
+    q2, k2, v2 = (qkv[:, :, i * c:(i + 1) * c].float().reshape(B, N, heads, d).transpose(1, 2) for i in range(3))
+    ref2 = F.scaled_dot_product_attention(q2, k2, v2, attn_mask=mask).transpose(1, 2).reshape(B, N, c)
+    assert rel(o2, ref2) < 2e-3
+    assert L.lib().ldx_attention_causal(q.data_ptr(), heads * d, k.data_ptr(), heads * d, v.data_ptr(), heads * d,
+                                        o.data_ptr(), heads * d, B, N, heads, 40, 0) != 0     # d = 64 only
+
+
+def test_linear_quick_gelu_and_clip_embed():
+    M, N, Kd = 154, 3072, 768
+    a, w, bias = h16(rnd(M, Kd, seed=160)), h16(rnd(N, Kd, seed=161, scale=Kd ** -0.5)), rnd(N, seed=162)
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.linear_desc(a, K.pack_linear(w), out, bias=bias, flags=L.EPI_QUICK_GELU))
+    x = a.float() @ w.float().t() + bias
+    assert rel(out, x * torch.sigmoid(1.702 * x)) < 1e-3
+    T, C, vocab = 77, 768, 1000
+    tok = torch.randint(0, vocab, (2 * T,), device=DEV, dtype=torch.int32)
+    te, pe = rnd(vocab, C, seed=163), rnd(T, C, seed=164)
+    emb = torch.empty(2 * T, C, dtype=torch.float16, device=DEV)
+    L.check(L.lib().ldx_clip_embed(tok.data_ptr(), te.data_ptr(), pe.data_ptr(), emb.data_ptr(), C, 2 * T, T, C, 0))
+    assert torch.equal(emb, (te[tok.long()] + pe.repeat(2, 1)).half())
+
+
 # ------------------------------------------------------------------------------- small ops
 def test_input_output_transforms():
     from oracle import ldm_oracle as O

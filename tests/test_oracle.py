@@ -120,3 +120,24 @@ def test_bislerp(golden):
         out = O.bislerp(x, c["width"], c["height"])
         assert out.shape == c["out"].shape, name
         assert torch.allclose(out, c["out"], rtol=1e-5, atol=1e-6), name
+
+
+def test_clip_text(golden):
+    """The CLIP text tower restatement against the reference's SDClipModel (raw forward, clip-skip -2, token weights)."""
+    g = golden("clip_text.pt")
+    cfg = sd15.SD15_CLIP
+    sd = sd15.seeded_state_dict(sd15.clip_text_param_shapes(cfg), g["clip_seed"], **g["init"])
+    with torch.inference_mode():
+        last, inter, pooled_proj, pooled = O.clip_text_forward(sd, cfg, g["tokens"], -2)
+        assert rel(last, g["last"]) < 2e-5 and rel(inter, g["inter"]) < 2e-5
+        assert rel(pooled, g["pooled"]) < 2e-5 and rel(pooled_proj, g["pooled_proj"]) < 2e-5
+        assert O.clip_text_forward(sd, cfg, g["tokens"][:1])[1] is None
+        assert rel(O.clip_text_forward(sd, cfg, g["tokens"][:1])[0], g["last_only"]) < 2e-5
+        cw, pw = O.clip_encode_token_weights(sd, cfg, [g["secs"][1]], -2, g["empty"])
+        assert cw.shape == g["cond_w"].shape == (1, 77, 768)
+        assert rel(cw, g["cond_w"]) < 2e-5 and rel(pw, g["pooled_w"]) < 2e-5
+        c2, p2 = O.clip_encode_token_weights(sd, cfg, [g["secs"][0], g["secs"][2]], -2, g["empty"])
+        assert c2.shape == g["cond_2"].shape == (1, 154, 768)
+        assert rel(c2, g["cond_2"]) < 2e-5 and rel(p2, g["pooled_2"]) < 2e-5
+        cl, _ = O.clip_encode_token_weights(sd, cfg, [g["secs"][0]], None, g["empty"])
+        assert rel(cl, g["cond_last"]) < 2e-5
