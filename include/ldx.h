@@ -203,6 +203,21 @@ int ldx_dpmpp2m_step(float* x, const float* denoised, const float* old_denoised,
 int ldx_euler_ancestral_step(float* x, const float* denoised, const float* noise, float sigma,
                              float sigma_down, float noise_scale, int64_t n, ldx_stream_t stream);
 
+/* DPM-Solver-12/23 with adaptive step size (sample_dpm_adaptive / DPMSolver, LD.py:976-1170), fp32 state:
+ *   ldx_dpm_eps:      eps = (x - denoised) / sigma                               (DPMSolver.eps, LD.py:990-999)
+ *   ldx_dpm_combine:  out = x - c1 * eps - c2 * (eps2 - eps)   (eps2 NULL: out = x - c1 * eps)
+ *                     = u1 / u2 / x_2 / x_3 of dpm_solver_2_step and dpm_solver_3_step (LD.py:1001-1038) with the
+ *                     host-computed scalars; products and differences are rounded separately, as in the reference
+ *   ldx_dpm_error_norm: err = || (x_low - x_high) / max(atol, rtol * max(|x_low|, |x_prev|)) ||_2 / sqrt(n)
+ *                     (LD.py:1094-1095) into the device float `err`; `workspace` holds LDX_DPM_ERROR_WS_DOUBLES
+ *                     doubles; two launches, fixed summation order. */
+#define LDX_DPM_ERROR_WS_DOUBLES 2048
+int ldx_dpm_eps(const float* x, const float* denoised, float sigma, float* eps, int64_t n, ldx_stream_t stream);
+int ldx_dpm_combine(const float* x, const float* eps, const float* eps2, float c1, float c2, float* out, int64_t n,
+                    ldx_stream_t stream);
+int ldx_dpm_error_norm(const float* x_low, const float* x_high, const float* x_prev, float atol, float rtol,
+                       int64_t n, void* workspace, float* err, ldx_stream_t stream);
+
 /* ------------------------------------------------------------------ recorded programs
  * A program is an ordered list of the calls above with all arguments frozen (TMA descriptors built
  * once).  ldx_program_run replays it on a stream; it is what a CUDA graph captures. */

@@ -16,6 +16,7 @@ EPI_GEGLU = 2
 EPI_OUT_F32 = 4
 EPI_ROWNORM = 8
 EPI_QUICK_GELU = 16
+DPM_ERROR_WS_DOUBLES = 2048
 
 OP_GEMM, OP_GROUP_NORM, OP_LAYER_NORM, OP_ATTENTION = 1, 2, 3, 4
 OP_NCHW_TO_NHWC, OP_TIMESTEP_EMB, OP_UPSAMPLE2X, OP_EPS_TO_DENOISED = 5, 6, 7, 8
@@ -93,6 +94,11 @@ _SIGS = {
                                  C.c_void_p]),
     "ldx_attention_causal": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                        C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ldx_dpm_eps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ldx_dpm_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_int64,
+                                  C.c_void_p]),
+    "ldx_dpm_error_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "ldx_vae_postprocess": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "ldx_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float,
                                    C.c_void_p]),

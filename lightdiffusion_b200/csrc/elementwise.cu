@@ -620,6 +620,54 @@ __global__ void clip_embed_kernel(const int* __restrict__ tokens, const float* _
   for (int c = threadIdx.x; c < C; c += blockDim.x) o[c] = __float2half_rn(te[c] + pe[c]);
 }
 
+// ---- DPM-Solver-12/23 adaptive (DPMSolver, LD.py:976-1116): every state update has the form
+//   out = x - c1 * eps - c2 * (e2 - eps)
+// with host scalars c1, c2 (u1: c2 = 0).  The products and differences are rounded separately, as the reference's
+// chain of torch kernels does, so that the step-size controller sees the same error norms.
+__global__ void dpm_eps_kernel(const float* __restrict__ x, const float* __restrict__ den, float inv_sigma,
+                               float* __restrict__ eps, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    eps[i] = __fmul_rn(__fsub_rn(x[i], den[i]), inv_sigma);
+}
+__global__ void dpm_combine_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ e2,
+                                   float c1, float c2, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float e = eps[i];
+    float v = __fsub_rn(x[i], __fmul_rn(c1, e));
+    if (e2) v = __fsub_rn(v, __fmul_rn(c2, __fsub_rn(e2[i], e)));
+    out[i] = v;
+  }
+}
+// partial[b] = sum over the block's elements of ((lo - hi) / max(atol, rtol * max(|lo|, |prev|)))^2   (LD.py:1094-1095)
+__global__ void __launch_bounds__(256) dpm_error_partial_kernel(const float* __restrict__ lo, const float* __restrict__ hi,
+                                                                const float* __restrict__ prev, float atol, float rtol,
+                                                                int64_t n, double* __restrict__ partial) {
+  __shared__ double red[8];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float l = lo[i];
+    const float delta = fmaxf(atol, __fmul_rn(rtol, fmaxf(fabsf(l), fabsf(prev[i]))));
+    const float q = __fdiv_rn(__fsub_rn(l, hi[i]), delta);
+    acc += (double)q * (double)q;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+// err = sqrt(sum of the partials) / sqrt(n): fixed summation order, so the result is run-to-run deterministic
+__global__ void dpm_error_final_kernel(const double* __restrict__ partial, int nb, double inv_sqrt_n, float* __restrict__ err) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < nb; ++b) t += partial[b];
+    *err = (float)(sqrt(t) * inv_sqrt_n);
+  }
+}
+
 // row softmax for n = NV * 1024 (the VAE AttnBlock's 4096 / 16384 tokens): the row lives in registers, so the
 // fp32 scores are read once (16-byte loads) and the fp16 probabilities written once (8-byte stores)
 template <int NV>
@@ -950,6 +998,33 @@ extern "C" int ldx_clip_embed(const int32_t* tokens, const float* tok_emb, const
   op.p[0] = tokens; op.p[1] = tok_emb; op.p[2] = pos_emb; op.p[3] = out; op.l[0] = ldo;
   op.i[0] = rows; op.i[1] = T; op.i[2] = C;
   return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_dpm_eps(const float* x, const float* denoised, float sigma, float* eps, int64_t n, ldx_stream_t stream) {
+  LDX_CHECK_ARG(x && denoised && eps && n > 0, "dpm_eps: null / empty");
+  LDX_CHECK_ARG(sigma > 0.f, "dpm_eps: sigma must be positive");
+  dpm_eps_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(x, denoised, 1.0f / sigma, eps, n);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
+}
+
+extern "C" int ldx_dpm_combine(const float* x, const float* eps, const float* eps2, float c1, float c2, float* out,
+                               int64_t n, ldx_stream_t stream) {
+  LDX_CHECK_ARG(x && eps && out && n > 0, "dpm_combine: null / empty");
+  dpm_combine_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(x, eps, eps2, c1, c2, out, n);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
+}
+
+extern "C" int ldx_dpm_error_norm(const float* x_low, const float* x_high, const float* x_prev, float atol, float rtol,
+                                  int64_t n, void* workspace, float* err, ldx_stream_t stream) {
+  LDX_CHECK_ARG(x_low && x_high && x_prev && workspace && err && n > 0, "dpm_error_norm: null / empty");
+  int nb = ew_blocks(n);
+  if (nb > LDX_DPM_ERROR_WS_DOUBLES) nb = LDX_DPM_ERROR_WS_DOUBLES;
+  dpm_error_partial_kernel<<<nb, 256, 0, as_stream(stream)>>>(x_low, x_high, x_prev, atol, rtol, n, (double*)workspace);
+  dpm_error_final_kernel<<<1, 32, 0, as_stream(stream)>>>((const double*)workspace, nb, 1.0 / sqrt((double)n), err);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
 }
 
 extern "C" int ldx_softmax_rows(const float* s, int64_t lds, void* out, int64_t ldo, int64_t rows, int n, float scale,

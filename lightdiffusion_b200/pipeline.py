@@ -15,7 +15,7 @@ import torch
 from . import _lib as L
 from .engine import UNetEngine, VAEDecoderEngine, VAEEncoderEngine, sigma_tables
 from .upscale import bislerp
-from .samplers import dpmpp2m_coefficients, get_ancestral_step, get_sigmas_karras
+from .samplers import dpmpp2m_coefficients, get_ancestral_step, get_sigmas_karras, sample_dpm_adaptive
 
 LATENT_SCALE = 0.18215          # SD15 latent format (LD.py:137-139)
 
@@ -74,6 +74,21 @@ class Txt2ImgPipeline:
         plan.set_context(torch.cat([uncond, cond]).to(dev))            # [uncond, cond] order, LD.py:2515
         launches += 1
         n = x.numel()
+        if sampler == "dpm_adaptive":
+            # dpm_adaptive_function (LD.py:2779-2797): sigma_min is the last non-zero sigma, sigma_max the first
+            if len(sig) <= 1:
+                return x / LATENT_SCALE
+            smin = sig[-1] if sig[-1] != 0 else sig[-2]
+            calls = [0]
+
+            def guided(xx, sigma_vec, **_):
+                calls[0] += 1
+                return plan.run(xx, sigma_vec, None, cfg_scale=cfg_scale)
+
+            xs, info = sample_dpm_adaptive(guided, x, float(smin), float(sig[0]), return_info=True)
+            self.gpu_launches = launches + calls[0] * plan.num_launches + info["steps"] * 9
+            self.sampler_info = info
+            return xs / LATENT_SCALE
         old = torch.empty_like(x)
         have_old, h_last = False, None
         for i in range(len(sig) - 1):

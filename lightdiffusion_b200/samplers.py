@@ -10,12 +10,14 @@ computed on the host from the sigmas with the same fp32 tensor arithmetic the re
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 from . import _lib as L
 
-__all__ = ["sample_dpmpp_2m", "sample_euler_ancestral", "get_ancestral_step", "get_sigmas_karras",
-           "dpmpp2m_coefficients"]
+__all__ = ["sample_dpmpp_2m", "sample_euler_ancestral", "sample_dpm_adaptive", "PIDStepSizeController",
+           "get_ancestral_step", "get_sigmas_karras", "dpmpp2m_coefficients"]
 
 
 def _stream():
@@ -115,4 +117,107 @@ def sample_euler_ancestral(model, x, sigmas, extra_args=None, callback=None, dis
                 "ldx_euler_ancestral_step")
         if callback is not None:
             callback({"x": x, "i": i, "sigma": sig[i], "sigma_hat": sig[i], "denoised": denoised})
+    return x
+
+
+class PIDStepSizeController:
+    """LD.py:944-973 (host scalars only)."""
+
+    def __init__(self, h, pcoeff, icoeff, dcoeff, order=1, accept_safety=0.81, eps=1e-8):
+        self.h = h
+        self.b1 = (pcoeff + icoeff + dcoeff) / order
+        self.b2 = -(pcoeff + 2 * dcoeff) / order
+        self.b3 = dcoeff / order
+        self.accept_safety = accept_safety
+        self.eps = eps
+        self.errs = []
+
+    def limiter(self, x):
+        return 1 + math.atan(x - 1)
+
+    def propose_step(self, error):
+        inv_error = 1 / (float(error) + self.eps)
+        if not self.errs:
+            self.errs = [inv_error, inv_error, inv_error]
+        self.errs[0] = inv_error
+        factor = self.errs[0] ** self.b1 * self.errs[1] ** self.b2 * self.errs[2] ** self.b3
+        factor = self.limiter(factor)
+        accept = factor >= self.accept_safety
+        if accept:
+            self.errs[2] = self.errs[1]
+            self.errs[1] = self.errs[0]
+        self.h *= factor
+        return accept
+
+
+@torch.no_grad()
+def sample_dpm_adaptive(model, x, sigma_min, sigma_max, extra_args=None, callback=None, disable=None, order=3,
+                        rtol=0.05, atol=0.0078, h_init=0.05, pcoeff=0.0, icoeff=1.0, dcoeff=0.0, accept_safety=0.81,
+                        eta=0.0, s_noise=1.0, noise_sampler=None, return_info=False):
+    """DPM-Solver-12 and 23 with adaptive step size: sample_dpm_adaptive / DPMSolver.dpm_solver_adaptive
+    (LD.py:1049-1170).  Per proposed step: three model calls (eps at s, s + h/3, s + 2h/3, shared by the embedded
+    2nd- and 3rd-order updates through the reference's eps cache), four fused state updates, one fused error-norm
+    reduction; the PID controller and every scalar coefficient run on the host with the reference's own 0-d fp32
+    tensor arithmetic.  The reference never adds noise on this path (``su`` is fixed at 0.0, LD.py:1086), so
+    ``eta`` only changes the controller's order, as it does there."""
+    if sigma_min <= 0 or sigma_max <= 0:
+        raise ValueError("sigma_min and sigma_max must not be 0")
+    extra_args = {} if extra_args is None else extra_args
+    _check_state(x)
+    lib, n, st = L.lib(), x.numel(), _stream()
+    sig_of = lambda t: t.neg().exp()
+    t_start = -torch.tensor(float(sigma_max)).log()
+    t_end = -torch.tensor(float(sigma_min)).log()
+    forward = bool(t_end > t_start)
+    h_init = abs(h_init) * (1 if forward else -1)
+    s = t_start
+    x = x.clone()
+    x_prev = x.clone()
+    ones = x.new_ones([x.shape[0]])
+    eps, eps_r1, eps_r2, u, x_low, x_high = (torch.empty_like(x) for _ in range(6))
+    ws = torch.empty(L.DPM_ERROR_WS_DOUBLES, dtype=torch.float64, device=x.device)
+    err = torch.empty(1, dtype=torch.float32, device=x.device)
+    pid = PIDStepSizeController(h_init, pcoeff, icoeff, dcoeff, 1.5 if eta else order, accept_safety)
+    info = {"steps": 0, "nfe": 0, "n_accept": 0, "n_reject": 0}
+
+    def model_eps(xx, t, out):
+        sg = float(sig_of(t))
+        den = model(xx, sg * ones, **extra_args)
+        _check_state(den)
+        L.check(lib.ldx_dpm_eps(xx.data_ptr(), den.data_ptr(), sg, out.data_ptr(), n, st), "ldx_dpm_eps")
+
+    def combine(c1, e2, c2, out):
+        L.check(lib.ldx_dpm_combine(x.data_ptr(), eps.data_ptr(), None if e2 is None else e2.data_ptr(), float(c1),
+                                    0.0 if c2 is None else float(c2), out.data_ptr(), n, st), "ldx_dpm_combine")
+
+    r1, r2 = 1 / 3, 2 / 3
+    while (s < t_end - 1e-5) if forward else (s > t_end + 1e-5):
+        t = torch.minimum(t_end, s + pid.h) if forward else torch.maximum(t_end, s + pid.h)
+        h = t - s
+        model_eps(x, s, eps)                                                       # eps(x, s)
+        s1, s2 = s + r1 * h, s + r2 * h
+        combine(sig_of(s1) * (r1 * h).expm1(), None, None, u)                      # u1 (shared by both orders)
+        model_eps(u, s1, eps_r1)
+        combine(sig_of(t) * h.expm1(), eps_r1, sig_of(t) / (2 * r1) * h.expm1(), x_low)       # x_2, LD.py:1009-1013
+        combine(sig_of(s2) * (r2 * h).expm1(), eps_r1,
+                sig_of(s2) * (r2 / r1) * ((r2 * h).expm1() / (r2 * h) - 1), u)                # u2, LD.py:1024-1031
+        model_eps(u, s2, eps_r2)
+        combine(sig_of(t) * h.expm1(), eps_r2, sig_of(t) / r2 * (h.expm1() / h - 1), x_high)  # x_3, LD.py:1033-1037
+        L.check(lib.ldx_dpm_error_norm(x_low.data_ptr(), x_high.data_ptr(), x_prev.data_ptr(), float(torch.tensor(atol)),
+                                       float(torch.tensor(rtol)), n, ws.data_ptr(), err.data_ptr(), st),
+                "ldx_dpm_error_norm")
+        accept = pid.propose_step(float(err))            # the one host sync of the step (float(error) in the reference)
+        if accept:
+            x_prev, x_low = x_low, x_prev
+            x, x_high = x_high, x
+            s = t
+            info["n_accept"] += 1
+        else:
+            info["n_reject"] += 1
+        info["nfe"] += order
+        info["steps"] += 1
+    # ``callback`` is accepted for signature compatibility: the reference stores it as info_callback (LD.py:1140-1147)
+    # and dpm_solver_adaptive never invokes it
+    if return_info:
+        return x, info
     return x

@@ -292,6 +292,58 @@ def sample_euler_ancestral(model, x, sigmas, extra_args=None, eta=1.0, s_noise=1
     return x
 
 
+def sample_dpm_adaptive(model, x, sigma_min, sigma_max, extra_args=None, order=3, rtol=0.05, atol=0.0078, h_init=0.05,
+                        pcoeff=0.0, icoeff=1.0, dcoeff=0.0, accept_safety=0.81, eta=0.0, return_info=False):
+    """sample_dpm_adaptive / DPMSolver.dpm_solver_adaptive, LD.py:1049-1170, with PIDStepSizeController (LD.py:944-973):
+    embedded DPM-Solver-2 (r1 = 1/3) and DPM-Solver-3 (r1 = 1/3, r2 = 2/3) sharing eps(x, s) and eps(u1, s1), an
+    error norm against max(atol, rtol * max(|x_low|, |x_prev|)), and an I-controller through 1 + atan(factor - 1)."""
+    extra_args = {} if extra_args is None else extra_args
+    sig = lambda t: t.neg().exp()
+    t_start, t_end = -torch.tensor(float(sigma_max)).log(), -torch.tensor(float(sigma_min)).log()
+    forward = bool(t_end > t_start)
+    h_cur = abs(h_init) * (1 if forward else -1)
+    atol_t, rtol_t = torch.tensor(atol), torch.tensor(rtol)
+    pid_order = 1.5 if eta else order
+    b1, b2, b3 = (pcoeff + icoeff + dcoeff) / pid_order, -(pcoeff + 2 * dcoeff) / pid_order, dcoeff / pid_order
+    errs = []
+    s, x_prev = t_start, x
+    info = {"steps": 0, "nfe": 0, "n_accept": 0, "n_reject": 0}
+
+    def eps_at(xx, t):
+        return (xx - model(xx, sig(t) * xx.new_ones([xx.shape[0]]), **extra_args)) / sig(t)
+
+    r1, r2 = 1 / 3, 2 / 3
+    while (s < t_end - 1e-5) if forward else (s > t_end + 1e-5):
+        t = torch.minimum(t_end, s + h_cur) if forward else torch.maximum(t_end, s + h_cur)
+        h = t - s
+        eps = eps_at(x, s)
+        s1, s2 = s + r1 * h, s + r2 * h
+        u1 = x - sig(s1) * (r1 * h).expm1() * eps
+        eps_r1 = eps_at(u1, s1)
+        x_low = x - sig(t) * h.expm1() * eps - sig(t) / (2 * r1) * h.expm1() * (eps_r1 - eps)
+        u2 = x - sig(s2) * (r2 * h).expm1() * eps - sig(s2) * (r2 / r1) * ((r2 * h).expm1() / (r2 * h) - 1) * (eps_r1 - eps)
+        eps_r2 = eps_at(u2, s2)
+        x_high = x - sig(t) * h.expm1() * eps - sig(t) / r2 * (h.expm1() / h - 1) * (eps_r2 - eps)
+        delta = torch.maximum(atol_t.to(x.device), rtol_t.to(x.device) * torch.maximum(x_low.abs(), x_prev.abs()))
+        error = torch.linalg.norm((x_low - x_high) / delta) / x.numel() ** 0.5
+        inv_error = 1 / (float(error) + 1e-8)
+        if not errs:
+            errs = [inv_error, inv_error, inv_error]
+        errs[0] = inv_error
+        factor = 1 + math.atan(errs[0] ** b1 * errs[1] ** b2 * errs[2] ** b3 - 1)
+        accept = factor >= accept_safety
+        if accept:
+            errs[2], errs[1] = errs[1], errs[0]
+            x_prev, x, s = x_low, x_high, t
+            info["n_accept"] += 1
+        else:
+            info["n_reject"] += 1
+        h_cur *= factor
+        info["nfe"] += order
+        info["steps"] += 1
+    return (x, info) if return_info else x
+
+
 # ----------------------------------------------------------------------------- VAE decoder
 def _vae_res(sd: SD, p: str, x):
     """ResnetBlock.forward, LD.py:3562-3576 (GN eps 1e-6)."""
@@ -479,6 +531,9 @@ def sample_latent(unet_sd: SD, ucfg: UNetConfig, noise, cond, uncond, cfg_scale:
         x = sample_dpmpp_2m(model, x, sigmas)
     elif sampler == "euler_ancestral":
         x = sample_euler_ancestral(model, x, sigmas, noise_sampler=noise_sampler)
+    elif sampler == "dpm_adaptive":            # dpm_adaptive_function, LD.py:2779-2797
+        smin = sigmas[-1] if sigmas[-1] != 0 else sigmas[-2]
+        x = sample_dpm_adaptive(model, x, float(smin), float(sigmas[0]))
     else:
         raise ValueError(sampler)
     return x.float() / LATENT_SCALE

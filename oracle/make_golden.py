@@ -217,6 +217,25 @@ def golden_clip(R):
                os.path.join(OUT, "clip_text.pt"))
 
 
+def golden_dpm_adaptive(R):
+    """Reference sample_dpm_adaptive (LD.py:1119) on the closed-form denoiser D(x,s) = x / (1 + s^2) and on a
+    non-linear one, with the accept / reject counts the PID controller produced."""
+    ms = R.ModelSamplingDiscrete(R.sm_SD15({}))
+    sig = R.calculate_sigmas(ms, "karras", 20)
+    g = torch.Generator().manual_seed(13)
+    x0 = torch.randn(3, 4, 8, 8, generator=g) * sig[0]
+    out = dict(x0=x0, sigma_min=float(sig[-2]), sigma_max=float(sig[0]), cases={},
+               source="sample_dpm_adaptive LD.py:1119-1170, DPMSolver LD.py:976-1116")
+    models = {"linear": lambda x, sigma, **kw: x / (1.0 + sigma.view(-1, 1, 1, 1) ** 2),
+              "tanh": lambda x, sigma, **kw: torch.tanh(x / (1.0 + sigma.view(-1, 1, 1, 1))) * 1.5}
+    for name, model in models.items():
+        for opts in (dict(), dict(rtol=0.01, atol=0.002, h_init=0.2), dict(eta=1.0, pcoeff=0.1, dcoeff=0.05)):
+            xr, info = R.sample_dpm_adaptive(model, x0.clone(), out["sigma_min"], out["sigma_max"], extra_args={},
+                                             disable=True, return_info=True, **opts)
+            out["cases"][(name, tuple(sorted(opts.items())))] = dict(x=xr.clone(), info=dict(info))
+    torch.save(out, os.path.join(OUT, "dpm_adaptive.pt"))
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -236,6 +255,7 @@ def main():
     golden_vae_encode(R)
     golden_bislerp(R)
     golden_clip(R)
+    golden_dpm_adaptive(R)
     golden_unet(R, "sd15_lat8", sd15.SD15_UNET, hw=8, b=2)   # real SD1.5 dims, small latent
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

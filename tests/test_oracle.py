@@ -141,3 +141,18 @@ def test_clip_text(golden):
         assert rel(c2, g["cond_2"]) < 2e-5 and rel(p2, g["pooled_2"]) < 2e-5
         cl, _ = O.clip_encode_token_weights(sd, cfg, [g["secs"][0]], None, g["empty"])
         assert rel(cl, g["cond_last"]) < 2e-5
+
+
+DPM_MODELS = {"linear": lambda x, sigma, **kw: x / (1.0 + sigma.view(-1, 1, 1, 1) ** 2),
+              "tanh": lambda x, sigma, **kw: torch.tanh(x / (1.0 + sigma.view(-1, 1, 1, 1))) * 1.5}
+
+
+def test_dpm_adaptive(golden):
+    """The DPM-Solver-12/23 restatement against the reference's sample_dpm_adaptive: same accepted / rejected step
+    counts (default, tight-tolerance and PID variants) and the same final state."""
+    g = golden("dpm_adaptive.pt")
+    for (name, opts), c in g["cases"].items():
+        x, info = O.sample_dpm_adaptive(DPM_MODELS[name], g["x0"].clone(), g["sigma_min"], g["sigma_max"],
+                                        return_info=True, **dict(opts))
+        assert info == c["info"], (name, opts, info, c["info"])
+        assert rel(x, c["x"]) < 2e-6, (name, opts)
