@@ -85,6 +85,25 @@ def test_unet_small_eps_parity(small_unet, hw, b):
         assert rel(e, ref) < EPS_TOL, (hw, b, s, rel(e, ref))
 
 
+@pytest.mark.parametrize("h,w,b", [(24, 40, 2), (8, 56, 1), (72, 88, 1), (96, 64, 1)])
+def test_unet_small_eps_parity_nonsquare(small_unet, h, w, b):
+    """Portrait / landscape latents (512x768 is 64x96): widths that are not powers of two, token counts that are
+    not multiples of the 128-query / 64-key attention tiles (24x40 -> 960, 240, 60, 15 tokens per level)."""
+    cfg, sd, eng = small_unet
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(b, 4, h, w, generator=g).to(DEV)
+    ctx = torch.randn(b, 77, cfg.context_dim, generator=g).to(DEV)
+    for s in (7.5, 0.3):
+        sigma = torch.full((b,), s, device=DEV)
+        xs = x * math.sqrt(1 + s * s)
+        e = eng.eps(xs, sigma, ctx)
+        ref = _oracle_eps(sd, cfg, xs, sigma, ctx)
+        assert e.shape == (b, 4, h, w)
+        assert rel(e, ref) < EPS_TOL, (h, w, b, s, rel(e, ref))
+    with pytest.raises(Exception):
+        eng.eps(torch.zeros(1, 4, 20, 24, device=DEV), torch.ones(1, device=DEV), ctx[:1])   # 20 is not a multiple of 8
+
+
 def test_unet_small_graph_equals_eager_and_is_deterministic(small_unet):
     cfg, sd, eng = small_unet
     x, ctx = _inputs(2, 16, cfg.context_dim, 8)
