@@ -513,6 +513,36 @@ def clip_encode_token_weights(sd: SD, cfg, token_weight_pairs, layer_idx: Option
     return torch.cat(zs, dim=-2), pooled[0:1].float()
 
 
+# ----------------------------------------------------------------------------- ESRGAN upscaler
+def esrgan_forward(sd: SD, x):
+    """RRDBNet.forward, LD.py:7073-7140 / 7224: conv_first -> ShortcutBlock(RRDB x nb -> trunk conv) -> (nearest 2x ->
+    conv -> LeakyReLU) x log2(scale) -> HR conv -> LeakyReLU -> last conv.  RRDB (LD.py:6897-6902) = three
+    ResidualDenseBlock_5C (LD.py:6990-6997), each x5 * 0.2 + x over a dense 5-conv stack with LeakyReLU(0.2)
+    (act(), LD.py:6767-6770); the RRDB output is again out * 0.2 + x.  x is NCHW."""
+    from lightdiffusion_b200.esrgan import to_old_arch          # key renaming only (new_to_old_arch, LD.py:7142-7199)
+    sd = to_old_arch(sd)
+    lrelu = lambda t: F.leaky_relu(t, 0.2)
+    c3 = lambda name, t: F.conv2d(t, sd[name + ".weight"], sd[name + ".bias"], padding=1)
+    nb = max(int(k.split(".")[3]) for k in sd if ".RDB1.conv1.0.weight" in k) + 1
+    fea = c3("model.0", x)
+    h = fea
+    for i in range(nb):
+        r = h
+        for j in (1, 2, 3):
+            p = f"model.1.sub.{i}.RDB{j}"
+            xs = [r]
+            for k in range(1, 5):
+                xs.append(lrelu(c3(f"{p}.conv{k}.0", torch.cat(xs, 1))))
+            r = c3(f"{p}.conv5.0", torch.cat(xs, 1)) * 0.2 + r
+        h = r * 0.2 + h
+    h = fea + c3(f"model.1.sub.{nb}", h)
+    tops = sorted(int(k.split(".")[1]) for k in sd if k.count(".") == 2 and k.endswith(".weight") and k != "model.0.weight")
+    for n in tops[:-2]:
+        h = lrelu(c3(f"model.{n}", F.interpolate(h, scale_factor=2, mode="nearest")))
+    h = lrelu(c3(f"model.{tops[-2]}", h))
+    return c3(f"model.{tops[-1]}", h)
+
+
 # ----------------------------------------------------------------------------- pipeline
 LATENT_SCALE = 0.18215      # SD15 latent format, LD.py:137-139
 

@@ -236,6 +236,24 @@ def golden_dpm_adaptive(R):
     torch.save(out, os.path.join(OUT, "dpm_adaptive.pt"))
 
 
+def golden_esrgan(R):
+    """Reference RRDBNet (LD.py:7025) built from seeded old-arch state dicts (2 RRDB blocks to keep the fixture small):
+    a 4x and a 2x model on small images."""
+    from lightdiffusion_b200.esrgan import esrgan_param_shapes
+    out = dict(cases={}, init=INIT, source="RRDBNet LD.py:7025-7225 via load_state_dict LD.py:7245")
+    g = torch.Generator().manual_seed(15)
+    for name, (nb, scale, seed, hw, arch) in dict(x4=(2, 4, 301, (20, 28), "realesrgan"),
+                                                  x2=(3, 2, 302, (16, 16), "esrgan")).items():
+        sd = sd15.seeded_state_dict(esrgan_param_shapes(nb, scale, arch=arch), seed, **INIT)
+        model = R.load_state_dict(dict(sd)).eval()
+        assert model.scale == scale and model.num_blocks == nb, (model.scale, model.num_blocks)
+        x = torch.rand(2, 3, *hw, generator=g)
+        with torch.inference_mode():
+            y = model(x)
+        out["cases"][name] = dict(num_blocks=nb, scale=scale, seed=seed, arch=arch, x=x, y=y.clone())
+    torch.save(out, os.path.join(OUT, "esrgan.pt"))
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -256,6 +274,7 @@ def main():
     golden_bislerp(R)
     golden_clip(R)
     golden_dpm_adaptive(R)
+    golden_esrgan(R)
     golden_unet(R, "sd15_lat8", sd15.SD15_UNET, hw=8, b=2)   # real SD1.5 dims, small latent
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

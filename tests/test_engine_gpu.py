@@ -350,3 +350,38 @@ def test_clip_encode_token_weights_matches_reference_golden(clip_eng):
     print("clip token weights vs reference golden", errs)
     assert cw.shape == (1, 77, 768) and c2.shape == (1, 154, 768) and pw.shape == (1, 768)
     assert max(errs) < COND_TOL
+
+
+# ------------------------------------------------------------------------------------ ESRGAN upscaler
+def test_esrgan_matches_reference_golden(golden):
+    """RRDBNet outputs of the real reference (fp32 weights) vs the engine (fp16 weights and activations)."""
+    from lightdiffusion_b200.esrgan import ESRGANEngine, esrgan_param_shapes
+    g = golden("esrgan.pt")
+    for name, c in g["cases"].items():
+        sd = sd15.seeded_state_dict(esrgan_param_shapes(c["num_blocks"], c["scale"], arch=c["arch"]), c["seed"], **g["init"])
+        eng = ESRGANEngine({k: v.to(DEV) for k, v in sd.items()})
+        assert eng.scale == c["scale"] and eng.num_blocks == c["num_blocks"]
+        y = eng(c["x"].to(DEV))
+        print("esrgan", name, "rel", rel(y.cpu(), c["y"]), "psnr", psnr(y.cpu(), c["y"]))
+        assert y.shape == c["y"].shape and y.dtype == torch.float32
+        assert rel(y.cpu(), c["y"]) < 5e-3
+    with pytest.raises(Exception):
+        eng(c["x"])                                   # CPU tensor: no fallback
+    with pytest.raises(Exception):
+        ESRGANEngine({"foo.weight": torch.zeros(1)})
+
+
+@pytest.mark.parametrize("b,h,w", [(1, 64, 64), (2, 40, 72), (1, 256, 256)])
+def test_esrgan_parity_full_depth(b, h, w):
+    """23-block 4x model (the Real-ESRGAN x4 shape) against the oracle on fp16-rounded weights; 256x256 is a tile of
+    the reference's tiled_scale at half size."""
+    from lightdiffusion_b200.esrgan import ESRGANEngine, esrgan_param_shapes
+    sd = rounded(sd15.seeded_state_dict(esrgan_param_shapes(23, 4), 303, bias_std=0.05))
+    eng = ESRGANEngine(sd)
+    x = torch.rand(b, 3, h, w, generator=torch.Generator().manual_seed(9)).to(DEV)
+    y = eng(x)
+    with torch.inference_mode():
+        ref = O.esrgan_forward(sd, x)
+    print("esrgan full depth", (b, h, w), "rel", rel(y, ref))
+    assert y.shape == (b, 3, 4 * h, 4 * w)
+    assert rel(y, ref) < 5e-3

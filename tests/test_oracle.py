@@ -156,3 +156,19 @@ def test_dpm_adaptive(golden):
                                         return_info=True, **dict(opts))
         assert info == c["info"], (name, opts, info, c["info"])
         assert rel(x, c["x"]) < 2e-6, (name, opts)
+
+
+def test_esrgan(golden):
+    """The RRDBNet restatement against the reference's model built by its own loader from both checkpoint layouts."""
+    from lightdiffusion_b200.esrgan import esrgan_param_shapes, to_old_arch
+    g = golden("esrgan.pt")
+    for name, c in g["cases"].items():
+        sd = sd15.seeded_state_dict(esrgan_param_shapes(c["num_blocks"], c["scale"], arch=c["arch"]), c["seed"], **g["init"])
+        with torch.inference_mode():
+            y = O.esrgan_forward(sd, c["x"])
+        assert y.shape == c["y"].shape == (2, 3, c["x"].shape[2] * c["scale"], c["x"].shape[3] * c["scale"])
+        assert rel(y, c["y"]) < 2e-5, name
+        # the three layouts name the same tensors
+        old = to_old_arch(sd)
+        assert list(old) == list(esrgan_param_shapes(c["num_blocks"], c["scale"], arch="old")) or \
+            set(old) == set(esrgan_param_shapes(c["num_blocks"], c["scale"], arch="old"))
