@@ -65,6 +65,7 @@ typedef struct {
                                weight rows must be interleaved by ldx_pack_geglu; out has N/2 columns */
 #define LDX_EPI_OUT_F32 4   /* store fp32 instead of fp16 */
 #define LDX_EPI_LRELU 32    /* out = max(x, 0.2 x), x = acc + bias (+ residual)  (ESRGAN conv_block act, LD.py:6767-6770) */
+#define LDX_EPI_RELU 64     /* out = max(x, 0), x = acc + bias (+ residual)  (TAESD Block, LD.py:695-703) */
 #define LDX_EPI_QUICK_GELU 16 /* out = x * sigmoid(1.702 x), x = acc + bias  (CLIPMLP quick_gelu, LD.py:4296-4321) */
 #define LDX_EPI_ROWNORM 8   /* LayerNorm of the A rows folded into the GEMM (F.layer_norm LD.py:2403 followed by
                                F.linear LD.py:2368): with w' = w * gamma (caller-folded), gsum[n] = sum_k w'[n,k] and

@@ -17,6 +17,7 @@ EPI_OUT_F32 = 4
 EPI_ROWNORM = 8
 EPI_QUICK_GELU = 16
 EPI_LRELU = 32
+EPI_RELU = 64
 DPM_ERROR_WS_DOUBLES = 2048
 
 OP_GEMM, OP_GROUP_NORM, OP_LAYER_NORM, OP_ATTENTION = 1, 2, 3, 4

@@ -429,8 +429,10 @@ static int layer_norm_impl(const void* x, int64_t ldx_, int rows, int C, float e
 }
 
 // ----------------------------------------------------------------------------- layout / small ops
+// mode 0: plain (optionally scaled by 1/sqrt(sigma^2+1)); 1: TAESD decoder Clamp, tanh(x / 3) * 3 (LD.py:691-693);
+// 2: TAESD encoder input, x * 0.5 + 0.5 (LD.py:759)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ sigma,
-                                    __half* __restrict__ y, int B, int C, int HW, int Cpad) {
+                                    __half* __restrict__ y, int B, int C, int HW, int Cpad, int mode) {
   const int64_t total = (int64_t)B * HW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int b = (int)(i / HW);
@@ -441,6 +443,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, const float* __
       if (c < C) {
         const float xv = x[((int64_t)b * C + c) * HW + pix];
         v = sigma ? xv / sqrtf(sigma[b] * sigma[b] + 1.0f) : xv;
+        if (mode == 1) v = tanhf(v / 3.0f) * 3.0f;
+        else if (mode == 2) v = v * 0.5f + 0.5f;
       }
       o[c] = __float2half_rn(v);
     }
@@ -812,10 +816,10 @@ int run_generic_op(const ldx_generic_op_t* op, cudaStream_t st) {
       // p: x, gamma, beta, y ; i: rows, C ; l: ldx, ldy ; f: eps
       return layer_norm_impl(p[0], l[0], i[0], i[1], f[0], (const float*)p[1], (const float*)p[2], (void*)p[3], l[1], st);
     case LDX_OP_NCHW_TO_NHWC: {
-      // p: x, sigma, y ; i: B, C, H, W, Cpad
+      // p: x, sigma, y ; i: B, C, H, W, Cpad, mode
       const int64_t n = (int64_t)i[0] * i[2] * i[3];
       nchw_to_nhwc_kernel<<<ew_blocks(n), 256, 0, st>>>((const float*)p[0], (const float*)p[1], (__half*)p[2], i[0],
-                                                        i[1], i[2] * i[3], i[4]);
+                                                        i[1], i[2] * i[3], i[4], i[5]);
       LDX_CUDA(cudaGetLastError());
       return LDX_OK;
     }

@@ -125,10 +125,11 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, uint32_t tm
   }
   if (!row_valid) return;
   const int n_out_total = kGeglu ? p.N / 2 : p.N;
-  if (p.flags & (LDX_EPI_SILU | LDX_EPI_QUICK_GELU | LDX_EPI_LRELU)) {
-    if (p.flags & LDX_EPI_LRELU) {
+  if (p.flags & (LDX_EPI_SILU | LDX_EPI_QUICK_GELU | LDX_EPI_LRELU | LDX_EPI_RELU)) {
+    if (p.flags & (LDX_EPI_LRELU | LDX_EPI_RELU)) {
+      const float slope = (p.flags & LDX_EPI_RELU) ? 0.0f : 0.2f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], slope * v[j]);
     } else {
       const float nk = (p.flags & LDX_EPI_QUICK_GELU) ? -1.702f * 1.4426950408889634f : -1.4426950408889634f;
 #pragma unroll
@@ -498,10 +499,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               __syncwarp();
               if (lane == 0) release_tmem(as);
             }
-            if (p.flags & (LDX_EPI_SILU | LDX_EPI_QUICK_GELU | LDX_EPI_LRELU)) {
-              if (p.flags & LDX_EPI_LRELU) {
+            if (p.flags & (LDX_EPI_SILU | LDX_EPI_QUICK_GELU | LDX_EPI_LRELU | LDX_EPI_RELU)) {
+              if (p.flags & (LDX_EPI_LRELU | LDX_EPI_RELU)) {
+                const float slope = (p.flags & LDX_EPI_RELU) ? 0.0f : 0.2f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], slope * v[j]);
               } else {
                 const float nk = (p.flags & LDX_EPI_QUICK_GELU) ? -1.702f * 1.4426950408889634f : -1.4426950408889634f;
 #pragma unroll
@@ -606,9 +608,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const SplitReduce r)
       const float2 a0 = unpack_h2(rr.x), a1 = unpack_h2(rr.y);
       acc.x += a0.x; acc.y += a0.y; acc.z += a1.x; acc.w += a1.y;
     }
-    if (r.silu == 3) {            // LeakyReLU(0.2)
-      acc.x = fmaxf(acc.x, 0.2f * acc.x); acc.y = fmaxf(acc.y, 0.2f * acc.y);
-      acc.z = fmaxf(acc.z, 0.2f * acc.z); acc.w = fmaxf(acc.w, 0.2f * acc.w);
+    if (r.silu >= 3) {            // 3 = LeakyReLU(0.2), 4 = ReLU
+      const float slope = r.silu == 4 ? 0.0f : 0.2f;
+      acc.x = fmaxf(acc.x, slope * acc.x); acc.y = fmaxf(acc.y, slope * acc.y);
+      acc.z = fmaxf(acc.z, slope * acc.z); acc.w = fmaxf(acc.w, slope * acc.w);
     } else if (r.silu) {          // 1 = SiLU, 2 = quick_gelu
       const float nk = r.silu == 2 ? -1.702f * 1.4426950408889634f : -1.4426950408889634f;
       acc.x = sigmoid_gate_f(acc.x, nk); acc.y = sigmoid_gate_f(acc.y, nk);
@@ -945,7 +948,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     p.split_stride = rows * d->N;
     g->ws_bytes = (size_t)nsplit * (size_t)p.split_stride * sizeof(float);
     g->red = SplitReduce{nullptr, nsplit, p.split_stride, (int)rows, d->N, d->W, d->H, d->bias, d->rowadd, d->ld_rowadd,
-                         d->residual, d->ldr, (d->flags & LDX_EPI_SILU) ? 1 : ((d->flags & LDX_EPI_QUICK_GELU) ? 2 : ((d->flags & LDX_EPI_LRELU) ? 3 : 0)), d->out,
+                         d->residual, d->ldr, (d->flags & LDX_EPI_SILU) ? 1 : ((d->flags & LDX_EPI_QUICK_GELU) ? 2 : ((d->flags & LDX_EPI_LRELU) ? 3 : ((d->flags & LDX_EPI_RELU) ? 4 : 0))), d->out,
                          d->o_sx,
                          d->o_sy > 0 ? d->o_sy : d->o_sx * d->W,
                          d->o_sb > 0 ? d->o_sb : (d->o_sy > 0 ? d->o_sy : d->o_sx * d->W) * d->H, d->o_off};

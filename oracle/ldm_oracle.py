@@ -543,6 +543,37 @@ def esrgan_forward(sd: SD, x):
     return c3(f"model.{tops[-1]}", h)
 
 
+# ----------------------------------------------------------------------------- TAESD
+def _taesd_stack(sd: SD, layout, x):
+    """Decoder2 / Encoder2 as nn.Sequential index lists (LD.py:705-723); Block = relu(conv-relu-conv-relu-conv(x) + x)."""
+    c3 = lambda n, t, stride=1: F.conv2d(t, sd[n + ".weight"], sd.get(n + ".bias"), stride=stride, padding=1)
+    for kind, i in layout:
+        if kind == "block":
+            h = c3(f"{i}.conv.4", F.relu(c3(f"{i}.conv.2", F.relu(c3(f"{i}.conv.0", x)))))
+            x = F.relu(h + x)
+        elif kind == "upconv":
+            x = c3(str(i), F.interpolate(x, scale_factor=2, mode="nearest"))
+        elif kind == "down":
+            x = c3(str(i), x, 2)
+        elif kind == "conv_relu":
+            x = F.relu(c3(str(i), x))
+        else:
+            x = c3(str(i), x)
+    return x
+
+
+def taesd_decode(sd: SD, latent):
+    """TAESD.decode, LD.py:748-753: Clamp (tanh(x/3)*3) -> Decoder2 -> .sub(0.5).mul(2); vae_shift 0, vae_scale 1."""
+    from lightdiffusion_b200.taesd import DECODER_LAYOUT
+    return _taesd_stack(sd, DECODER_LAYOUT, torch.tanh(latent / 3) * 3).sub(0.5).mul(2)
+
+
+def taesd_encode(sd: SD, image):
+    """TAESD.encode, LD.py:756-759: Encoder2(x * 0.5 + 0.5)."""
+    from lightdiffusion_b200.taesd import ENCODER_LAYOUT
+    return _taesd_stack(sd, ENCODER_LAYOUT, image * 0.5 + 0.5)
+
+
 # ----------------------------------------------------------------------------- pipeline
 LATENT_SCALE = 0.18215      # SD15 latent format, LD.py:137-139
 

@@ -254,6 +254,26 @@ def golden_esrgan(R):
     torch.save(out, os.path.join(OUT, "esrgan.pt"))
 
 
+def golden_taesd(R):
+    """Reference Decoder2 / Encoder2 (LD.py:705-723) with seeded weights, wrapped the way TAESD.decode / encode do
+    (LD.py:748-759; TAESD() itself insists on a weights file that is not in the checkout)."""
+    from lightdiffusion_b200.taesd import taesd_param_shapes
+    g = torch.Generator().manual_seed(16)
+    dsd = sd15.seeded_state_dict(taesd_param_shapes("decoder"), 401, **INIT)
+    esd = sd15.seeded_state_dict(taesd_param_shapes("encoder"), 402, **INIT)
+    dec, enc = R.Decoder2(), R.Encoder2()
+    dec.load_state_dict(dsd, strict=True)
+    enc.load_state_dict(esd, strict=True)
+    lat = torch.randn(2, 4, 8, 12, generator=g) * 2.5
+    img = torch.rand(2, 3, 64, 48, generator=g) * 2 - 1
+    with torch.inference_mode():
+        y = dec(lat).sub(0.5).mul(2)
+        z = enc(img * 0.5 + 0.5)
+    torch.save(dict(latent=lat, decoded=y.clone(), image=img, encoded=z.clone(), seeds=(401, 402), init=INIT,
+                    source="Decoder2 / Encoder2 LD.py:705-723, TAESD.decode / encode LD.py:748-759"),
+               os.path.join(OUT, "taesd.pt"))
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -275,6 +295,7 @@ def main():
     golden_clip(R)
     golden_dpm_adaptive(R)
     golden_esrgan(R)
+    golden_taesd(R)
     golden_unet(R, "sd15_lat8", sd15.SD15_UNET, hw=8, b=2)   # real SD1.5 dims, small latent
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -385,3 +385,28 @@ def test_esrgan_parity_full_depth(b, h, w):
     print("esrgan full depth", (b, h, w), "rel", rel(y, ref))
     assert y.shape == (b, 3, 4 * h, 4 * w)
     assert rel(y, ref) < 5e-3
+
+
+# ------------------------------------------------------------------------------------ TAESD previews
+def test_taesd_matches_reference_golden(golden):
+    from lightdiffusion_b200.taesd import TAESDEngine, taesd_param_shapes
+    g = golden("taesd.pt")
+    dsd = sd15.seeded_state_dict(taesd_param_shapes("decoder"), g["seeds"][0], **g["init"])
+    esd = sd15.seeded_state_dict(taesd_param_shapes("encoder"), g["seeds"][1], **g["init"])
+    eng = TAESDEngine({k: v.to(DEV) for k, v in dsd.items()}, {k: v.to(DEV) for k, v in esd.items()})
+    y = eng.decode(g["latent"].to(DEV))
+    z = eng.encode(g["image"].to(DEV))
+    print("taesd vs reference golden: decode", rel(y.cpu(), g["decoded"]), "encode", rel(z.cpu(), g["encoded"]))
+    assert y.shape == g["decoded"].shape and z.shape == g["encoded"].shape
+    assert rel(y.cpu(), g["decoded"]) < 5e-3 and rel(z.cpu(), g["encoded"]) < 5e-3
+    # the 64x64 latent of a 512x512 image, against the oracle on fp16-rounded weights
+    dr = rounded(dsd)
+    lat = (torch.randn(3, 4, 64, 64, generator=torch.Generator().manual_seed(2)) * 2).to(DEV)
+    eng2 = TAESDEngine(dr)
+    with torch.inference_mode():
+        ref = O.taesd_decode(dr, lat)
+    assert rel(eng2.decode(lat), ref) < 5e-3
+    with pytest.raises(Exception):
+        eng2.encode(torch.zeros(1, 3, 64, 64, device=DEV))      # built without encoder weights
+    with pytest.raises(Exception):
+        eng.decode(g["latent"])                                   # CPU tensor

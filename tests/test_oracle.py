@@ -172,3 +172,15 @@ def test_esrgan(golden):
         old = to_old_arch(sd)
         assert list(old) == list(esrgan_param_shapes(c["num_blocks"], c["scale"], arch="old")) or \
             set(old) == set(esrgan_param_shapes(c["num_blocks"], c["scale"], arch="old"))
+
+
+def test_taesd(golden):
+    """The TAESD restatement against the reference's Decoder2 / Encoder2 stacks."""
+    from lightdiffusion_b200.taesd import taesd_param_shapes
+    g = golden("taesd.pt")
+    dsd = sd15.seeded_state_dict(taesd_param_shapes("decoder"), g["seeds"][0], **g["init"])
+    esd = sd15.seeded_state_dict(taesd_param_shapes("encoder"), g["seeds"][1], **g["init"])
+    with torch.inference_mode():
+        assert rel(O.taesd_decode(dsd, g["latent"]), g["decoded"]) < 2e-5
+        assert rel(O.taesd_encode(esd, g["image"]), g["encoded"]) < 2e-5
+    assert g["decoded"].shape == (2, 3, 64, 96) and g["encoded"].shape == (2, 4, 8, 6)
