@@ -33,6 +33,7 @@ int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* 
 static constexpr int BQ = 128;
 static constexpr int BKV = 64;
 static constexpr int ATT_MAX_NG = 4;
+static constexpr int ATT_MAX_ST = 6;        // K / V ring depth bound
 #ifndef LDX_ATT_DBG
 #define LDX_ATT_DBG 0           // timing experiments only: 1 = no exponentials
 #endif
@@ -60,11 +61,16 @@ struct AttnCfg {
   // set to 1.0 after it lands, so O[:, D] accumulates sum_j P_ij and the softmax warps skip 64 FADDs a tile.
   static constexpr bool ONES = (DN > D) && (LDX_ATT_ONES != 0);
   // single-group CTAs (short K/V: cross-attention) stay small so that several fit on an SM
-  static constexpr int KST = (DCH == 1 && NG == 1) ? 1 : 2;
-  static constexpr int VST = (DCH == 1 && NG > 1) ? 2 : 1;
+#ifndef LDX_ATT_KST_NG
+#define LDX_ATT_KST_NG 2        // K / V ring depth and P buffers of the multi-group (d <= 64) configuration
+#define LDX_ATT_VST_NG 2
+#define LDX_ATT_PB_NG 2
+#endif
+  static constexpr int KST = (DCH == 1 && NG > 1) ? LDX_ATT_KST_NG : ((DCH == 1 && NG == 1) ? 1 : 2);
+  static constexpr int VST = (DCH == 1 && NG > 1) ? LDX_ATT_VST_NG : 1;
   static constexpr int Q_BYTES = DCH * BQ * 128;    // per group
   static constexpr int KV_BYTES = DCH * BKV * 128;
-  static constexpr int PB = (DCH == 1 && NG > 1) ? 2 : 1;   // P tiles per group: with one, P(j) waits for P V(j-1) to drain
+  static constexpr int PB = (DCH == 1 && NG > 1) ? LDX_ATT_PB_NG : 1;   // P tiles per group: with one, P(j) waits for P V(j-1) to drain
   static constexpr int P_BYTES = BQ * BKV * 2;      // per group and buffer
   static constexpr int TMEM_NEED = NG * (BKV + DN);
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
@@ -79,11 +85,12 @@ struct AttnCfg {
   static constexpr int MIN_BLOCKS = B1 < 1 ? 1 : B1;
   static_assert(TMEM_NEED <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "smem budget");
+  static_assert(KST <= ATT_MAX_ST && VST <= ATT_MAX_ST, "ring depth");
 };
 
-struct AttnBarriers {
+struct AttnBarriers {           // must fit the 512 bytes reserved in AttnCfg::SMEM
   uint64_t q_full[ATT_MAX_NG], s_full[ATT_MAX_NG], s_free[ATT_MAX_NG], p_full[ATT_MAX_NG][2], pv_done[ATT_MAX_NG][2];
-  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2], v_ready[2];
+  uint64_t k_full[ATT_MAX_ST], k_empty[ATT_MAX_ST], v_full[ATT_MAX_ST], v_empty[ATT_MAX_ST], v_ready[ATT_MAX_ST];
   uint32_t tmem_base;
 };
 
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
         mbar_init(&bars->pv_done[g][i], 1);
       }
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ATT_MAX_ST; ++i) {
       mbar_init(&bars->k_full[i], 1);
       mbar_init(&bars->k_empty[i], ng_act);    // one tcgen05.commit per active group
       mbar_init(&bars->v_full[i], 1);
