@@ -56,7 +56,20 @@ struct AttnCfg {
   static constexpr int DCH = (D + 63) / 64;         // 64-column smem chunks per row
   static constexpr int DN = DK * 16;                // UMMA N of P V
   static constexpr int NG = NG_;                    // 128-row query groups per CTA
-  static constexpr int THREADS = 32 * (2 + NG + 4 * NG);   // producer, V patcher, NG MMA issuers, 4 softmax warps / group
+  // Register rebalancing (setmaxnreg) for the multi-group configuration: the helper warps (producer, V patcher, NG MMA
+  // issuers, padded to two whole warpgroups) drop to 32 registers and the softmax warpgroups rise from the launch-time
+  // 80 to 104, so that a softmax thread holds a whole 64-key S row: one TMEM round trip per tile, S released to the
+  // next Q K^T before any exponential, one running-max test per tile, no spills.
+#ifndef LDX_ATT_REBALANCE
+#define LDX_ATT_REBALANCE 1
+#endif
+#ifndef LDX_ATT_HELPER_REGS
+#define LDX_ATT_HELPER_REGS 40     // 256 * helper + 512 * softmax <= 768 * 80 (the launch-time allocation)
+#define LDX_ATT_SOFTMAX_REGS 96
+#endif
+  static constexpr bool REBAL = (NG_ > 1) && (LDX_ATT_REBALANCE != 0);
+  static constexpr int HELPERS = REBAL ? 8 : 2 + NG_;     // warps before the first softmax warp
+  static constexpr int THREADS = 32 * (HELPERS + 4 * NG);  // producer, V patcher, NG MMA issuers, 4 softmax warps / group
   // Row sums on the tensor core: when P V has a spare accumulator column (DN > D) the V tile's column D is
   // set to 1.0 after it lands, so O[:, D] accumulates sum_j P_ij and the softmax warps skip 64 FADDs a tile.
   static constexpr bool ONES = (DN > D) && (LDX_ATT_ONES != 0);
@@ -171,6 +184,10 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
   const uint32_t tO = tmem_base + NG * BKV;           // group g: DN fp32 columns at g * DN
   pdl_prologue();
 
+  // With register rebalancing the roles split at warpgroup granularity first, so that each setmaxnreg dominates the
+  // code of its side (ptxas budgets registers per region): warps 0-7 helpers, 8.. softmax.
+  if (warp < C::HELPERS) {
+  if constexpr (C::REBAL) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LDX_ATT_HELPER_REGS));
   if (warp == 0) {
     // ---- TMA producer: warp-uniform loop, one elected lane issues.  K runs one tile ahead of V: the K
     // buffer frees as soon as every group's S = Q K^T has been issued, the V buffer only after the softmax.
@@ -275,11 +292,14 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
         __syncwarp();
       }
     }
-  } else if ((warp - 2 - NG) / 4 < ng_act) {
+  }
+  } else {
+  if constexpr (C::REBAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LDX_ATT_SOFTMAX_REGS));
+  if ((warp - C::HELPERS) / 4 < ng_act) {
     // ------------------------------------------------------------------ softmax warps (thread = query row)
     // Online softmax at HALF-tile granularity (32 keys): one TMEM read per score, 32 live score registers,
     // and the running-max test sits on a 32-element chain instead of a 64-element one.
-    const int g = (warp - 2 - NG) / 4;
+    const int g = (warp - C::HELPERS) / 4;
     const int qd = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
     const uint32_t lane_off = (uint32_t)(qd * 32) << 16;
@@ -292,6 +312,98 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
     const float c = p.scale_log2;
     float m_used = -INFINITY;   // row max the exponentials are relative to (raw score units)
     float l = 0.f;
+    if constexpr (C::REBAL) {
+      // ---- whole-tile variant (104 registers): S row in registers, S released at once, one max test per tile
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(s_full, j & 1);
+        tc_fence_after();
+        const int pb = j % C::PB;
+        uint8_t* prow = prow0 + pb * C::P_BYTES;
+        const int kv_left = p.Nk - j * BKV;
+        uint32_t ra[32], rb[32];
+        tmem_ld32(tSg, ra);
+        tmem_ld32(tSg + 32, rb);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);     // S(j) is in registers: the accumulator may be reused
+        float s[64];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s[i] = __uint_as_float(ra[i]);
+          s[32 + i] = __uint_as_float(rb[i]);
+        }
+        if (kv_left < BKV) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i)
+            if (i >= kv_left) s[i] = -INFINITY;
+        }
+        if constexpr (CAUSAL) {
+          const int k0 = j * BKV, qi = q_cta + g * BQ + row;
+          if (k0 + 63 > qi) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+              if (k0 + i > qi) s[i] = -INFINITY;
+          }
+        }
+        float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+#pragma unroll
+        for (int i = 4; i < 64; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
+          mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+        }
+        const float m_t = fmaxf(mx0, mx1);
+        const bool grow = (m_t - m_used) * c > 8.0f;
+        if (j == 0) {
+          m_used = m_t;
+        } else if (__any_sync(0xffffffffu, grow)) {
+          const float m_new = fmaxf(m_used, m_t);
+          const float alpha = ex2_approx((m_used - m_new) * c);
+          m_used = m_new;
+          if constexpr (!C::ONES) l *= alpha;
+          mbar_wait(pv_done + (j - 1) % C::PB, ((j - 1) / C::PB) & 1);     // O is quiescent
+          tc_fence_after();
+          // four columns at a time: the 64 live score registers leave little room in this (rare) path
+#pragma unroll 1
+          for (int cc = 0; cc < C::DN / 4; ++cc) {
+            uint32_t o0, o1, o2, o3;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(o0), "=r"(o1), "=r"(o2), "=r"(o3) : "r"(tOg + cc * 4) : "memory");
+            tmem_ld_wait();
+            o0 = __float_as_uint(__uint_as_float(o0) * alpha);
+            o1 = __float_as_uint(__uint_as_float(o1) * alpha);
+            o2 = __float_as_uint(__uint_as_float(o2) * alpha);
+            o3 = __float_as_uint(__uint_as_float(o3) * alpha);
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%4], {%0, %1, %2, %3};"
+                         :: "r"(o0), "r"(o1), "r"(o2), "r"(o3), "r"(tOg + cc * 4) : "memory");
+          }
+          tmem_st_wait();
+        }
+        const float mc = m_used * c;
+        if (j >= C::PB) mbar_wait(pv_done + pb, ((j - C::PB) / C::PB) & 1);   // P V(j - PB) has read this buffer
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {       // 64 keys = 8 16-byte chunks; chunk index XOR (row % 8) = SWIZZLE_128B
+          uint32_t pk[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = ch * 8 + 2 * i;
+            const float p0 = ex2_approx(fmaf(s[e], c, -mc)), p1 = ex2_approx(fmaf(s[e + 1], c, -mc));
+            if constexpr (!C::ONES) {
+              l0 += p0;
+              l1 += p1;
+            }
+            pk[i] = pack_h2(p0, p1);
+          }
+          *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        l += l0 + l1;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full + pb);
+      }
+    } else
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
@@ -442,6 +554,8 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
         }
       }
     }
+  }
+
   }
 
   tc_fence_before();
