@@ -301,8 +301,9 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
   if constexpr (C::REBAL) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LDX_ATT_SOFTMAX_REGS));
   if ((warp - C::HELPERS) / 4 < ng_act) {
     // ------------------------------------------------------------------ softmax warps (thread = query row)
-    // Online softmax at HALF-tile granularity (32 keys): one TMEM read per score, 32 live score registers,
-    // and the running-max test sits on a 32-element chain instead of a 64-element one.
+    // Online softmax, one 64-key tile at a time with the whole S row in registers (WHOLE, the default everywhere).
+    // The HALF-tile (32 key) variant below it is the fallback for LDX_ATT_REBALANCE=0 / LDX_ATT_WHOLE_NG1=0: it
+    // keeps 32 live score registers and fits the 80-register cap of the multi-group configuration without setmaxnreg.
     const int g = (warp - C::HELPERS) / 4;
     const int qd = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;
@@ -317,44 +318,68 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
     float m_used = -INFINITY;   // row max the exponentials are relative to (raw score units)
     float l = 0.f;
     if constexpr (C::WHOLE) {
-      // ---- whole-tile variant (104 registers): S row in registers, S released at once, one max test per tile
-      for (int j = 0; j < nkv; ++j) {
-        mbar_wait(s_full, j & 1);
+      // ---- whole-tile variant: S row in registers, S released at once, one max test per tile.  With PREFETCH the
+      // first half of S(j + 1) is requested from TMEM in the middle of tile j's exponentials (its registers are dead by
+      // then) and the second half right after P(j) is published, so most of the TMEM round trip is off the chain.
+#ifndef LDX_ATT_PREFETCH
+#define LDX_ATT_PREFETCH 0       // measured: 705 vs 675 us at d = 40 (the mid-tile wait for S(j + 1) stalls the in-order warp)
+#endif
+      constexpr bool PF = LDX_ATT_PREFETCH != 0;
+      uint32_t ra[32], rb[32];
+      auto release_s = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);     // S is in registers: the accumulator may be reused
+      };
+      if constexpr (PF) {
+        mbar_wait(s_full, 0);
         tc_fence_after();
-        const int pb = j % C::PB;
-        uint8_t* prow = prow0 + pb * C::P_BYTES;
-        const int kv_left = p.Nk - j * BKV;
-        uint32_t ra[32], rb[32];
         tmem_ld32(tSg, ra);
         tmem_ld32(tSg + 32, rb);
         tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);     // S(j) is in registers: the accumulator may be reused
-        float s[64];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          s[i] = __uint_as_float(ra[i]);
-          s[32 + i] = __uint_as_float(rb[i]);
+        release_s();
+      }
+      for (int j = 0; j < nkv; ++j) {
+        const int pb = j % C::PB;
+        uint8_t* prow = prow0 + pb * C::P_BYTES;
+        const int kv_left = p.Nk - j * BKV;
+        if constexpr (!PF) {
+          mbar_wait(s_full, j & 1);
+          tc_fence_after();
+          tmem_ld32(tSg, ra);
+          tmem_ld32(tSg + 32, rb);
+          tmem_ld_wait();
+          release_s();
         }
+        const uint32_t ninf = 0xff800000u;
         if (kv_left < BKV) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i)
-            if (i >= kv_left) s[i] = -INFINITY;
+          for (int i = 0; i < 32; ++i) {
+            if (i >= kv_left) ra[i] = ninf;
+            if (32 + i >= kv_left) rb[i] = ninf;
+          }
         }
         if constexpr (CAUSAL) {
           const int k0 = j * BKV, qi = q_cta + g * BQ + row;
           if (k0 + 63 > qi) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i)
-              if (k0 + i > qi) s[i] = -INFINITY;
+            for (int i = 0; i < 32; ++i) {
+              if (k0 + i > qi) ra[i] = ninf;
+              if (k0 + 32 + i > qi) rb[i] = ninf;
+            }
           }
         }
-        float mx0 = fmaxf(s[0], s[1]), mx1 = fmaxf(s[2], s[3]);
+        float mx0 = fmaxf(__uint_as_float(ra[0]), __uint_as_float(ra[1]));
+        float mx1 = fmaxf(__uint_as_float(ra[2]), __uint_as_float(ra[3]));
 #pragma unroll
-        for (int i = 4; i < 64; i += 4) {
-          mx0 = fmaxf(mx0, fmaxf(s[i], s[i + 1]));
-          mx1 = fmaxf(mx1, fmaxf(s[i + 2], s[i + 3]));
+        for (int i = 4; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(ra[i]), __uint_as_float(ra[i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(ra[i + 2]), __uint_as_float(ra[i + 3])));
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(rb[i]), __uint_as_float(rb[i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(rb[i + 2]), __uint_as_float(rb[i + 3])));
         }
         const float m_t = fmaxf(mx0, mx1);
         const bool grow = (m_t - m_used) * c > 8.0f;
@@ -386,26 +411,47 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
         const float mc = m_used * c;
         if (j >= C::PB) mbar_wait(pv_done + pb, ((j - C::PB) / C::PB) & 1);   // P V(j - PB) has read this buffer
         float l0 = 0.f, l1 = 0.f;
+        // 64 keys = 8 16-byte chunks; chunk index XOR (row % 8) = SWIZZLE_128B
+        auto half = [&](const uint32_t (&r)[32], int ch0) {
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {       // 64 keys = 8 16-byte chunks; chunk index XOR (row % 8) = SWIZZLE_128B
-          uint32_t pk[4];
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t pk[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int e = ch * 8 + 2 * i;
-            const float p0 = ex2_approx(fmaf(s[e], c, -mc)), p1 = ex2_approx(fmaf(s[e + 1], c, -mc));
-            if constexpr (!C::ONES) {
-              l0 += p0;
-              l1 += p1;
+            for (int i = 0; i < 4; ++i) {
+              const int e = ch * 8 + 2 * i;
+              const float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), c, -mc));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), c, -mc));
+              if constexpr (!C::ONES) {
+                l0 += p0;
+                l1 += p1;
+              }
+              pk[i] = pack_h2(p0, p1);
             }
-            pk[i] = pack_h2(p0, p1);
+            *reinterpret_cast<uint4*>(prow + (((ch0 + ch) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          *reinterpret_cast<uint4*>(prow + ((ch ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        };
+        half(ra, 0);
+        const bool more = j + 1 < nkv;
+        if constexpr (PF) {
+          if (more) {                            // S(j + 1) was issued when S(j) was released: normally long complete
+            mbar_wait(s_full, (j + 1) & 1);
+            tc_fence_after();
+            tmem_ld32(tSg, ra);
+          }
         }
+        half(rb, 4);
         l += l0 + l1;
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full + pb);
+        if constexpr (PF) {
+          if (more) {
+            tmem_ld32(tSg + 32, rb);
+            tmem_ld_wait();
+            release_s();
+          }
+        }
       }
     } else
     for (int j = 0; j < nkv; ++j) {
