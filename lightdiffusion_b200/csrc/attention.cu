@@ -419,8 +419,17 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = ch * 8 + 2 * i;
-              const float p0 = ex2_approx(fmaf(__uint_as_float(r[e]), c, -mc));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(r[e + 1]), c, -mc));
+              const float x0 = fmaf(__uint_as_float(r[e]), c, -mc), x1 = fmaf(__uint_as_float(r[e + 1]), c, -mc);
+              float p0, p1;
+              if (LDX_ATT_DBG == 1) {
+                p0 = x0;
+                p1 = x1;
+              } else {
+                p0 = (LDX_ATT_POLY_MOD > 0 && e % (LDX_ATT_POLY_MOD > 0 ? LDX_ATT_POLY_MOD : 1) == LDX_ATT_POLY_MOD - 1)
+                         ? ex2_poly(x0) : ex2_approx(x0);
+                p1 = (LDX_ATT_POLY_MOD > 0 && (e + 1) % (LDX_ATT_POLY_MOD > 0 ? LDX_ATT_POLY_MOD : 1) == LDX_ATT_POLY_MOD - 1)
+                         ? ex2_poly(x1) : ex2_approx(x1);
+              }
               if constexpr (!C::ONES) {
                 l0 += p0;
                 l1 += p1;
