@@ -284,6 +284,27 @@ def test_attention_peaked_scores_rescale_path():
     assert rel(o, ref) < 2e-3
 
 
+@pytest.mark.parametrize("B,Nq,Nk,heads,d", [(1, 700, 1000, 2, 40), (2, 513, 257, 3, 40), (1, 300, 640, 2, 80),
+                                             (1, 128, 320, 1, 160), (1, 1024, 2048, 2, 64)])
+def test_attention_growing_row_max(B, Nq, Nk, heads, d):
+    """Scores whose row maximum keeps growing along the key axis: every tile takes the lazy O-rescale path of the
+    online softmax (ragged Nq / Nk, partially filled query groups)."""
+    g = torch.Generator().manual_seed(170 + Nq)
+    q = torch.randn(B, Nq, heads * d, generator=g).to(DEV)
+    k = torch.randn(B, Nk, heads * d, generator=g).to(DEV)
+    ramp = torch.linspace(0.2, 6.0, Nk, device=DEV).view(1, Nk, 1)        # later keys dominate: max grows by >> 2^8
+    k = h16(k.abs() * ramp * q.sign().mean(1, keepdim=True).sign())
+    q, v = h16(q.abs() * q.sign().mean(1, keepdim=True).sign()), h16(torch.randn(B, Nk, heads * d, generator=g).to(DEV))
+    o = torch.zeros_like(q)
+    K.run_op(K.attention_op(q, k, v, o, heads))
+    qf, kf, vf = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    s = (qf @ kf.transpose(-1, -2)) / d ** 0.5
+    assert float((s.cummax(-1).values[..., -1] - s.cummax(-1).values[..., 63]).min()) * 1.4427 > 8.0   # the path is taken
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Nq, heads * d)
+    assert torch.isfinite(o).all()
+    assert rel(o, ref) < 3e-3, rel(o, ref)
+
+
 @pytest.mark.parametrize("B,N,heads", [(1, 77, 12), (3, 77, 12), (2, 64, 4), (2, 130, 2), (1, 256, 1)])
 def test_attention_causal(B, N, heads):
     """The CLIP text tower's attention (LD.py:4443-4449, 4291): -inf above the diagonal, d = 64."""
