@@ -325,14 +325,17 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
 #define LDX_ATT_PREFETCH 0       // measured: 705 vs 675 us at d = 40 (the mid-tile wait for S(j + 1) stalls the in-order warp)
 #endif
       constexpr bool PF = LDX_ATT_PREFETCH != 0;
+      // barrier addresses in the shared window, computed once (see smem_u32_pinned)
+      const uint32_t a_sfull = smem_u32_pinned(s_full), a_sfree = smem_u32_pinned(s_free);
+      const uint32_t a_pfull = smem_u32_pinned(p_full), a_pvdone = smem_u32_pinned(pv_done);
       uint32_t ra[32], rb[32];
       auto release_s = [&]() {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(s_free);     // S is in registers: the accumulator may be reused
+        if (lane == 0) mbar_arrive_a(a_sfree);   // S is in registers: the accumulator may be reused
       };
       if constexpr (PF) {
-        mbar_wait(s_full, 0);
+        mbar_wait_a(a_sfull, 0);
         tc_fence_after();
         tmem_ld32(tSg, ra);
         tmem_ld32(tSg + 32, rb);
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
         uint8_t* prow = prow0 + pb * C::P_BYTES;
         const int kv_left = p.Nk - j * BKV;
         if constexpr (!PF) {
-          mbar_wait(s_full, j & 1);
+          mbar_wait_a(a_sfull, j & 1);
           tc_fence_after();
           tmem_ld32(tSg, ra);
           tmem_ld32(tSg + 32, rb);
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
           const float alpha = ex2_approx((m_used - m_new) * c);
           m_used = m_new;
           if constexpr (!C::ONES) l *= alpha;
-          mbar_wait(pv_done + (j - 1) % C::PB, ((j - 1) / C::PB) & 1);     // O is quiescent
+          mbar_wait_a(a_pvdone + 8 * ((j - 1) % C::PB), ((j - 1) / C::PB) & 1);     // O is quiescent
           tc_fence_after();
           // four columns at a time: the 64 live score registers leave little room in this (rare) path
 #pragma unroll 1
@@ -409,7 +412,7 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
           tmem_st_wait();
         }
         const float mc = m_used * c;
-        if (j >= C::PB) mbar_wait(pv_done + pb, ((j - C::PB) / C::PB) & 1);   // P V(j - PB) has read this buffer
+        if (j >= C::PB) mbar_wait_a(a_pvdone + 8 * pb, ((j - C::PB) / C::PB) & 1);   // P V(j - PB) has read this buffer
         float l0 = 0.f, l1 = 0.f;
         // 64 keys = 8 16-byte chunks; chunk index XOR (row % 8) = SWIZZLE_128B
         auto half = [&](const uint32_t (&r)[32], int ch0) {
@@ -443,7 +446,7 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
         const bool more = j + 1 < nkv;
         if constexpr (PF) {
           if (more) {                            // S(j + 1) was issued when S(j) was released: normally long complete
-            mbar_wait(s_full, (j + 1) & 1);
+            mbar_wait_a(a_sfull, (j + 1) & 1);
             tc_fence_after();
             tmem_ld32(tSg, ra);
           }
@@ -453,7 +456,7 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full + pb);
+        if (lane == 0) mbar_arrive_a(a_pfull + 8 * pb);
         if constexpr (PF) {
           if (more) {
             tmem_ld32(tSg + 32, rb);

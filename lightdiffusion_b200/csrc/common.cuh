@@ -84,6 +84,29 @@ LDX_DEVICE bool mbar_try_wait(uint32_t addr, uint32_t parity) {
 #endif
   return done != 0;
 }
+// The same on a precomputed shared-window address.  smem_u32_pinned() hides the conversion from the optimiser,
+// which otherwise rematerialises the whole address computation (8-10 instructions) at every barrier operation of
+// a register-tight loop.
+LDX_DEVICE uint32_t smem_u32_pinned(const void* p) {
+  uint32_t a;
+  asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(a) : "l"(p));
+  return a;
+}
+LDX_DEVICE void mbar_arrive_a(uint32_t addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+LDX_DEVICE void mbar_wait_a(uint32_t addr, uint32_t parity) {
+  if (mbar_try_wait(addr, parity)) return;
+  long long t0 = 0;
+  for (uint32_t it = 1;; ++it) {
+    if (mbar_try_wait(addr, parity)) break;
+    if ((it & 1023u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > LDX_WAIT_LIMIT_CYCLES) __trap();
+    }
+  }
+}
 LDX_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   if (mbar_try_wait(addr, parity)) return;      // common case: the phase has already completed
