@@ -59,6 +59,49 @@ def test_dpmpp2m_coefficients_reproduce_reference_trajectory(golden):
     assert abs(float(sd ** 2 + su ** 2) - float(sig[4] ** 2)) < 1e-5
 
 
+def test_neighbour_component_schemas(golden):
+    """Parameter schemas of the components around the loop, counted against the reference modules (fixtures carry
+    the reference's own parameter counts) and against each other."""
+    enc = sd15.vae_encoder_param_shapes()
+    assert sum(torch.Size(s).numel() for k, s in enc.items() if k.startswith("encoder.")) == golden("vae_encode.pt")["n_encoder_params"]
+    clip = sd15.clip_text_param_shapes()
+    assert sd15.count_params(clip) == 49408 * 768 + 77 * 768 + 12 * (4 * (768 * 768 + 768) + 2 * 2 * 768
+                                                                   + 3072 * 768 + 3072 + 768 * 3072 + 768) + 2 * 768 + 768 * 768
+    from lightdiffusion_b200.esrgan import esrgan_param_shapes, to_old_arch
+    for scale in (2, 4):
+        old = esrgan_param_shapes(3, scale, arch="old")
+        for arch in ("esrgan", "realesrgan"):
+            new = esrgan_param_shapes(3, scale, arch=arch)
+            mapped = to_old_arch({k: torch.empty(0).new_empty(v) for k, v in new.items()})
+            assert set(mapped) == set(old) and all(tuple(mapped[k].shape) == old[k] for k in old), (scale, arch)
+    with pytest.raises(Exception):
+        to_old_arch({"foo.weight": torch.zeros(1)})
+    from lightdiffusion_b200.taesd import taesd_param_shapes
+    assert sd15.count_params(taesd_param_shapes("decoder")) == 4 * 64 * 9 + 64 + 10 * 3 * (64 * 64 * 9 + 64) + 3 * 64 * 64 * 9 + 64 * 3 * 9 + 3
+    assert sd15.count_params(taesd_param_shapes("encoder")) == 3 * 64 * 9 + 64 + 10 * 3 * (64 * 64 * 9 + 64) + 3 * 64 * 64 * 9 + 64 * 4 * 9 + 4
+
+
+def test_host_side_tables_and_controllers():
+    """bislerp axis tables, the empty-prompt token row and the PID step-size controller against the restatements."""
+    from oracle import ldm_oracle as O
+    from lightdiffusion_b200.upscale import _axis_table_cpu
+    for old, new in ((64, 128), (12, 18), (12, 17), (8, 4), (5, 5), (1, 3)):
+        r, i1, i2 = _axis_table_cpu(old, new)
+        ro, o1, o2 = O._bilinear_table(old, new)
+        assert torch.equal(r, ro) and torch.equal(i1.long(), o1) and torch.equal(i2.long(), o2)
+        assert int(i2.max()) <= old - 1 and int(i1.min()) >= 0
+    from lightdiffusion_b200.clip import SD1ClipEncoder, gen_empty_tokens
+    assert gen_empty_tokens(SD1ClipEncoder.special_tokens, 77) == [49406, 49407] + [49407] * 75
+    from lightdiffusion_b200.samplers import PIDStepSizeController
+    pid = PIDStepSizeController(0.05, 0.1, 1.0, 0.05, order=3, accept_safety=0.81)
+    accepts = [pid.propose_step(e) for e in (0.5, 0.9, 3.0, 40.0, 0.2, 1.0)]
+    assert accepts == [True, True, False, False, True, True]      # large errors are rejected and shrink h
+    assert 0.0 < pid.h < 0.2
+    pid2 = PIDStepSizeController(0.05, 0.0, 1.0, 0.0, order=3)
+    pid2.propose_step(1.0)
+    assert abs(pid2.h - 0.05) < 1e-6                              # unit error leaves the step size unchanged
+
+
 def test_shard_range_partitions_everything():
     for n, w in [(64, 8), (64, 2), (10, 4), (3, 8), (1, 1)]:
         got = []
