@@ -61,6 +61,30 @@ def test_no_cpu_fallback(lib):
         conv(torch.zeros(1, 8, 4, 4))
 
 
+def test_argument_validation_returns_error_codes(lib):
+    """Bad arguments are rejected with a negative status and a message before anything is launched (so this needs
+    no device): the reference surface raises Python exceptions, the shim turns these codes into LdxError."""
+    l = lib.lib()
+    buf = ctypes.create_string_buffer(256)
+    addr = ctypes.addressof(buf)
+    bad = [
+        l.ldx_dpm_eps(None, addr, 1.0, addr, 4, None),
+        l.ldx_dpm_eps(addr, addr, 0.0, addr, 4, None),                     # sigma must be positive
+        l.ldx_dpm_combine(addr, None, None, 1.0, 0.0, addr, 4, None),
+        l.ldx_dpm_error_norm(addr, addr, addr, 0.01, 0.05, 4, None, addr, None),
+        l.ldx_bislerp_axis(addr, addr, addr, addr, addr, 1, 17, 1, 4, 8, 1, None),   # more than 16 channels
+        l.ldx_bislerp_axis(addr, addr, None, addr, addr, 1, 4, 1, 4, 8, 1, None),
+        l.ldx_clip_embed(addr, addr, addr, addr, 4, 2, 77, 768, None),     # row pitch below the width
+        l.ldx_vae_preprocess(None, addr, 4, None),
+        l.ldx_vae_sample_posterior(addr, None, None, 1, 4, 16, None),
+        l.ldx_attention_causal(addr, 64, addr, 64, addr, 64, addr, 64, 1, 77, 1, 40, None),   # d = 64 only
+    ]
+    assert all(rc != 0 for rc in bad), bad
+    assert l.ldx_last_error_string()
+    with pytest.raises(lib.LdxError):
+        lib.check(bad[0], "ldx_dpm_eps")
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under lightdiffusion_b200/ may import it, except
     smoke.py, which uses it only as the checker."""
