@@ -99,7 +99,8 @@ typedef struct {
   float ln_eps;             /* LDX_EPI_ROWNORM: LayerNorm eps */
   const float* ln_gsum;     /* LDX_EPI_ROWNORM: [N] fp32 (packed like the bias for LDX_EPI_GEGLU) */
   int32_t ln_c;             /* LDX_EPI_ROWNORM: normalised width C (the A row length before K padding) */
-  int32_t reserved_;
+  int32_t rowstats_out_parts; /* 0 = unchecked; else the [rows, parts, 2] extent of rowstats_out: the launch is
+                               rejected unless it equals ldx_gemm_rowstats_parts(d) */
 } ldx_gemm_desc_t;
 
 int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream);
@@ -164,12 +165,25 @@ int ldx_eps_to_denoised(const void* eps, int64_t lde, const float* x, const floa
  * (calc_cond_batch chunk LD.py:2569 + cfg_function LD.py:2594-2606). */
 int ldx_cfg_denoised(const void* eps, int64_t lde, const float* x, const float* sigma, float scale,
                      float* den, int b, int C, int H, int W, ldx_stream_t stream);
+/* The whole tail of one guided DPM++ 2M step in ONE launch (sampling_function LD.py:2569-2606 followed by the
+ * update of sample_dpmpp_2m_sde at eta = 0, LD.py:1209-1236): eps holds the [uncond..., cond...] batch of 2b
+ * samples (fp16 NHWC, pitch lde); den = u + (c - u) * cfg_scale on the denoised predictions x - eps * sigma;
+ *   x <- c_x * x + c_d * den [+ c_o * (den - old_denoised) when have_old]     (x <- den when last != 0)
+ *   old_denoised <- den ; denoised_out <- den (optional, may be NULL: callbacks / previews)
+ *   sigma_io[0..b) <- sigma_next (optional: the sigma vector the next UNet evaluation reads)
+ * x, old_denoised, denoised_out: fp32 NCHW [b, C, H, W], in place. */
+int ldx_cfg_dpmpp2m_step(const void* eps, int64_t lde, float* x, float* old_denoised, float* denoised_out,
+                         float sigma, float cfg_scale, float c_x, float c_d, float c_o, int have_old, int last,
+                         float sigma_next, float* sigma_io, int b, int C, int H, int W, ldx_stream_t stream);
 /* cfg_function on two fp32 predictions (LD.py:2605). */
 int ldx_cfg_combine(const float* cond, const float* uncond, float scale, float* out, int64_t n,
                     ldx_stream_t stream);
 /* decoded fp16 NHWC [B,H,W,ldc] (first 3 channels) -> clamp((v+1)/2, 0, 1) fp32 NHWC [B,H,W,3]
  * (VAE.process_output + movedim, LD.py:6296-6298, 6377-6380). */
 int ldx_vae_postprocess(const void* dec, int64_t ldc, float* img, int64_t npix, ldx_stream_t stream);
+/* Same conversion quantised to uint8 NHWC [B,H,W,3] the way the reference saves / gathers images
+ * (np.clip(255 * img, 0, 255).astype(uint8), SaveImage LD.py:6750-6751): 4x fewer bytes for the final gather. */
+int ldx_vae_postprocess_u8(const void* dec, int64_t ldc, void* img, int64_t npix, ldx_stream_t stream);
 /* VAE.encode input side: pixels fp32 NHWC [npix, 3] in [0,1] -> 2x - 1, fp16 NHWC [npix, 8] with channels 3..7
  * zero (VAE.process_input + movedim + cast, LD.py:6295, 6385, 6402-6405). out must be 16-byte aligned. */
 int ldx_vae_preprocess(const float* pixels, void* out, int64_t npix, ldx_stream_t stream);

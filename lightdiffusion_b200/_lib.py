@@ -52,7 +52,7 @@ class GemmDesc(C.Structure):
                 ("residual", C.c_void_p), ("ldr", C.c_int64),
                 ("flags", C.c_int32), ("bn", C.c_int32),
                 ("rowstats_out", C.c_void_p), ("rowstats_in", C.c_void_p), ("rowstats_in_parts", C.c_int32),
-                ("ln_eps", C.c_float), ("ln_gsum", C.c_void_p), ("ln_c", C.c_int32), ("reserved_", C.c_int32)]
+                ("ln_eps", C.c_float), ("ln_gsum", C.c_void_p), ("ln_c", C.c_int32), ("rowstats_out_parts", C.c_int32)]
 
 
 class GenericOp(C.Structure):
@@ -87,6 +87,9 @@ _SIGS = {
                                       C.c_int, C.c_int, C.c_void_p]),
     "ldx_cfg_denoised": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
                                    C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ldx_cfg_dpmpp2m_step": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float,
+                                       C.c_float, C.c_float, C.c_float, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldx_cfg_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     "ldx_vae_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ldx_vae_sample_posterior": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]),
@@ -102,6 +105,7 @@ _SIGS = {
     "ldx_dpm_error_norm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int64, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
     "ldx_vae_postprocess": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ldx_vae_postprocess_u8": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "ldx_softmax_rows": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_float,
                                    C.c_void_p]),
     "ldx_dpmpp2m_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int64,

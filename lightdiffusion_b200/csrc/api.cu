@@ -21,12 +21,20 @@ int cuda_fail(cudaError_t e, const char* what) {
   return LDX_E_CUDA;
 }
 
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev;
+}
+
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[LDX_MAX_DEVICES];      // zero-initialised; one slot per device ordinal
+  const int dev = current_device();
+  std::atomic<int>& slot = cache[dev & (LDX_MAX_DEVICES - 1)];
+  int n = slot.load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -160,10 +168,16 @@ extern "C" int ldx_program_num_ops(const ldx_program_t* prog) { return prog ? (i
 extern "C" int ldx_program_run_timed(ldx_program_t* prog, ldx_stream_t stream, float* ms_out, int n) {
   LDX_CHECK_ARG(prog && ms_out && n == (int)prog->ops.size(), "program_run_timed: bad args");
   cudaStream_t st = as_stream(stream);
-  std::vector<cudaEvent_t> ev(n + 1);
-  for (int i = 0; i <= n; ++i) LDX_CUDA(cudaEventCreate(&ev[i]));
-  LDX_CUDA(cudaEventRecord(ev[0], st));
+  std::vector<cudaEvent_t> ev(n + 1, nullptr);
   int rc = LDX_OK;
+  for (int i = 0; i <= n && rc == LDX_OK; ++i) {
+    cudaError_t e = cudaEventCreate(&ev[i]);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventCreate");
+  }
+  if (rc == LDX_OK) {
+    cudaError_t e = cudaEventRecord(ev[0], st);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventRecord");
+  }
   for (int i = 0; i < n && rc == LDX_OK; ++i) {
     const ProgOp& op = prog->ops[i];
     if (op.kind == LDX_OP_GEMM) rc = gemm_launch(op.gemm, st);
@@ -177,7 +191,8 @@ extern "C" int ldx_program_run_timed(ldx_program_t* prog, ldx_stream_t stream, f
   }
   if (rc == LDX_OK)
     for (int i = 0; i < n; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
-  for (int i = 0; i <= n; ++i) cudaEventDestroy(ev[i]);
+  for (int i = 0; i <= n; ++i)
+    if (ev[i]) cudaEventDestroy(ev[i]);
   return rc;
 }
 

@@ -667,12 +667,9 @@ static int attention_prepare(const void* q, int64_t ldq, const void* k, int64_t 
 template <int D, int NG_, bool CAUSAL = false>
 static int attention_launch_t(const AttnLaunch* L, cudaStream_t st) {
   using C = AttnCfg<D, NG_>;
-  static bool attr = false;
-  if (!attr) {
-    LDX_CUDA(cudaFuncSetAttribute(ldx_attention_kernel<D, NG_, CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::SMEM));
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};          // per kernel instantiation, one bit per device
+  int arc = set_max_dyn_smem_once(ldx_attention_kernel<D, NG_, CAUSAL>, C::SMEM, attr_done);
+  if (arc) return arc;
   LDX_CUDA(launch_k(ldx_attention_kernel<D, NG_, CAUSAL>, L->grid, dim3(C::THREADS), (size_t)C::SMEM, st, 1, L->p));
   return LDX_OK;
 }

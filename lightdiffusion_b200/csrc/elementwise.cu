@@ -306,11 +306,9 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
   a.eps = eps; a.silu = silu; a.gamma = gamma; a.beta = beta;
   a.y = (__half*)y; a.ldy = ldy; a.partial = stats;
   const size_t smem = (size_t)a.P * C * 2 * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    LDX_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-    attr = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  int arc = set_max_dyn_smem_once(gn_stats_kernel, 128 * 1024, attr_done);
+  if (arc) return arc;
   LDX_CHECK_ARG(smem <= 128 * 1024, "group_norm: smem");
   LDX_CUDA(launch_k(gn_stats_kernel, dim3(B, nslab), dim3(threads), smem, stream, 1, a));
   // apply: more slabs for bandwidth
@@ -530,6 +528,37 @@ __global__ void cfg_denoised_kernel(const __half* __restrict__ eps, int64_t lde,
   }
 }
 
+// One launch for the tail of a DPM++ 2M step under classifier-free guidance (sampling_function LD.py:2605 +
+// sample_dpmpp_2m_sde at eta = 0, LD.py:1209-1236): den = du + (dc - du) * scale with d* = x - eps* * sigma;
+// x <- cx * x + cd * den [+ co * (den - old)] (x <- den on the last step); old <- den; and the next step's sigma is
+// written to the UNet plan's input vector.  sigma arrives as a scalar (no thread reads sigma_io, so the write
+// is race-free).  bytes per latent element: 2 x 2 (eps halves, fp16) + 4 (x) + 4 (old) read, 4 + 4 written.
+__global__ void cfg_dpmpp2m_step_kernel(const __half* __restrict__ eps, int64_t lde, float* __restrict__ x,
+                                        float* __restrict__ old, float* __restrict__ den_out, float sigma, float scale,
+                                        float cx, float cd, float co, int have_old, int last, float sigma_next,
+                                        float* __restrict__ sigma_io, int nb, int C, int HW) {
+  const int64_t total = (int64_t)nb * C * HW;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int pix = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const int b = (int)(i / ((int64_t)HW * C));
+    const float eu = __half2float(eps[((int64_t)b * HW + pix) * lde + c]);
+    const float ec = __half2float(eps[((int64_t)(b + nb) * HW + pix) * lde + c]);
+    const float xv = x[i];
+    const float du = xv - eu * sigma, dc = xv - ec * sigma;
+    const float d = du + (dc - du) * scale;
+    float v = d;
+    if (!last) {
+      v = cx * xv + cd * d;
+      if (have_old) v = v + co * (d - old[i]);
+    }
+    x[i] = v;
+    old[i] = d;
+    if (den_out) den_out[i] = d;
+  }
+  if (sigma_io && blockIdx.x == 0 && threadIdx.x < nb) sigma_io[threadIdx.x] = sigma_next;
+}
+
 __global__ void cfg_combine_kernel(const float* __restrict__ c, const float* __restrict__ u, float scale,
                                    float* __restrict__ out, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -542,6 +571,16 @@ __global__ void vae_post_kernel(const __half* __restrict__ dec, int64_t ldc, flo
     const int c = (int)(i % 3);
     const float v = (__half2float(dec[pix * ldc + c]) + 1.0f) / 2.0f;
     img[i] = fminf(fmaxf(v, 0.0f), 1.0f);
+  }
+}
+
+// same, quantised the way the reference saves images (255 * img, clipped, uint8; LD.py:6616-6620 SaveImage)
+__global__ void vae_post_u8_kernel(const __half* __restrict__ dec, int64_t ldc, uint8_t* __restrict__ img, int64_t npix) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npix * 3; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pix = i / 3;
+    const int c = (int)(i % 3);
+    const float v = fminf(fmaxf((__half2float(dec[pix * ldc + c]) + 1.0f) / 2.0f, 0.0f), 1.0f);
+    img[i] = (uint8_t)fminf(fmaxf(255.0f * v, 0.0f), 255.0f);          // numpy astype(uint8) truncates
   }
 }
 
@@ -968,6 +1007,20 @@ extern "C" int ldx_cfg_denoised(const void* eps, int64_t lde, const float* x, co
   return run_generic_op(&op, as_stream(stream));
 }
 
+extern "C" int ldx_cfg_dpmpp2m_step(const void* eps, int64_t lde, float* x, float* old_denoised, float* denoised_out,
+                                    float sigma, float cfg_scale, float c_x, float c_d, float c_o, int have_old,
+                                    int last, float sigma_next, float* sigma_io, int b, int C, int H, int W,
+                                    ldx_stream_t stream) {
+  LDX_CHECK_ARG(eps && x && old_denoised, "cfg_dpmpp2m_step: null");
+  LDX_CHECK_ARG(b >= 1 && b <= 256 && C >= 1 && H >= 1 && W >= 1 && lde >= C, "cfg_dpmpp2m_step: bad extents");
+  const int64_t n = (int64_t)b * C * H * W;
+  cfg_dpmpp2m_step_kernel<<<ew_blocks(n), 256, 0, as_stream(stream)>>>(
+      (const __half*)eps, lde, x, old_denoised, denoised_out, sigma, cfg_scale, c_x, c_d, c_o, have_old, last,
+      sigma_next, sigma_io, b, C, H * W);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
+}
+
 extern "C" int ldx_cfg_combine(const float* cond, const float* uncond, float scale, float* out, int64_t n,
                                ldx_stream_t stream) {
   LDX_CHECK_ARG(cond && uncond && out, "cfg_combine: null");
@@ -981,6 +1034,13 @@ extern "C" int ldx_vae_postprocess(const void* dec, int64_t ldc, float* img, int
   ldx_generic_op_t op = make_op(LDX_OP_VAE_POST);
   op.p[0] = dec; op.p[1] = img; op.l[0] = ldc; op.l[1] = npix;
   return run_generic_op(&op, as_stream(stream));
+}
+
+extern "C" int ldx_vae_postprocess_u8(const void* dec, int64_t ldc, void* img, int64_t npix, ldx_stream_t stream) {
+  LDX_CHECK_ARG(dec && img && npix > 0 && ldc >= 3, "vae_postprocess_u8: null / empty");
+  vae_post_u8_kernel<<<ew_blocks(npix * 3), 256, 0, as_stream(stream)>>>((const __half*)dec, ldc, (uint8_t*)img, npix);
+  LDX_CUDA(cudaGetLastError());
+  return LDX_OK;
 }
 
 extern "C" int ldx_vae_preprocess(const float* pixels, void* out, int64_t npix, ldx_stream_t stream) {

@@ -23,6 +23,8 @@
 // Roofline: tensor-pipe bound; algorithmic FLOPs = 2 * M * N * K.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -694,36 +696,44 @@ static int pow2_ceil(int v) {
   return p;
 }
 
-// 256 x 256 fp16 identity in device memory (lazily created, lives for the process): B operand of the
-// fused-residual K steps.  Any bn x 64 slice of a larger identity that a tile needs equals a slice of this one.
+// Read-only device constants, one copy per device ordinal, created on first use under a mutex (the reference
+// samples from a worker thread, LD.py:10453, and one process may drive several GPUs).
+static std::mutex g_const_mu;
+
+// 256 x 256 fp16 identity: B operand of the fused-residual K steps.  Any bn x 64 slice of a larger identity
+// that a tile needs equals a slice of this one.
 static const void* identity256() {
-  static void* dev = nullptr;
-  if (!dev) {
+  static void* dev_ptr[LDX_MAX_DEVICES] = {};
+  const int dev = current_device() & (LDX_MAX_DEVICES - 1);
+  std::lock_guard<std::mutex> lock(g_const_mu);
+  if (!dev_ptr[dev]) {
     __half* host = (__half*)calloc(256 * 256, sizeof(__half));
     if (!host) return nullptr;
     for (int i = 0; i < 256; ++i) host[i * 256 + i] = __float2half(1.0f);
     void* ptr = nullptr;
     if (cudaMalloc(&ptr, 256 * 256 * sizeof(__half)) == cudaSuccess &&
         cudaMemcpy(ptr, host, 256 * 256 * sizeof(__half), cudaMemcpyHostToDevice) == cudaSuccess)
-      dev = ptr;
+      dev_ptr[dev] = ptr;
     free(host);
   }
-  return dev;
+  return dev_ptr[dev];
 }
 
-// Zero fp32 vector (lazily created): stands in for a missing bias so the TMA-store epilogue needs no null checks.
+// Zero fp32 vector: stands in for a missing bias so the TMA-store epilogue needs no null checks.
 static const float* zeros_f32(int n) {
-  static float* dev = nullptr;
-  static int cap = 0;
-  if (n > cap) {
+  static float* dev_ptr[LDX_MAX_DEVICES] = {};
+  static int cap[LDX_MAX_DEVICES] = {};
+  const int dev = current_device() & (LDX_MAX_DEVICES - 1);
+  std::lock_guard<std::mutex> lock(g_const_mu);
+  if (n > cap[dev]) {
     const int want = n > 16384 ? n : 16384;
     float* ptr = nullptr;
     if (cudaMalloc(&ptr, (size_t)want * sizeof(float)) != cudaSuccess) return nullptr;
     if (cudaMemset(ptr, 0, (size_t)want * sizeof(float)) != cudaSuccess) return nullptr;
-    dev = ptr;            // an older, smaller vector stays alive for launches that already captured it
-    cap = want;
+    dev_ptr[dev] = ptr;   // an older, smaller vector stays alive for launches that already captured it
+    cap[dev] = want;
   }
-  return dev;
+  return dev_ptr[dev];
 }
 
 // fp16 output rows addressable with 8-byte vector stores (split-K reduce kernel)
@@ -998,6 +1008,9 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     if (rc) return rc;
     p.tma_epi = 1;
     p.rowstats_out = d->rowstats_out;
+    LDX_CHECK_ARG(!d->rowstats_out || d->rowstats_out_parts == 0 || d->rowstats_out_parts == p.n_tiles * EPI_GROUPS,
+                  "rowstats_out holds %d parts per row but this launch writes %d", d->rowstats_out_parts,
+                  p.n_tiles * EPI_GROUPS);
     if (d->flags & LDX_EPI_ROWNORM) {
       LDX_CHECK_ARG(d->rowstats_in && d->ln_gsum && d->rowstats_in_parts >= 1 && d->rowstats_in_parts <= 256 &&
                         d->ln_c >= 1,
@@ -1023,11 +1036,9 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
 
 template <int kCtas, int kEpi>
 static int gemm_launch_t(const GemmLaunch* g, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    LDX_CUDA(cudaFuncSetAttribute(ldx_gemm_kernel<kCtas, kEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};          // per kernel instantiation, one bit per device
+  int arc = set_max_dyn_smem_once(ldx_gemm_kernel<kCtas, kEpi>, 227 * 1024, attr_done);
+  if (arc) return arc;
   LDX_CUDA(launch_k(ldx_gemm_kernel<kCtas, kEpi>, dim3(g->grid), dim3(GEMM_THREADS), (size_t)g->smem_bytes, stream, kCtas,
                     g->p));
   return LDX_OK;
@@ -1129,7 +1140,13 @@ extern "C" int ldx_debug_gemm_ts(unsigned long long* out) {
 
 extern "C" int ldx_gemm_rowstats_parts(const ldx_gemm_desc_t* d) {
   GemmLaunch g;
-  if (gemm_prepare(d, &g) != LDX_OK) return -1;
+  if (!d) return -1;
+  // plan the launch exactly as it will run with rowstats_out attached (a GEMM that writes row statistics is
+  // never split-K), whether or not the caller has bound the buffer yet
+  ldx_gemm_desc_t q = *d;
+  if (!q.rowstats_out) q.rowstats_out = reinterpret_cast<float*>(static_cast<uintptr_t>(16));
+  q.rowstats_out_parts = 0;
+  if (gemm_prepare(&q, &g) != LDX_OK) return -1;
   if (!g.p.tma_epi) {
     set_error("rowstats_out needs the TMA-store epilogue (fp16 output, 16-byte aligned strides)");
     return -1;

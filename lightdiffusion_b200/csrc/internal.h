@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "../../include/ldx.h"
 
 namespace ldx {
@@ -67,7 +69,22 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   cfg.numAttrs = (unsigned)n;
   return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
-int num_sms();
+int num_sms();          // of the calling thread's current device (cached per device)
+int current_device();
+
+static constexpr int LDX_MAX_DEVICES = 64;
+
+// cudaFuncSetAttribute is per device: one bit per device ordinal, set after the first successful call on that
+// device.  Two threads racing on the same device both set the (idempotent) attribute; nothing is torn.
+template <typename Kernel>
+inline int set_max_dyn_smem_once(Kernel kernel, int bytes, std::atomic<uint64_t>& done) {
+  const uint64_t bit = 1ull << (current_device() & (LDX_MAX_DEVICES - 1));
+  if (!(done.load(std::memory_order_acquire) & bit)) {
+    LDX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done.fetch_or(bit, std::memory_order_release);
+  }
+  return LDX_OK;
+}
 
 // ---- implicit GEMM: frozen kernel parameters (TMA descriptors encoded once)
 struct KSeg {

@@ -10,6 +10,7 @@ fails loudly when libldx.so or a sm_100 device is missing.
 from __future__ import annotations
 
 import math
+from collections import OrderedDict
 from typing import Dict, List, Optional, Tuple
 
 import os
@@ -41,6 +42,32 @@ FUSE_LN3 = os.environ.get("LDX_FUSE_LN3", "1") == "1"
 # (LD.py:2545-2551); the layers before the first cross-attention therefore run once per latent (bit-identical
 # results).  LDX_SHARE_CFG_PREFIX=0 evaluates the full 2b batch everywhere.
 SHARE_CFG_PREFIX = os.environ.get("LDX_SHARE_CFG_PREFIX", "1") == "1"
+# A plan owns its activation pool (~0.5 GB for the SD1.5 UNet at B = 16) and a CUDA graph; an engine keeps the most
+# recently used MAX_PLANS of them (an img2img flow over varied tile sizes would otherwise exhaust HBM).
+MAX_PLANS = int(os.environ.get("LDX_MAX_PLANS", "4"))
+
+
+class _PlanCache:
+    """LRU map key -> plan.  Evicted plans are dropped (their pool, graph and recorded program are freed)."""
+
+    def __init__(self, capacity: int = MAX_PLANS):
+        self.capacity, self._d = max(1, capacity), OrderedDict()
+
+    def get(self, key, make):
+        if key in self._d:
+            self._d.move_to_end(key)
+            return self._d[key]
+        while len(self._d) >= self.capacity:
+            self._d.popitem(last=False)
+        self._d[key] = make()
+        return self._d[key]
+
+    def __len__(self):
+        return len(self._d)
+
+    def __contains__(self, key):
+        return key in self._d
+
 
 class _Pool:
     """Size-keyed free list so that dead activations are reused (keeps the working set L2-friendly)."""
@@ -70,7 +97,7 @@ class _Pool:
 
 def _f32(sd, name, dev):
     """fp16-rounded parameter as fp32 (the reference fp16 model stores every parameter in fp16)."""
-    return sd[name].to(device=dev, dtype=F16).float().contiguous()
+    return sd[name].detach().to(F16).float().contiguous().to(dev)      # converted where it lives, then one copy
 
 
 # =============================================================================== UNet
@@ -84,7 +111,7 @@ class UNetEngine:
         self.sigmas, log_sigmas = sigma_tables()
         self.log_sigmas = log_sigmas.to(self.dev)
         self.w: Dict[str, torch.Tensor] = {}
-        self._plans: Dict[tuple, "UNetPlan"] = {}
+        self._plans = _PlanCache()
         self._pack(state_dict)
 
     # ---- one-time weight packing
@@ -115,10 +142,10 @@ class UNetEngine:
                 else:
                     w[s.name + ".w"] = K.pack_conv3x3(self._pad_in(sd[s.name + ".weight"]))
                     w[s.name + ".b"] = _f32(sd, s.name + ".bias", dev)
-        w["emb_all.w"] = K.pack_linear(torch.cat([t.to(dev) for t in emb_w], 0))
-        w["emb_all.b"] = torch.cat([t.to(device=dev, dtype=F16).float() for t in emb_b]).contiguous()
+        w["emb_all.w"] = K.pack_linear(torch.cat(emb_w, 0))
+        w["emb_all.b"] = torch.cat([t.detach().to(F16).float() for t in emb_b]).contiguous().to(dev)
         self.emb_total = off
-        w["kv_all.w"] = K.pack_linear(torch.cat([t.to(dev) for t in kv_w], 0))
+        w["kv_all.w"] = K.pack_linear(torch.cat(kv_w, 0))
         self.kv_total = kvo
         w["out.g"], w["out.beta"] = _f32(sd, "out.0.weight", dev), _f32(sd, "out.0.bias", dev)
         w["out.w"], w["out.b"] = K.pack_conv3x3(sd["out.2.weight"]), _f32(sd, "out.2.bias", dev)
@@ -172,23 +199,31 @@ class UNetEngine:
         w[p + ".ff2.w"], w[p + ".ff2.b"] = K.pack_linear(sd[t + ".ff.net.2.weight"]), _f32(sd, t + ".ff.net.2.bias", dev)
 
     # ---- plans
-    def plan(self, B: int, H: int, W: int, cfg_pairs: bool = False) -> "UNetPlan":
-        key = (B, H, W, cfg_pairs)
-        if key not in self._plans:
-            self._plans[key] = UNetPlan(self, B, H, W, cfg_pairs)
-        return self._plans[key]
+    def plan(self, B: int, H: int, W: int, cfg_pairs: bool = False, ctx_len: int = 77) -> "UNetPlan":
+        """ctx_len: context tokens per sample (77 * sections: the reference concatenates the 77-token sections of a
+        long prompt and repeats the shorter of cond / uncond to their lcm, LD.py:647-663)."""
+        return self._plans.get((B, H, W, cfg_pairs, ctx_len), lambda: UNetPlan(self, B, H, W, cfg_pairs, ctx_len))
+
+    @staticmethod
+    def cat_contexts(*ctxs: torch.Tensor) -> torch.Tensor:
+        """CONDCrossAttn.concat (LD.py:647-663): contexts of different token counts are repeated to their lcm
+        (repeating keys does not change softmax attention), then concatenated along the batch."""
+        n = 1
+        for c in ctxs:
+            n = n * c.shape[1] // math.gcd(n, c.shape[1])
+        return torch.cat([c if c.shape[1] == n else c.repeat(1, n // c.shape[1], 1) for c in ctxs])
 
     @torch.no_grad()
     def denoise(self, x: torch.Tensor, sigma: torch.Tensor, context: Optional[torch.Tensor]) -> torch.Tensor:
         """apply_model: x fp32 [B,4,H,W], sigma [B], context [B,77,ctx] -> denoised fp32 [B,4,H,W]."""
         B, _, H, W = x.shape
-        return self.plan(B, H, W).run(x, sigma, context).clone()
+        return self.plan(B, H, W, ctx_len=context.shape[1]).run(x, sigma, context).clone()
 
     @torch.no_grad()
     def eps(self, x, sigma, context) -> torch.Tensor:
         """Raw UNet output (fp16 NHWC buffer converted to fp32 NCHW) for parity tests."""
         B, _, H, W = x.shape
-        pl = self.plan(B, H, W)
+        pl = self.plan(B, H, W, ctx_len=context.shape[1])
         pl.run(x, sigma, context)
         return pl.eps_buf[..., :self.cfg.out_channels].float().permute(0, 3, 1, 2).contiguous()
 
@@ -196,14 +231,16 @@ class UNetEngine:
     def denoise_cfg(self, x, sigma, cond, uncond, scale: float, context_changed: bool = True) -> torch.Tensor:
         """sampling_function (LD.py:2609): one 2b batch ordered [uncond, cond], then cfg_function."""
         b, _, H, W = x.shape
-        pl = self.plan(2 * b, H, W, cfg_pairs=True)
-        ctx = torch.cat([uncond, cond]) if context_changed else None
-        return pl.run(x, sigma, ctx, cfg_scale=scale).clone()
+        ctx = self.cat_contexts(uncond, cond)
+        pl = self.plan(2 * b, H, W, cfg_pairs=True, ctx_len=ctx.shape[1])
+        return pl.run(x, sigma, ctx if context_changed else None, cfg_scale=scale).clone()
 
 
 class UNetPlan:
-    def __init__(self, eng: UNetEngine, B: int, H: int, W: int, cfg_pairs: bool):
-        self.eng, self.B, self.H, self.W, self.cfg_pairs = eng, B, H, W, cfg_pairs
+    def __init__(self, eng: UNetEngine, B: int, H: int, W: int, cfg_pairs: bool, ctx_len: int = 77):
+        self.eng, self.B, self.H, self.W, self.cfg_pairs, self.ctx_len = eng, B, H, W, cfg_pairs, ctx_len
+        if ctx_len < 1:
+            raise L.LdxError(f"context length {ctx_len} must be positive")
         cfg, dev = eng.cfg, eng.dev
         down = 2 ** (len(cfg.channel_mult) - 1)
         if H % down or W % down:
@@ -213,21 +250,20 @@ class UNetPlan:
         self.nb = nb
         self.x_in = torch.zeros(nb, cfg.in_channels, H, W, dtype=F32, device=dev)
         self.sigma_in = torch.ones(nb, dtype=F32, device=dev)
-        self.ctx = torch.zeros(B, 77, cfg.context_dim, dtype=F16, device=dev)
+        self.ctx = torch.zeros(B, ctx_len, cfg.context_dim, dtype=F16, device=dev)
         self.den = torch.zeros(nb, cfg.out_channels, H, W, dtype=F32, device=dev)
         self.cfg_scale = torch.tensor([1.0])    # host copy; the CFG op is re-recorded when it changes
         self.stats = torch.empty(B * L.GN_STATS_FLOATS_PER_BATCH, dtype=F32, device=dev)
         self._rs_cache = {}
-        self.kv_all = torch.empty(B * 77, eng.kv_total, dtype=F16, device=dev)
+        self.kv_all = torch.empty(B * ctx_len, eng.kv_total, dtype=F16, device=dev)
         self.ctx_prog = K.Program()
-        self.ctx_prog.add(K.linear_desc(self.ctx.view(B * 77, -1), eng.w["kv_all.w"], self.kv_all))
+        self.ctx_prog.add(K.linear_desc(self.ctx.view(B * ctx_len, -1), eng.w["kv_all.w"], self.kv_all))
         self.prog = K.Program()
         self._build()
         self.tail_prog: Optional[K.Program] = None
         self._tail_scale: Optional[float] = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.use_graph = True
-        self._ctx_len = 77
 
     # ---- op helpers
     def _gn(self, x0, x1, g, b, eps, silu):
@@ -274,7 +310,7 @@ class UNetPlan:
         if key not in self._rs_cache:
             self._rs_cache[key] = torch.empty(rows, parts, 2, dtype=F32, device=self.eng.dev)
         st = self._rs_cache[key]
-        d.rowstats_out = st.data_ptr()
+        d.rowstats_out, d.rowstats_out_parts = st.data_ptr(), parts
         return st
 
     def _rowstats_like(self, st: torch.Tensor, rows: int, slot: int):
@@ -328,7 +364,7 @@ class UNetPlan:
         q2 = a
         self.prog.add(K.linear_desc(t2, w[p + ".q2.w"], q2, bias=w[p + ".q2.b"], rownorm=(st2, w[p + ".q2.g"], 1e-5, c)))
         kvo = eng.kv_off[p]
-        kv3 = self.kv_all.view(Bn, 77, eng.kv_total)
+        kv3 = self.kv_all.view(Bn, self.ctx_len, eng.kv_total)
         a2 = pool.alloc(m, c)
         self.prog.add(K.attention_op(q2.view(Bn, n, c), kv3[:, :, kvo:kvo + c], kv3[:, :, kvo + c:kvo + 2 * c],
                                      a2.view(Bn, n, c), s.heads))
@@ -454,24 +490,34 @@ class UNetPlan:
                                 p=[self.eps_buf.data_ptr(), self.x_in.data_ptr(), self.sigma_in.data_ptr(),
                                    self.den.data_ptr()],
                                 i=[self.nb, cfg.out_channels, self.H, self.W], l=[8], f=[scale]))
-            self.tail_prog, self._tail_scale, self.graph = tp, scale, None
+            self.tail_prog, self._tail_scale = tp, scale
         return self.tail_prog
 
     @property
     def num_launches(self) -> int:
         return self.prog.num_launches + (1 if self.cfg_pairs else 0)
 
-    def _launch_all(self):
-        self.prog.run()
-        if self.cfg_pairs:
-            self.tail_prog.run()
-
     def set_context(self, context: torch.Tensor):
         """Copies the context in and recomputes the cross-attention K/V of all 16 blocks (step-invariant)."""
-        if context.shape[1] != 77 or context.shape[0] != self.B:
-            raise L.LdxError(f"context must be [{self.B}, 77, {self.eng.cfg.context_dim}], got {tuple(context.shape)}")
+        if tuple(context.shape) != tuple(self.ctx.shape):
+            raise L.LdxError(f"context must be {tuple(self.ctx.shape)}, got {tuple(context.shape)}")
         self.ctx.copy_(context.to(F16))
         self.ctx_prog.run()
+
+    def run_body(self):
+        """Replays the recorded UNet program (CUDA graph) on the plan's resident inputs (x_in, sigma_in, context);
+        the result is the fp16 NHWC eps buffer.  The CFG / sampler tail is launched by the caller."""
+        if not self.use_graph:
+            self.prog.run()
+            return
+        if self.graph is None:
+            self.prog.run()                         # warm-up (sets kernel attributes) outside capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.prog.run()
+            self.graph = g
+        self.graph.replay()
 
     def run(self, x, sigma, context=None, cfg_scale: Optional[float] = None) -> torch.Tensor:
         """Returns the plan's output buffer (denoised fp32 NCHW); valid until the next run."""
@@ -481,19 +527,9 @@ class UNetPlan:
             self.x_in.copy_(x)
         if sigma.data_ptr() != self.sigma_in.data_ptr():
             self.sigma_in.copy_(sigma)
+        self.run_body()
         if self.cfg_pairs:
-            self._tail(1.0 if cfg_scale is None else float(cfg_scale))
-        if not self.use_graph:
-            self._launch_all()
-            return self.den
-        if self.graph is None:
-            self._launch_all()                      # warm-up (sets kernel attributes) outside capture
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._launch_all()
-            self.graph = g
-        self.graph.replay()
+            self._tail(1.0 if cfg_scale is None else float(cfg_scale)).run()
         return self.den
 
 
@@ -505,7 +541,7 @@ class VAEDecoderEngine:
         L.require_device()
         self.cfg, self.dev = cfg, torch.device(device)
         self.w: Dict[str, torch.Tensor] = {}
-        self._plans: Dict[tuple, "VAEPlan"] = {}
+        self._plans = _PlanCache()
         sd, dev, w = state_dict, self.dev, self.w
         w["pq.w"], w["pq.b"] = K.pack_linear(sd["post_quant_conv.weight"]), _f32(sd, "post_quant_conv.bias", dev)
         w["cin.w"] = K.pack_conv3x3(UNetEngine._pad_in(sd["decoder.conv_in.weight"]))
@@ -540,16 +576,26 @@ class VAEDecoderEngine:
         w[p + ".conv2.w"], w[p + ".conv2.b"] = w2, b2
 
     def plan(self, B, H, W) -> "VAEPlan":
-        key = (B, H, W)
-        if key not in self._plans:
-            self._plans[key] = VAEPlan(self, B, H, W)
-        return self._plans[key]
+        return self._plans.get((B, H, W), lambda: VAEPlan(self, B, H, W))
 
     @torch.no_grad()
     def decode(self, z: torch.Tensor) -> torch.Tensor:
         """VAE.decode: z fp32 [B,4,h,w] (already / 0.18215) -> image fp32 [B, 8h, 8w, 3] in [0,1]."""
         B, _, H, W = z.shape
         return self.plan(B, H, W).run(z).clone()
+
+    @torch.no_grad()
+    def decode_u8(self, z: torch.Tensor) -> torch.Tensor:
+        """VAE.decode followed by the quantisation the reference applies when it saves an image
+        (clip(255 * img, 0, 255).astype(uint8), LD.py:6750-6751): uint8 [B, 8h, 8w, 3]."""
+        B, _, H, W = z.shape
+        pl = self.plan(B, H, W)
+        pl.run(z)
+        out = torch.empty(pl.img.shape, dtype=torch.uint8, device=self.dev)
+        L.check(L.lib().ldx_vae_postprocess_u8(pl.dec_buf.data_ptr(), pl.dec_buf.shape[-1], out.data_ptr(),
+                                               out.numel() // 3, torch.cuda.current_stream().cuda_stream),
+                "ldx_vae_postprocess_u8")
+        return out
 
     @torch.no_grad()
     def decode_raw(self, z):
@@ -682,7 +728,7 @@ class VAEEncoderEngine(VAEDecoderEngine):
         L.require_device()
         self.cfg, self.dev = cfg, torch.device(device)
         self.w: Dict[str, torch.Tensor] = {}
-        self._plans: Dict[tuple, "VAEEncodePlan"] = {}
+        self._plans = _PlanCache()
         sd, dev, w = state_dict, self.dev, self.w
         w["cin.w"] = K.pack_conv3x3(UNetEngine._pad_in(sd["encoder.conv_in.weight"]))
         w["cin.b"] = _f32(sd, "encoder.conv_in.bias", dev)
@@ -706,10 +752,7 @@ class VAEEncoderEngine(VAEDecoderEngine):
         torch.cuda.synchronize()
 
     def plan(self, B, H, W) -> "VAEEncodePlan":
-        key = (B, H, W)
-        if key not in self._plans:
-            self._plans[key] = VAEEncodePlan(self, B, H, W)
-        return self._plans[key]
+        return self._plans.get((B, H, W), lambda: VAEEncodePlan(self, B, H, W))
 
     def decode(self, z):
         raise L.LdxError("VAEEncoderEngine has no decoder; use VAEDecoderEngine")

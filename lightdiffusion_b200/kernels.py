@@ -118,21 +118,29 @@ def rowstats_parts(d: L.GemmDesc) -> int:
 def attach_rowstats(d: L.GemmDesc, rows: int) -> torch.Tensor:
     """Allocates [rows, parts, 2] fp32 and makes GEMM `d` write its per-row output statistics there."""
     stats = torch.empty(rows, rowstats_parts(d), 2, dtype=torch.float32, device="cuda")
-    d.rowstats_out = stats.data_ptr()
+    d.rowstats_out, d.rowstats_out_parts = stats.data_ptr(), stats.shape[1]
     return stats
+
+
+def _dev16(t: torch.Tensor) -> torch.Tensor:
+    """fp16 copy on the GPU; host tensors are converted on the host first (one H2D copy, no cast kernel)."""
+    return t.detach().to(torch.float16).contiguous().to("cuda")
 
 
 def fold_layer_norm(w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor):
     """LayerNorm(gamma, beta) followed by Linear(w, bias)  ->  (w' fp16 [N, K], gsum fp32 [N], bias' fp32 [N]) for
-    LDX_EPI_ROWNORM: w' = w * gamma, gsum = rowsum(w'), bias' = bias + w @ beta (F.layer_norm LD.py:2403 + F.linear)."""
-    w32 = w.to(device="cuda", dtype=torch.float16).float()
-    g32, b32 = gamma.to(device="cuda", dtype=torch.float32), beta.to(device="cuda", dtype=torch.float32)
+    LDX_EPI_ROWNORM: w' = w * gamma, gsum = rowsum(w'), bias' = bias + w @ beta (F.layer_norm LD.py:2403 + F.linear).
+    A one-time load-time transform, computed where the weights live (host or device) with elementwise products and
+    row sums only."""
+    src = w.device
+    w32 = w.detach().to(torch.float16).float()
+    g32, b32 = gamma.detach().to(src, torch.float32), beta.detach().to(src, torch.float32)
     wf = (w32 * g32[None, :]).to(torch.float16)
-    gsum = wf.float().sum(1).contiguous()
-    bf = w32 @ b32
+    gsum = wf.float().sum(1)
+    bf = (w32 * b32[None, :]).sum(1)
     if bias is not None:
-        bf = bf + bias.to(device="cuda", dtype=torch.float32)
-    return wf.contiguous(), gsum, bf.contiguous()
+        bf = bf + bias.detach().to(src, torch.float32)
+    return wf.contiguous().to("cuda"), gsum.contiguous().to("cuda"), bf.contiguous().to("cuda")
 
 
 # ----------------------------------------------------------------------------- descriptor builders
@@ -204,7 +212,7 @@ def run_gemm(d: L.GemmDesc):
 # ----------------------------------------------------------------------------- weight packing
 def pack_conv3x3(w_oihw: torch.Tensor) -> torch.Tensor:
     cout, cin = w_oihw.shape[:2]
-    w16 = w_oihw.to(device="cuda", dtype=torch.float16).contiguous()
+    w16 = _dev16(w_oihw)
     out = torch.empty(cout, 9 * ceil64(cin), dtype=torch.float16, device="cuda")
     L.check(L.lib().ldx_pack_conv3x3(w16.data_ptr(), out.data_ptr(), cout, cin, _stream()), "ldx_pack_conv3x3")
     return out
@@ -212,7 +220,7 @@ def pack_conv3x3(w_oihw: torch.Tensor) -> torch.Tensor:
 
 def pack_upconv3x3(w_oihw: torch.Tensor) -> torch.Tensor:
     cout, cin = w_oihw.shape[:2]
-    w16 = w_oihw.to(device="cuda", dtype=torch.float16).contiguous()
+    w16 = _dev16(w_oihw)
     out = torch.empty(4, cout, 4 * ceil64(cin), dtype=torch.float16, device="cuda")
     L.check(L.lib().ldx_pack_upconv3x3(w16.data_ptr(), out.data_ptr(), cout, cin, _stream()), "ldx_pack_upconv3x3")
     return out
@@ -220,18 +228,18 @@ def pack_upconv3x3(w_oihw: torch.Tensor) -> torch.Tensor:
 
 def pack_linear(w: torch.Tensor) -> torch.Tensor:
     """[N, K] (or 1x1 conv [N, K, 1, 1]) -> fp16 [N, ceil64(K)] (zero padded)."""
-    w2 = w.reshape(w.shape[0], -1).to(device="cuda", dtype=torch.float16)
+    w2 = w.detach().reshape(w.shape[0], -1).to(torch.float16)
     n, k = w2.shape
     if k % 64 == 0:
-        return w2.contiguous()
-    out = torch.zeros(n, ceil64(k), dtype=torch.float16, device="cuda")
+        return w2.contiguous().to("cuda")
+    out = torch.zeros(n, ceil64(k), dtype=torch.float16, device=w2.device)
     out[:, :k] = w2
-    return out
+    return out.to("cuda")
 
 
 def pack_geglu(w: torch.Tensor, bias: torch.Tensor, half_bn: int = 128):
-    w16 = w.to(device="cuda", dtype=torch.float16).contiguous()
-    b32 = bias.to(device="cuda", dtype=torch.float32).contiguous()
+    w16 = _dev16(w)
+    b32 = bias.detach().to(torch.float32).contiguous().to("cuda")
     two_f, k = w16.shape
     assert k % 64 == 0
     wo, bo = torch.empty_like(w16), torch.empty_like(b32)

@@ -172,21 +172,23 @@ class UNetFunctionWrapper:
     """model_function_wrapper: replaces BaseModel.apply_model for the batched [uncond, cond] call.
 
     ``wrapper(apply_model_fn, {"input", "timestep", "c", "cond_or_uncond"}) -> denoised`` (LD.py:2558-2567).
-    """
+
+    calc_cond_batch hands over a FRESH ``torch.cat`` of the conditioning on every call (cond_cat -> CONDCrossAttn.concat,
+    LD.py:647-663, 2546) and the caching allocator recycles addresses, so a tensor's (pointer, version, shape) says
+    nothing about its content: the cross-attention K/V of the 16 blocks are recomputed from the context on every call
+    (one [B * tokens, 768] x [768, 20480] GEMM, ~1 % of a UNet step).  Contexts of 77 * k tokens (long prompts, padded
+    by the reference to the lcm of the cond / uncond lengths) select a plan of that context length."""
 
     def __init__(self, engine):
         self.engine = engine
-        self._ctx_tag = None
 
     def __call__(self, apply_model_fn, params):
         x, sigma, c = params["input"], params["timestep"], params["c"]
         ctx = c["c_crossattn"]
         b, _, h, w = x.shape
-        plan = self.engine.plan(b, h, w)
-        tag = (ctx.data_ptr(), ctx._version, tuple(ctx.shape))
-        new_ctx = tag != self._ctx_tag or plan is not getattr(self, "_plan", None)
-        self._ctx_tag, self._plan = tag, plan
-        return plan.run(x.float(), sigma.float(), ctx if new_ctx else None).clone()
+        _require(ctx.dim() == 3 and ctx.shape[0] == b, f"c_crossattn must be [{b}, tokens, dim], got {tuple(ctx.shape)}")
+        plan = self.engine.plan(b, h, w, ctx_len=ctx.shape[1])
+        return plan.run(x.float(), sigma.float(), ctx).clone()
 
     def to(self, device):
         return self

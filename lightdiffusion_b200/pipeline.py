@@ -60,7 +60,8 @@ class Txt2ImgPipeline:
                noise_sampler=None) -> torch.Tensor:
         b, _, H, W = noise.shape
         dev = self.unet.dev
-        plan = self.unet.plan(2 * b, H, W, cfg_pairs=True)
+        ctx = self.unet.cat_contexts(uncond.to(dev), cond.to(dev))     # [uncond, cond] order, LD.py:2515; lcm-padded
+        plan = self.unet.plan(2 * b, H, W, cfg_pairs=True, ctx_len=ctx.shape[1])
         sig = torch.as_tensor(sigmas).detach().to("cpu", torch.float32)
         lib, st = L.lib(), torch.cuda.current_stream().cuda_stream
         launches = 0
@@ -71,7 +72,7 @@ class Txt2ImgPipeline:
         x.copy_(noise * torch.sqrt(1.0 + sig[0] ** 2.0) if max_denoise else noise * sig[0])
         if latent is not None and torch.count_nonzero(latent) > 0:
             x.add_(latent.to(dev, torch.float32) * LATENT_SCALE)      # process_latent_in (LD.py:2938-2941)
-        plan.set_context(torch.cat([uncond, cond]).to(dev))            # [uncond, cond] order, LD.py:2515
+        plan.set_context(ctx)
         launches += 1
         n = x.numel()
         if sampler == "dpm_adaptive":
@@ -91,22 +92,33 @@ class Txt2ImgPipeline:
             return xs / LATENT_SCALE
         old = torch.empty_like(x)
         have_old, h_last = False, None
+        C = self.unet.cfg.out_channels
+        if sampler == "dpmpp_2m":
+            # per step: one graph replay of the UNet program + ONE fused tail launch (CFG, denoised, DPM++ 2M update,
+            # old <- denoised, next sigma); coefficients in the reference's 0-d fp32 tensor arithmetic on the host
+            if len(sig) > 1:
+                plan.sigma_in.fill_(float(sig[0]))
+            for i in range(len(sig) - 1):
+                plan.run_body()
+                last = bool(sig[i + 1] == 0)
+                if last:
+                    c_x, c_d, c_o, h = 0.0, 1.0, None, None
+                else:
+                    c_x, c_d, c_o, h = dpmpp2m_coefficients(sig, i, h_last if have_old else None)
+                L.check(lib.ldx_cfg_dpmpp2m_step(plan.eps_buf.data_ptr(), plan.eps_buf.shape[-1], x.data_ptr(),
+                                                 old.data_ptr(), None, float(sig[i]), float(cfg_scale), c_x, c_d,
+                                                 0.0 if c_o is None else c_o, int(have_old and c_o is not None),
+                                                 int(last), float(sig[i + 1]), plan.sigma_in.data_ptr(), b, C, H, W,
+                                                 st), "ldx_cfg_dpmpp2m_step")
+                launches += plan.prog.num_launches + 1
+                have_old, h_last = True, h
+            self.gpu_launches = launches
+            return x / LATENT_SCALE
         for i in range(len(sig) - 1):
             plan.sigma_in.fill_(float(sig[i]))
             den = plan.run(x, plan.sigma_in, None, cfg_scale=cfg_scale)
             launches += plan.num_launches
-            if sampler == "dpmpp_2m":
-                if sig[i + 1] == 0:
-                    x.copy_(den)
-                    h = None
-                else:
-                    c_x, c_d, c_o, h = dpmpp2m_coefficients(sig, i, h_last if have_old else None)
-                    L.check(lib.ldx_dpmpp2m_step(x.data_ptr(), den.data_ptr(), old.data_ptr() if have_old else None,
-                                                 c_x, c_d, 0.0 if c_o is None else c_o, n, st), "ldx_dpmpp2m_step")
-                    launches += 1
-                old.copy_(den)
-                have_old, h_last = True, h
-            elif sampler == "euler_ancestral":
+            if sampler == "euler_ancestral":
                 sigma_down, sigma_up = get_ancestral_step(sig[i], sig[i + 1])
                 nz = None
                 if sig[i + 1] > 0:
@@ -122,10 +134,13 @@ class Txt2ImgPipeline:
         return x / LATENT_SCALE                                      # process_latent_out (LD.py:2965)
 
     @torch.no_grad()
-    def generate(self, noise, cond, uncond, cfg_scale, sigmas, sampler="dpmpp_2m", latent=None, noise_sampler=None):
+    def generate(self, noise, cond, uncond, cfg_scale, sigmas, sampler="dpmpp_2m", latent=None, noise_sampler=None,
+                 u8: bool = False):
+        """``u8``: also quantise the decoded images to uint8 (what the reference saves, LD.py:6750) and return
+        them instead of the fp32 images -- the compact form the multi-GPU gather moves."""
         z = self.sample(noise, cond, uncond, cfg_scale, sigmas, sampler, latent, noise_sampler)
-        img = self.vae.decode(z)
-        self.gpu_launches += self.vae.plan(*[z.shape[0], z.shape[2], z.shape[3]]).prog.num_launches
+        img = self.vae.decode_u8(z) if u8 else self.vae.decode(z)
+        self.gpu_launches += self.vae.plan(*[z.shape[0], z.shape[2], z.shape[3]]).prog.num_launches + int(u8)
         return z, img
 
 
@@ -170,17 +185,19 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 def gather_images(local: torch.Tensor, n_total: int, group=None) -> Optional[torch.Tensor]:
-    """The one collective of the path: all ranks' decoded images -> rank 0 (all_gather over NCCL/NVLink
-    on GPUs, gloo in CPU tests).  ``local`` is this rank's [n_local, H, W, 3] block, padded to the
-    common shard size."""
+    """The one collective of the path: every rank's decoded images land on rank 0 ONLY (a gather over
+    NCCL/NVLink on GPUs, gloo in CPU tests); the other ranks send their block and move on.  ``local`` is this
+    rank's [n_local, H, W, 3] block (uint8 from ``decode_u8`` -- 786 KB per 512x512 image -- or fp32), padded to
+    the common shard size.  Returns the [n_total, H, W, 3] stack on rank 0 and None elsewhere."""
     import torch.distributed as dist
-    world = dist.get_world_size(group)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
     per = (n_total + world - 1) // world
     pad = per - local.shape[0]
     if pad:
         local = torch.cat([local, local.new_zeros(pad, *local.shape[1:])])
-    out = [torch.empty_like(local) for _ in range(world)]
-    dist.all_gather(out, local.contiguous(), group=group)
-    if dist.get_rank(group) != 0:
+    local = local.contiguous()
+    out = [torch.empty_like(local) for _ in range(world)] if rank == 0 else None
+    dist.gather(local, out, dst=0, group=group)
+    if rank != 0:
         return None
     return torch.cat(out)[:n_total]

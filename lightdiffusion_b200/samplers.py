@@ -16,7 +16,7 @@ import torch
 
 from . import _lib as L
 
-__all__ = ["sample_dpmpp_2m", "sample_euler_ancestral", "sample_dpm_adaptive", "PIDStepSizeController",
+__all__ = ["sample_dpmpp_2m", "sample_dpmpp_2m_sde", "sample_euler_ancestral", "sample_dpm_adaptive", "PIDStepSizeController",
            "get_ancestral_step", "get_sigmas_karras", "dpmpp2m_coefficients"]
 
 
@@ -48,11 +48,11 @@ def get_ancestral_step(sigma_from, sigma_to, eta=1.0):
     return sigma_down, sigma_up
 
 
-def dpmpp2m_coefficients(sig: torch.Tensor, i: int, h_last):
-    """(c_x, c_d, c_o, h) of step i: x <- c_x x + c_d D + c_o (D - D_old).  LD.py:1209-1226 with eta = 0."""
+def dpmpp2m_coefficients(sig: torch.Tensor, i: int, h_last, eta: float = 0.0):
+    """(c_x, c_d, c_o, h) of step i: x <- c_x x + c_d D + c_o (D - D_old).  LD.py:1209-1226 (solver 'midpoint')."""
     t, s = -sig[i].log(), -sig[i + 1].log()
     h = s - t
-    eta_h = 0.0 * h
+    eta_h = eta * h
     c_x = sig[i + 1] / sig[i] * (-eta_h).exp()
     c_d = (-h - eta_h).expm1().neg()
     c_o = None
@@ -63,13 +63,18 @@ def dpmpp2m_coefficients(sig: torch.Tensor, i: int, h_last):
 
 
 @torch.no_grad()
-def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0,
+def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=0.0, s_noise=1.0,
                     noise_sampler=None):
-    """DPM-Solver++(2M): the reference's sample_dpmpp_2m_sde (LD.py:1174-1244) at eta=0, solver
-    'midpoint' (SURVEY gotcha 1).  ``eta``/``s_noise``/``noise_sampler`` are accepted for signature
-    compatibility; the deterministic sampler draws no noise."""
+    """DPM-Solver++(2M): the reference's sample_dpmpp_2m_sde (LD.py:1174-1244), solver 'midpoint'.  The north-star
+    sampler is its deterministic case eta = 0 (SURVEY gotcha 1), the default here; the reference's ksampler closure
+    passes its own eta (LD.py:2800-2816).  With eta > 0 the SDE noise term (LD.py:1229-1236) is added from the
+    caller's ``noise_sampler(sigma, sigma_next)``; the reference's default BrownianTreeNoiseSampler (torchsde) is
+    not part of this path, so eta > 0 without a noise_sampler raises instead of silently dropping the noise."""
     extra_args = {} if extra_args is None else extra_args
     _check_state(x)
+    if eta and noise_sampler is None:
+        raise L.LdxError("sample_dpmpp_2m: eta > 0 needs a noise_sampler (the reference's Brownian-tree default is "
+                         "outside the hot path); pass eta=0 for the deterministic DPM++ 2M")
     sig = _host_sigmas(sigmas)
     x = x.clone()
     s_in = x.new_ones([x.shape[0]])
@@ -82,15 +87,32 @@ def sample_dpmpp_2m(model, x, sigmas, extra_args=None, callback=None, disable=No
             x = denoised.clone()
             h = None
         else:
-            c_x, c_d, c_o, h = dpmpp2m_coefficients(sig, i, h_last if old_denoised is not None else None)
+            c_x, c_d, c_o, h = dpmpp2m_coefficients(sig, i, h_last if old_denoised is not None else None, eta)
             L.check(lib.ldx_dpmpp2m_step(x.data_ptr(), denoised.data_ptr(),
                                          None if c_o is None else old_denoised.data_ptr(), c_x, c_d,
                                          0.0 if c_o is None else c_o, n, _stream()), "ldx_dpmpp2m_step")
+            if eta:
+                nz = noise_sampler(sig[i], sig[i + 1]).to(x.device, torch.float32).contiguous()
+                coef = float(sig[i + 1] * (-2 * eta * h).expm1().neg().sqrt() * s_noise)
+                # x <- x + coef * noise  (ldx_dpm_combine computes x - c1 * eps)
+                L.check(lib.ldx_dpm_combine(x.data_ptr(), nz.data_ptr(), None, -coef, 0.0, x.data_ptr(), n, _stream()),
+                        "ldx_dpm_combine")
         if callback is not None:
             callback({"x": x, "i": i, "sigma": sig[i], "sigma_hat": sig[i], "denoised": denoised})
         old_denoised = denoised.clone()      # the model may hand back a buffer it reuses next call
         h_last = h
     return x
+
+
+def sample_dpmpp_2m_sde(model, x, sigmas, extra_args=None, callback=None, disable=None, eta=1.0, s_noise=1.0,
+                        noise_sampler=None, solver_type="midpoint"):
+    """The name and full signature the reference's ksampler closure resolves at call time (LD.py:1174-1185,
+    2800-2816): assign this over the module global to route ``ksampler("dpmpp_2m_sde", {"eta": 0.0})`` -- the
+    reference's spelling of DPM++ 2M -- through the fused update kernel."""
+    if solver_type != "midpoint":
+        raise L.LdxError(f"sample_dpmpp_2m_sde: solver_type {solver_type!r} is not on the hot path (midpoint only)")
+    return sample_dpmpp_2m(model, x, sigmas, extra_args=extra_args, callback=callback, disable=disable, eta=eta,
+                           s_noise=s_noise, noise_sampler=noise_sampler)
 
 
 @torch.no_grad()
@@ -121,7 +143,9 @@ def sample_euler_ancestral(model, x, sigmas, extra_args=None, callback=None, dis
 
 
 class PIDStepSizeController:
-    """LD.py:944-973 (host scalars only)."""
+    """Step-size controller of dpm_solver_adaptive.  Host scalar arithmetic that has to reproduce the reference's
+    accept / reject sequence bit for bit, so it deliberately follows LD.py:944-973 statement by statement (same
+    coefficients b1..b3, same error history update, same atan limiter); nothing here touches the device."""
 
     def __init__(self, h, pcoeff, icoeff, dcoeff, order=1, accept_safety=0.81, eps=1e-8):
         self.h = h

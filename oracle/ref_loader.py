@@ -26,14 +26,16 @@ def reference_available() -> bool:
     return os.path.exists(os.path.join(REF_DIR, "LightDiffusion.py"))
 
 
-_CACHED = None
+_CACHED = {}
 
 
-def load_reference():
-    """exec the reference source into a module (≈16 s) and return it."""
-    global _CACHED
-    if _CACHED is not None:
-        return _CACHED
+def load_reference(force_cpu: bool = False):
+    """exec the reference source into a module (≈16 s) and return it.  ``force_cpu`` loads a second, independent
+    copy whose device manager is pinned to the CPU state (LD.py:1380) even on a GPU box: the reference's own CPU
+    path, timed by bench.py beside the GPU numbers."""
+    cpu = force_cpu or not torch.cuda.is_available()
+    if cpu in _CACHED:
+        return _CACHED[cpu]
     for name in ["tkinter", "tkinter.filedialog", "customtkinter", "ollama", "torchsde",
                  "segment_anything", "ultralytics", "PIL.ImageTk"]:
         m = mock.MagicMock(name=name)
@@ -45,7 +47,7 @@ def load_reference():
     PIL.ImageTk = sys.modules["PIL.ImageTk"]
     path = os.path.join(REF_DIR, "LightDiffusion.py")
     src = open(path).read()
-    if not torch.cuda.is_available():
+    if cpu:
         assert src.count("cpu_state = CPUState.GPU\n") == 1
         src = src.replace("cpu_state = CPUState.GPU\n", "cpu_state = CPUState.CPU\n")
     real_glob = _glob.glob
@@ -53,9 +55,10 @@ def load_reference():
     cwd = os.getcwd()
     os.chdir(REF_DIR)
     try:
-        mod = types.ModuleType("LightDiffusion_ref")
+        name = "LightDiffusion_ref_cpu" if (cpu and torch.cuda.is_available()) else "LightDiffusion_ref"
+        mod = types.ModuleType(name)
         mod.__file__ = path
-        sys.modules["LightDiffusion_ref"] = mod
+        sys.modules[name] = mod
         exec(compile(src, path, "exec"), mod.__dict__)
     finally:
         os.chdir(cwd)
@@ -71,7 +74,7 @@ def load_reference():
 
     mod.app = _App()
     mod.PROGRESS_BAR_ENABLED = False
-    _CACHED = mod
+    _CACHED[cpu] = mod
     return mod
 
 
@@ -99,9 +102,9 @@ def build_ref_model(R, cfg, sd, dtype=torch.float32):
     return model.eval()
 
 
-def build_ref_vae(R, sd, dtype=torch.float32):
+def build_ref_vae(R, sd, dtype=torch.float32, device=None):
     """Reference VAE (LD.py:6282) with our seeded decoder and/or encoder weights (the other half left as built)."""
-    vae = R.VAE(sd={}, device=torch.device("cpu"), dtype=dtype)
+    vae = R.VAE(sd={}, device=torch.device("cpu") if device is None else device, dtype=dtype)
     fsm = vae.first_stage_model
     own = fsm.state_dict()
     halves = (("encoder.", "quant_conv.") if any(k.startswith("encoder.") for k in sd) else ()) + \

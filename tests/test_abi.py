@@ -78,6 +78,9 @@ def test_argument_validation_returns_error_codes(lib):
         l.ldx_vae_preprocess(None, addr, 4, None),
         l.ldx_vae_sample_posterior(addr, None, None, 1, 4, 16, None),
         l.ldx_attention_causal(addr, 64, addr, 64, addr, 64, addr, 64, 1, 77, 1, 40, None),   # d = 64 only
+        l.ldx_cfg_dpmpp2m_step(addr, 8, addr, None, None, 1.0, 7.0, 0.5, 0.5, 0.0, 0, 0, 0.5, None, 1, 4, 8, 8, None),
+        l.ldx_cfg_dpmpp2m_step(addr, 2, addr, addr, None, 1.0, 7.0, 0.5, 0.5, 0.0, 0, 0, 0.5, None, 1, 4, 8, 8, None),  # pitch < C
+        l.ldx_vae_postprocess_u8(addr, 8, None, 16, None),
     ]
     assert all(rc != 0 for rc in bad), bad
     assert l.ldx_last_error_string()

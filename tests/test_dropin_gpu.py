@@ -1,0 +1,219 @@
+"""Drop-in boundary with the REFERENCE in the driver's seat.
+
+The unmodified reference (`LightDiffusion.py`, loaded by oracle/ref_loader.py from the copy that travels with
+the repo under baseline/_ref/reference, or from $LDX_REFERENCE_DIR) runs its own `sample()` ->
+CFGGuider -> KSAMPLER -> `sample_dpmpp_2m_sde(eta=0)` -> `sampling_function` -> `calc_cond_batch` loop on the
+GPU, and the ldx seams are installed INTO it the way INTEGRATION.md says a maintainer would:
+
+  seam #4  patcher.set_model_unet_function_wrapper(UNetFunctionWrapper(engine))      (LD.py:3277, 2558-2567)
+  seam #3  LightDiffusion.sample_dpmpp_2m_sde = samplers.sample_dpmpp_2m_sde           (LD.py:2800-2816)
+  seam #1  LightDiffusion.disable_weight_init = LightDiffusion.ops = ldx_ops before BaseModel(...)
+                                                                                       (LD.py:5810-5816, 4511)
+  seam #2  LightDiffusion.optimized_attention = ops.optimized_attention                (LD.py:4035)
+
+Every comparison is against the reference's own PyTorch path on the same seeded fp16 weights, seeds, latents and
+conditioning: its fp16 GPU path (the secondary oracle of SURVEY §4(iii)) and the same code in fp32.
+Tolerances: per-step UNet eps within 2e-3 relative L2 (north_star) of the reference's fp32 evaluation of the
+same fp16 weights; against the reference's fp16 path the bar is that path's own distance from fp32 (both are
+fp16 roundings of the same function, measured and printed), see DESIGN.md §2.
+"""
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LOCAL_REF = os.path.join(ROOT, "baseline", "_ref", "reference")
+if "LDX_REFERENCE_DIR" not in os.environ and os.path.exists(os.path.join(_LOCAL_REF, "LightDiffusion.py")):
+    os.environ["LDX_REFERENCE_DIR"] = _LOCAL_REF
+
+DEV = "cuda"
+EPS_TOL = 2e-3
+STEPS = 6
+B_IMG = 2
+LAT = 64
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.fixture(scope="module")
+def env():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from oracle import ref_loader
+    if not ref_loader.reference_available():
+        pytest.skip(f"reference not found under {ref_loader.REF_DIR} (set LDX_REFERENCE_DIR)")
+    from lightdiffusion_b200 import sd15
+    from lightdiffusion_b200.engine import UNetEngine
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    R = ref_loader.load_reference()
+    cfg = sd15.SD15_UNET
+    sd = {k: v.to(torch.float16) for k, v in
+          sd15.seeded_state_dict(sd15.unet_param_shapes(cfg), 1234, bias_std=0.05, norm_jitter=0.1).items()}
+    m16 = ref_loader.build_ref_model(R, cfg, sd, torch.float16).to(DEV)
+    eng = UNetEngine({k: v.to(DEV) for k, v in sd.items()}, cfg)
+    dev = torch.device(DEV)
+    patcher = R.ModelPatcher(m16, load_device=dev, offload_device=dev, current_device=dev)
+    sigmas = R.calculate_sigmas(m16.model_sampling, "karras", STEPS)
+
+    def conds(seed):
+        g = torch.Generator().manual_seed(seed)
+        return ([[torch.randn(B_IMG, 77, 768, generator=g), {}]], [[torch.randn(B_IMG, 77, 768, generator=g), {}]])
+
+    lat = torch.zeros(B_IMG, 4, LAT, LAT)
+    noise = R.prepare_noise(lat, 42)
+
+    def run(p, pos, neg, sig=sigmas):
+        with torch.inference_mode():
+            return R.sample(p, noise, pos, neg, 7.0, dev, R.ksampler("dpmpp_2m_sde", {"eta": 0.0}), sig,
+                            model_options=p.model_options, latent_image=lat, disable_pbar=True, seed=42).float().clone()
+
+    return dict(R=R, cfg=cfg, sd=sd, m16=m16, eng=eng, patcher=patcher, sigmas=sigmas, conds=conds, run=run, dev=dev)
+
+
+class _Recorder:
+    """model_function_wrapper that lets the stock apply_model run and keeps its inputs and output."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, apply_model_fn, params):
+        out = apply_model_fn(params["input"], params["timestep"], **params["c"])
+        self.calls.append((params["input"].clone(), params["timestep"].clone(), params["c"]["c_crossattn"].clone(),
+                           list(params["cond_or_uncond"]), out.clone()))
+        return out
+
+
+@pytest.fixture(scope="module")
+def recorded(env):
+    """One stock reference run (fp16 GPU path) with every calc_cond_batch call recorded."""
+    rec = _Recorder()
+    p = env["patcher"].clone()
+    p.set_model_unet_function_wrapper(rec)
+    pos, neg = env["conds"](3)
+    z = env["run"](p, pos, neg)
+    assert len(rec.calls) == STEPS
+    return rec.calls, z, (pos, neg)
+
+
+def test_seam4_per_step_eps_vs_reference_paths(env, recorded):
+    """calc_cond_batch's exact per-step inputs through UNetFunctionWrapper vs the reference's apply_model."""
+    from lightdiffusion_b200.ops import UNetFunctionWrapper
+    from oracle import ref_loader
+    calls, _, _ = recorded
+    R = env["R"]
+    m32 = ref_loader.build_ref_model(R, env["cfg"], env["sd"], torch.float32).to(DEV)
+    wrap = UNetFunctionWrapper(env["eng"])
+    worst32 = worst16 = floor = 0.0
+    with torch.inference_mode():
+        for x, t, ctx, cou, out16 in calls:
+            assert cou == [1, 0] and x.shape[0] == 2 * B_IMG           # [uncond, cond] in one batch (LD.py:2515)
+            ours = wrap(None, {"input": x, "timestep": t, "c": {"c_crossattn": ctx}, "cond_or_uncond": cou})
+            out32 = m32.apply_model(x, t, c_crossattn=ctx, transformer_options={})
+            s = t.view(-1, 1, 1, 1)
+            e_ours, e16, e32 = (x - ours) / s, (x - out16) / s, (x - out32) / s
+            r32, r16, f = rel(e_ours, e32), rel(e_ours, e16), rel(e16, e32)
+            print(f"sigma {float(t[0]):8.4f}: ours vs ref fp32 {r32:.2e} | ours vs ref fp16 {r16:.2e} | "
+                  f"ref fp16 vs ref fp32 {f:.2e}")
+            worst32, worst16, floor = max(worst32, r32), max(worst16, r16), max(floor, f)
+    del m32
+    torch.cuda.empty_cache()
+    assert worst32 <= EPS_TOL, worst32
+    # two fp16 evaluations of the same function: the distance between them is bounded by the sum of their own
+    # distances from the fp32 evaluation, and ours must not be the larger contributor
+    assert worst32 <= floor * 1.05 + 1e-4, (worst32, floor)
+    assert worst16 <= floor + worst32, (worst16, floor, worst32)
+
+
+def test_seam4_reference_sample_with_wrapper_and_prompt_change(env, recorded):
+    """The reference's own sample() loop with the ldx engine behind model_function_wrapper; a second prompt on the
+    same patcher must not be served the first prompt's cross-attention K/V."""
+    from lightdiffusion_b200.ops import UNetFunctionWrapper
+    _, z_a_ref, (pos_a, neg_a) = recorded
+    p = env["patcher"].clone()
+    p.set_model_unet_function_wrapper(UNetFunctionWrapper(env["eng"]))
+    z_a = env["run"](p, pos_a, neg_a)
+    pos_b, neg_b = env["conds"](4)
+    z_b = env["run"](p, pos_b, neg_b)                       # same shapes, fresh tensors, different content
+    z_b_ref = env["run"](env["patcher"], pos_b, neg_b)
+    ra, rb, cross = rel(z_a, z_a_ref), rel(z_b, z_b_ref), rel(z_b, z_a_ref)
+    print(f"final latent after {STEPS} steps: prompt A {ra:.2e}, prompt B {rb:.2e}; B vs A's reference {cross:.2e}")
+    assert ra < 2e-2 and rb < 2e-2, (ra, rb)
+    assert cross > 10 * rb                                  # the prompts really differ
+
+
+def test_seam4_long_prompt_context(env):
+    """A two-section cond (154 tokens) against a 77-token uncond: the reference repeats the shorter one to the lcm
+    (LD.py:647-663) and the wrapper receives [4, 154, 768]."""
+    from lightdiffusion_b200.ops import UNetFunctionWrapper
+    g = torch.Generator().manual_seed(9)
+    pos = [[torch.randn(B_IMG, 154, 768, generator=g), {}]]
+    neg = [[torch.randn(B_IMG, 77, 768, generator=g), {}]]
+    sig = env["sigmas"][-3:]
+    z_ref = env["run"](env["patcher"], pos, neg, sig)
+    p = env["patcher"].clone()
+    p.set_model_unet_function_wrapper(UNetFunctionWrapper(env["eng"]))
+    z = env["run"](p, pos, neg, sig)
+    r = rel(z, z_ref)
+    print(f"154-token cond / 77-token uncond, final latent: {r:.2e}")
+    assert r < 2e-2, r
+
+
+def test_seam3_reference_ksampler_calls_ldx_sampler(env, recorded, monkeypatch):
+    """ksampler("dpmpp_2m_sde", {"eta": 0}) resolves sample_dpmpp_2m_sde at call time (LD.py:2800-2816): with the
+    module global replaced, the reference's KSAMPLER drives the fused update kernel around its own UNet."""
+    from lightdiffusion_b200 import samplers as S
+    _, z_ref, (pos, neg) = recorded
+    R = env["R"]
+    seen = []
+
+    def spy(*a, **k):
+        seen.append(k.get("eta"))
+        return S.sample_dpmpp_2m_sde(*a, **k)
+
+    monkeypatch.setattr(R, "sample_dpmpp_2m_sde", spy)
+    z = env["run"](env["patcher"], pos, neg)
+    assert seen == [0.0]
+    r = rel(z, z_ref)
+    print(f"reference UNet + ldx DPM++ 2M update: final latent {r:.2e}")
+    assert r < 1e-4, r                                      # same fp16 UNet; only the fp32 update arithmetic differs
+
+
+def test_seams_1_2_reference_unet_built_from_ldx_ops(env, recorded, monkeypatch):
+    """UNetModel1(operations=ldx_ops) (BaseModel.__init__ LD.py:5810-5816) with optimized_attention replaced
+    (LD.py:4035): the reference's own module graph, every Linear / Conv2d / GroupNorm / LayerNorm / attention
+    call landing in libldx.so."""
+    from lightdiffusion_b200 import ops
+    from oracle import ref_loader
+    calls, _, _ = recorded
+    R = env["R"]
+    monkeypatch.setattr(R, "disable_weight_init", ops.ldx_ops)
+    monkeypatch.setattr(R, "ops", ops.ldx_ops)             # GEGLU's projection reads the module-global (LD.py:4511)
+    m = ref_loader.build_ref_model(R, env["cfg"], env["sd"], torch.float16).to(DEV)
+    kinds = {type(mod).__module__ for mod in m.diffusion_model.modules()
+             if isinstance(mod, (torch.nn.Linear, torch.nn.Conv2d, torch.nn.GroupNorm, torch.nn.LayerNorm))}
+    assert kinds == {"lightdiffusion_b200.ops"}, kinds
+    n_attn = []
+    real_attn = ops.optimized_attention
+
+    def attn(q, k, v, heads, mask=None):
+        n_attn.append(q.shape[1])
+        return real_attn(q, k, v, heads, mask)
+
+    monkeypatch.setattr(R, "optimized_attention", attn)
+    worst = 0.0
+    with torch.inference_mode():
+        for x, t, ctx, cou, out16 in calls[:: max(1, STEPS // 3)]:
+            out = m.apply_model(x, t, c_crossattn=ctx, transformer_options={})
+            s = t.view(-1, 1, 1, 1)
+            r = rel((x - out) / s, (x - out16) / s)
+            print(f"sigma {float(t[0]):8.4f}: reference graph on ldx ops vs reference fp16: {r:.2e}")
+            worst = max(worst, r)
+    assert n_attn and len(n_attn) % 32 == 0                 # 16 self + 16 cross attention calls per evaluation
+    assert worst <= 3e-3, worst                             # two fp16 paths: bounded by the sum of their fp32 distances

@@ -181,6 +181,71 @@ def test_unet_sd15_eps_parity(sd15_unet):
     assert max(errs) < EPS_TOL, errs
 
 
+def test_unet_sd15_eps_parity_benched_config_b8(sd15_unet):
+    """BASELINE.json config 2, the shape bench.py times: 8 images -> the B = 16 classifier-free-guidance plan
+    (different tile / CTA-pair choices than B = 2, split-K on the 8x8 convs, the shared CFG prefix at 320-channel
+    width).  Every one of the 16 eps maps is compared with the oracle at four sigmas of the Karras schedule."""
+    cfg, sd, eng = sd15_unet
+    b = 8
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(b, 4, 64, 64, generator=g).to(DEV)
+    cond = torch.randn(b, 77, cfg.context_dim, generator=g).to(DEV)
+    uncond = torch.randn(b, 77, cfg.context_dim, generator=g).to(DEV)
+    plan = eng.plan(2 * b, 64, 64, cfg_pairs=True)
+    ctx = torch.cat([uncond, cond])
+    plan.set_context(ctx)
+    worst = []
+    for s in (14.6146, 4.4998, 0.7909, 0.0292):
+        sigma = torch.full((b,), s, device=DEV)
+        xs = x * math.sqrt(1 + s * s)
+        den = plan.run(xs, sigma, None, cfg_scale=7.0).clone()
+        e = plan.eps_buf[..., :cfg.out_channels].float().permute(0, 3, 1, 2).contiguous()      # [16, 4, 64, 64]
+        refs = []
+        for lo in range(0, 2 * b, 4):                   # oracle in chunks of 4 samples (fp32 attention memory)
+            xin = torch.cat([xs, xs])[lo:lo + 4]
+            refs.append(_oracle_eps(sd, cfg, xin, torch.full((4,), s, device=DEV), ctx[lo:lo + 4]))
+        ref = torch.cat(refs)
+        per = [rel(e[i], ref[i]) for i in range(2 * b)]
+        worst.append(max(per))
+        # the fused CFG tail on top of those eps maps (cfg_function LD.py:2605 on the denoised predictions)
+        du, dc = xs - ref[:b] * s, xs - ref[b:] * s
+        den_ref = du + (dc - du) * 7.0
+        assert rel((xs - den) / s, (xs - den_ref) / s) < 3 * EPS_TOL
+    print("SD1.5 B=16 CFG plan, worst per-sample eps rel-L2 per sigma:", worst)
+    assert max(worst) < EPS_TOL, worst
+
+
+def test_unet_long_context_154_tokens(small_unet):
+    """Two 77-token prompt sections: the cond is [b, 154, C] and the uncond [b, 77, C]; the reference repeats the
+    shorter one to the lcm (CONDCrossAttn.concat, LD.py:647-663), which leaves softmax attention unchanged."""
+    cfg, sd, eng = small_unet
+    g = torch.Generator().manual_seed(61)
+    x = (torch.randn(2, 4, 16, 16, generator=g) * 4).to(DEV)
+    cond = torch.randn(2, 154, cfg.context_dim, generator=g).to(DEV)
+    uncond = torch.randn(2, 77, cfg.context_dim, generator=g).to(DEV)
+    sigma = torch.tensor([3.0, 0.7], device=DEV)
+    out = eng.denoise_cfg(x, sigma, cond, uncond, 7.0)
+    model = O.cfg_denoiser(sd, cfg, cond, uncond.repeat(1, 2, 1), 7.0, model_dtype=torch.float16)
+    with torch.inference_mode():
+        ref = model(x, sigma)
+    sv = sigma.view(-1, 1, 1, 1)
+    assert rel((x - out) / sv, (x - ref) / sv) < 3 * EPS_TOL
+    e = eng.eps(x, sigma, cond)                          # plain (non-CFG) plan with a 154-token context
+    assert rel(e, _oracle_eps(sd, cfg, x, sigma, cond)) < EPS_TOL
+    with pytest.raises(Exception):
+        eng.plan(2, 16, 16).set_context(cond)            # a 77-token plan rejects a 154-token context loudly
+
+
+def test_plan_cache_is_bounded(small_unet):
+    """An img2img flow over many tile shapes must not keep every plan (pool + CUDA graph) alive."""
+    from lightdiffusion_b200 import engine as E
+    cfg, sd, eng = small_unet
+    for hw in (8, 16, 24, 32, 40, 48):
+        eng.plan(1, hw, hw)
+    assert len(eng._plans) <= E.MAX_PLANS
+    assert (1, 48, 48, False, 77) in eng._plans and (1, 8, 8, False, 77) not in eng._plans
+
+
 def test_unet_sd15_eps_parity_hires_128(sd15_unet):
     """BASELINE.json config 4: the hires-fix second pass runs the UNet on a 128x128 latent
     (16384-token self-attention at the 320-channel level)."""

@@ -119,8 +119,12 @@ def _gather_worker(rank, world, port, n_total, q):
     lo, hi = shard_range(n_total, rank, world)
     local = torch.stack([torch.full((4, 4, 3), float(i)) for i in range(lo, hi)]) if hi > lo else torch.zeros(0, 4, 4, 3)
     out = gather_images(local, n_total)
+    u8 = gather_images((local % 251).to(torch.uint8), n_total)         # the compact form the bench gathers
     if rank == 0:
+        assert u8.dtype == torch.uint8 and u8[:, 0, 0, 0].tolist() == [i % 251 for i in range(n_total)]
         q.put(out[:, 0, 0, 0].tolist())
+    else:
+        assert out is None and u8 is None                              # the images land on rank 0 only
     dist.barrier()
     dist.destroy_process_group()
 

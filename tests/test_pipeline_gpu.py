@@ -258,21 +258,33 @@ def test_small_hires_fix_matches_oracle(small_pipe):
     assert psnr(img, imgr) >= 40.0
 
 
-def test_sd15_txt2img_20step_psnr():
+@pytest.mark.parametrize("b", [1, 8])
+def test_sd15_txt2img_20step_psnr(b):
     """north_star: 20-step DPM++ 2M Karras, CFG 7, 512^2, random-init SD1.5 weights -> decoded image
-    >= 40 dB PSNR against the reference algorithm on the same weights, seeds and latents."""
+    >= 40 dB PSNR against the reference algorithm on the same weights, seeds and latents.  b = 8 is the
+    configuration bench.py times (BASELINE.json config 2: the B = 16 CFG plan, fused step tail, VAE decode of 8
+    latents); every image of the batch has to clear the bar on its own."""
     cfg = sd15.SD15_UNET
     usd = rounded(sd15.seeded_state_dict(sd15.unet_param_shapes(cfg), 1234))
     vsd = rounded(sd15.seeded_state_dict(sd15.vae_decoder_param_shapes(), 99))
     pipe = Txt2ImgPipeline(UNetEngine(usd, cfg), VAEDecoderEngine(vsd))
-    b, hw = 1, 64
+    hw = 64
     cond, uncond = _conds(b, cfg.context_dim, 42)
     torch.manual_seed(42)
     noise = torch.randn(b, 4, hw, hw).to(DEV)            # prepare_noise: CPU generator seeded per image
     sig = calculate_sigmas("karras", 20)
     z, img = pipe.generate(noise, cond, uncond, 7.0, sig, "dpmpp_2m")
+    zs, imgs = [], []
     with torch.inference_mode():
-        zr, imgr = O.txt2img(usd, cfg, vsd, sd15.SD15_VAE, noise, cond.half().float(), uncond.half().float(), 7.0,
-                             sig.to(DEV), "dpmpp_2m")
-    print("sd15 20-step latent rel", rel(z, zr), "psnr", psnr(img, imgr))
-    assert psnr(img, imgr) >= 40.0
+        for lo in range(0, b, 2):                        # the oracle runs two images at a time (fp32 memory)
+            sl = slice(lo, min(b, lo + 2))
+            zr, imgr = O.txt2img(usd, cfg, vsd, sd15.SD15_VAE, noise[sl], cond[sl].half().float(),
+                                 uncond[sl].half().float(), 7.0, sig.to(DEV), "dpmpp_2m")
+            zs.append(zr); imgs.append(imgr)
+    zr, imgr = torch.cat(zs), torch.cat(imgs)
+    per_image = [psnr(img[i], imgr[i]) for i in range(b)]
+    print(f"sd15 20-step b={b}: latent rel", rel(z, zr), "psnr per image", [round(p, 1) for p in per_image])
+    assert min(per_image) >= 40.0, per_image
+    u8 = pipe.vae.decode_u8(z)                           # the quantised form the multi-GPU gather moves
+    assert u8.dtype == torch.uint8 and u8.shape == img.shape
+    assert int((u8.int() - (255.0 * img).clamp(0, 255).to(torch.uint8).int()).abs().max()) == 0
