@@ -115,6 +115,21 @@ int ldx_pack_conv3x3(const void* w_oihw, void* w_packed, int cout, int cin, ldx_
  * LD.py:3507-3511): folds the 3x3 taps onto the low-resolution grid -> 4 output-parity phases of
  * 2x2 taps: [4 phases][Cout][4 * ceil64(Cin)] fp16, summed in fp32. */
 int ldx_pack_upconv3x3(const void* w_oihw, void* w_packed, int cout, int cin, ldx_stream_t stream);
+/* 3x3 stride-1 pad-1 convolution with 1..5 output channels: the VAE decoder's conv_out 128 -> 3 (LD.py:3880-3882)
+ * and the UNet's out conv 320 -> 4 (LD.py:5655-5661), through F.conv2d / _conv_forward (LD.py:2382).  HBM bound: every
+ * input pixel is read once (16 x 16 halo tiles by TMA), the tensor core produces the 9 * Cout per-tap partial
+ * products of each INPUT pixel and the epilogue gathers the nine taps of each output pixel.
+ *   x        fp16 NHWC [B, H, W, Cin], pixel pitch ldx_pix elements (16-byte aligned, Cin % 8 == 0)
+ *   w_packed ldx_pack_conv3x3_small(w_oihw): [ceil16(9 * Cout)][ceil64(Cin)] fp16, row tap * Cout + o
+ *   out16    fp16 NHWC, pixel pitch ldo16 (first Cout channels written), or NULL
+ *   out_img  fp32 NHWC [B, H, W, Cout], or NULL; post = 1 applies VAE.process_output to the fp16-rounded result:
+ *            clamp((v + 1) / 2, 0, 1) (LD.py:6296-6298, 6377-6380); post = 0 stores it as is */
+int ldx_conv3x3_small(const void* x, int B, int H, int W, int Cin, int64_t ldx_pix, const void* w_packed,
+                      const float* bias, int Cout, void* out16, int64_t ldo16, float* out_img, int post,
+                      ldx_stream_t stream);
+int ldx_pack_conv3x3_small(const void* w_oihw, void* w_packed, int cout, int cin, ldx_stream_t stream);
+/* number of fp16 elements ldx_pack_conv3x3_small writes (-1: unsupported Cout) */
+int ldx_conv3x3_small_packed_elems(int cout, int cin);
 /* GEGLU proj weight [2*F, K] (+ bias[2*F]) -> rows interleaved in blocks of `half_bn` so that one
  * output tile holds matching value/gate columns. */
 int ldx_pack_geglu(const void* w, const float* bias, void* w_packed, float* bias_packed, int two_f, int k,
@@ -242,6 +257,8 @@ enum {
   LDX_OP_NCHW_TO_NHWC = 5, LDX_OP_TIMESTEP_EMB = 6, LDX_OP_UPSAMPLE2X = 7, LDX_OP_EPS_TO_DENOISED = 8,
   LDX_OP_CFG_DENOISED = 9, LDX_OP_VAE_POST = 10, LDX_OP_SOFTMAX = 11,
   /* LDX_OP_ATTENTION takes i[5] = 1 for the causal variant (ldx_attention_causal) */
+  LDX_OP_CONV_SMALL = 16,    /* ldx_conv3x3_small.  p: x, w_packed, bias, out16, out_img ; i: B, H, W, Cin, Cout, post ;
+                                l: pixel pitch of x, pixel pitch of out16 */
   LDX_OP_CLIP_EMBED = 15,    /* p: tokens, tok_emb, pos_emb, out ; l: ldo ; i: rows, T, C */
   LDX_OP_VAE_PRE = 13,       /* p: pixels, out ; l: npix */
   LDX_OP_VAE_SAMPLE = 14,    /* p: moments, noise, z ; l: n, hw ; i: zc */

@@ -23,7 +23,7 @@ DPM_ERROR_WS_DOUBLES = 2048
 OP_GEMM, OP_GROUP_NORM, OP_LAYER_NORM, OP_ATTENTION = 1, 2, 3, 4
 OP_NCHW_TO_NHWC, OP_TIMESTEP_EMB, OP_UPSAMPLE2X, OP_EPS_TO_DENOISED = 5, 6, 7, 8
 OP_CFG_DENOISED, OP_VAE_POST, OP_SOFTMAX = 9, 10, 11
-OP_DUP, OP_VAE_PRE, OP_VAE_SAMPLE, OP_CLIP_EMBED = 12, 13, 14, 15
+OP_DUP, OP_VAE_PRE, OP_VAE_SAMPLE, OP_CLIP_EMBED, OP_CONV_SMALL = 12, 13, 14, 15, 16
 
 GN_STATS_FLOATS_PER_BATCH = 64 * 32 * 2      # ldx_group_norm workspace: B * this many floats
 
@@ -71,6 +71,10 @@ _SIGS = {
     "ldx_gemm_rowstats_parts": (C.c_int, [C.POINTER(GemmDesc)]),
     "ldx_pack_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldx_pack_upconv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ldx_conv3x3_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p]),
+    "ldx_pack_conv3x3_small": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ldx_conv3x3_small_packed_elems": (C.c_int, [C.c_int, C.c_int]),
     "ldx_pack_geglu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "ldx_group_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int,
                                  C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,

@@ -195,8 +195,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
   const int stages = p.stages;
   const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
   const int worker = (int)blockIdx.x / kCtas, nworkers = (int)gridDim.x / kCtas;
-  const int bn_cta = p.bn / kCtas;                           // B rows this CTA loads
+  const int bn_cta = p.bn / kCtas;                           // B rows this CTA loads per stage
+  const int nsub = p.nsub;                                   // accumulators per tile (1, or 2 halves of bn / 2 columns)
+  const int sub_rows = bn_cta / nsub;                        // B rows of one accumulator held by this CTA
   const uint32_t b_stage_bytes = (uint32_t)bn_cta * BK * 2;
+  const uint32_t b_sub_bytes = (uint32_t)sub_rows * BK * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)stages * A_STAGE_BYTES;
   uint8_t* sC = sB + (size_t)stages * b_stage_bytes;          // per-warp staging slots (1024-aligned)
@@ -245,7 +248,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
         const int split = p.nsplit > 1 ? tile / p.base_tiles : 0;
         tile_coords<kCtas>(p, tile - split * p.base_tiles, (int)cta_rank, nt, tx, ty, tb);
         const int k_lo = split * p.ksplit, k_hi = min(p.nk, k_lo + p.ksplit);   // this tile's K steps
-        const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * p.bn + (int)cta_rank * bn_cta;
+        // rows of B this CTA fetches for accumulator j: bn0 + j * (bn / nsub) (the pair splits each accumulator's rows)
+        const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * p.bn + (int)cta_rank * sub_rows;
+        const int sub_step = p.bn / nsub;
         int kcol = 0;
         auto load_step = [&](const CUtensorMap* am, int ac0, int ax, int ay, const CUtensorMap* bm, int bk, int bn0) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2 * (A_STAGE_BYTES + b_stage_bytes));
               tma_load_4d_pair(dA, am, lbar, ac0, ax, ay, b0);
               tma_load_2d_pair(dB, bm, lbar, bk, bn0);
+              if (nsub == 2) tma_load_2d_pair(dB + b_sub_bytes, bm, lbar, bk, bn0 + sub_step);
             }
           } else {
             if (elect_one()) {
@@ -284,20 +290,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
         // residual fused as an identity K segment (see gemm_prepare): A = the residual tile's own column
         // range, B = the matching rows of I
         for (int dk = 0; dk < p.diag_chunks; ++dk)
-          load_step(&p.amap[p.diag_src], nt * p.bn + dk * BK, x0, y0, &p.idmap, dk * BK, (int)cta_rank * bn_cta);
+          load_step(&p.amap[p.diag_src], nt * p.bn + dk * BK, x0, y0, &p.idmap, dk * BK, (int)cta_rank * sub_rows);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA; warp-uniform
     // loop, one elected lane issues)
     if (cta_rank == 0) {
-      const uint32_t idesc = umma_idesc_f16(BM * kCtas, p.bn);
+      const uint32_t idesc = umma_idesc_f16(BM * kCtas, p.bn / nsub);
+      const uint32_t sub_cols = (uint32_t)(p.bn / nsub);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
       for (int tile = worker; tile < p.num_tiles; tile += nworkers, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int as = p.single_acc ? 0 : (it & 1);
+        const uint32_t aphase = p.single_acc ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
         mbar_wait(&bars->tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * p.acc_stride;
@@ -314,8 +321,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t ad = umma_desc_kmajor_sw128(a_addr + k * 32), bd = umma_desc_kmajor_sw128(b_addr + k * 32);
-              if constexpr (kCtas == 2) umma_f16_ss_pair(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
-              else umma_f16_ss(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+              if constexpr (kCtas == 2) {
+                umma_f16_ss_pair(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+                if (nsub == 2)    // second accumulator: same A stage, the other half of the B stage
+                  umma_f16_ss_pair(d_tmem + sub_cols, ad, umma_desc_kmajor_sw128(b_addr + b_sub_bytes + k * 32), idesc,
+                                   (uint32_t)((kb | k) != 0));
+              } else {
+                umma_f16_ss(d_tmem, ad, bd, idesc, (uint32_t)((kb | k) != 0));
+              }
             }
             // frees the smem stage (in both CTAs) once these MMAs have read it
             if constexpr (kCtas == 2) umma_commit_pair(&bars->empty[stage], 3); else umma_commit(&bars->empty[stage]);
@@ -361,8 +374,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
     int it = 0;
     PH_DECL
     for (int tile = worker; tile < p.num_tiles; tile += nworkers, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = p.single_acc ? 0 : (it & 1);
+      const uint32_t aphase = p.single_acc ? (uint32_t)(it & 1) : (uint32_t)((it >> 1) & 1);
       int nt, tx, ty, tb;
       const int split = p.nsplit > 1 ? tile / p.base_tiles : 0;
       tile_coords<kCtas>(p, tile - split * p.base_tiles, (int)cta_rank, nt, tx, ty, tb);
@@ -700,19 +713,20 @@ static int pow2_ceil(int v) {
 // samples from a worker thread, LD.py:10453, and one process may drive several GPUs).
 static std::mutex g_const_mu;
 
-// 256 x 256 fp16 identity: B operand of the fused-residual K steps.  Any bn x 64 slice of a larger identity
-// that a tile needs equals a slice of this one.
+// IDENT_N x IDENT_N fp16 identity: B operand of the fused-residual K steps.  Any bn x 64 slice of a larger identity
+// that a tile needs equals a slice of this one (bn <= 512 with two accumulators).
+static constexpr int IDENT_N = 512;
 static const void* identity256() {
   static void* dev_ptr[LDX_MAX_DEVICES] = {};
   const int dev = current_device() & (LDX_MAX_DEVICES - 1);
   std::lock_guard<std::mutex> lock(g_const_mu);
   if (!dev_ptr[dev]) {
-    __half* host = (__half*)calloc(256 * 256, sizeof(__half));
+    __half* host = (__half*)calloc((size_t)IDENT_N * IDENT_N, sizeof(__half));
     if (!host) return nullptr;
-    for (int i = 0; i < 256; ++i) host[i * 256 + i] = __float2half(1.0f);
+    for (int i = 0; i < IDENT_N; ++i) host[(size_t)i * IDENT_N + i] = __float2half(1.0f);
     void* ptr = nullptr;
-    if (cudaMalloc(&ptr, 256 * 256 * sizeof(__half)) == cudaSuccess &&
-        cudaMemcpy(ptr, host, 256 * 256 * sizeof(__half), cudaMemcpyHostToDevice) == cudaSuccess)
+    if (cudaMalloc(&ptr, (size_t)IDENT_N * IDENT_N * sizeof(__half)) == cudaSuccess &&
+        cudaMemcpy(ptr, host, (size_t)IDENT_N * IDENT_N * sizeof(__half), cudaMemcpyHostToDevice) == cudaSuccess)
       dev_ptr[dev] = ptr;
     free(host);
   }
@@ -742,17 +756,27 @@ static bool tma_ok_out_aligned(const ldx_gemm_desc_t* d) {
          d->o_sy % 4 == 0 && d->o_sb % 4 == 0 && d->o_sx > 0;
 }
 
-// Tile configuration: N tile width and 1-CTA vs CTA-pair kernel.  Cost model per 16-wide K step and per
-// SM: tensor pipe bn/2 cycles vs operand fetch (L2 -> smem) of (128 + bn/ctas) rows x 32 bytes at an
-// effective ~61 B/clk/SM (calibrated on B200: the 1-CTA 128x256 tile runs at ~0.64 of the MMA rate).
-static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas, int* bn_out, int* ctas_out) {
+// Tile configuration: N tile width, 1-CTA vs CTA-pair kernel, one or two accumulators per tile.  Cost model per
+// SM in tensor-pipe clocks: per 16-wide K step the tensor pipe needs bn/2 cycles and the operand fetch (L2 -> smem)
+// (128 + bn/ctas) rows x 32 bytes at an effective ~61 B/clk/SM (calibrated on B200: the 1-CTA 128x256 tile runs at
+// ~0.64 of the MMA rate); a tile costs nk16 such steps, and a CTA runs ceil(tiles / workers) tiles back to back.
+// Two-accumulator tiles (CTA pairs, bn in {320, ..., 512} = 2 x bn/2 columns sharing every A stage) exist for the
+// wave count: N = 1280 at M = 4096 is 80 pair tiles of 256 x 256 on 74 CTA pairs -- two waves, the second 8 % full
+// -- but 64 tiles of 256 x 320, ONE wave.  They fill TMEM, so their accumulator is single buffered and the epilogue
+// of a tile (~7 clocks per column) is exposed instead of hidden behind the next tile's main loop.
+static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas, int nk16, bool allow_dual, int* bn_out,
+                          int* ctas_out, int* nsub_out) {
   const bool geglu = (flags & LDX_EPI_GEGLU) != 0;
   double best_cost = 1e30;
   *bn_out = 128;
   *ctas_out = 1;
+  *nsub_out = 1;
+  if (nk16 < 1) nk16 = 1;
   for (int ctas = 1; ctas <= 2; ++ctas) {
     if (force_ctas && ctas != force_ctas) continue;
-    for (int bn = 256; bn >= 32; bn -= 32) {
+    for (int bn = (ctas == 2 && allow_dual) ? 512 : 256; bn >= 32; bn -= 32) {
+      const int nsub = bn > 256 ? 2 : 1;
+      if (nsub == 2 && (bn % 64 || geglu)) continue;          // each accumulator is a multiple of 32 columns wide
       if (geglu && bn % 64) continue;
       if (ctas == 2 && bn < 64) continue;
       const long long n_tiles = (N + bn - 1) / bn;
@@ -761,11 +785,13 @@ static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas
       const double waves = (double)((tiles + workers - 1) / workers);
       const double mma = bn / 2.0, fetch = (128 + bn / (double)ctas) * 0.52;
       const double per_k = mma > fetch ? mma : fetch;
-      const double cost = waves * (per_k + 6.0);
+      double cost = waves * (per_k + 6.0) * nk16;
+      if (nsub == 2) cost = cost * 1.03 + waves * bn * 7.0;   // exposed epilogue; keep single-accumulator tiles on ties
       if (cost < best_cost - 1e-9) {
         best_cost = cost;
         *bn_out = bn;
         *ctas_out = ctas;
+        *nsub_out = nsub;
       }
     }
   }
@@ -840,19 +866,25 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   }
   if (nsplit > 1) { tma_ok = false; fuse_res = false; }
   g->nsplit = nsplit;
-  int bn = d->bn, ctas = 1;
+  int bn = d->bn, ctas = 1, nsub = 1;
+  static int dual_env = -1;
+  if (dual_env < 0) { const char* e = getenv("LDX_GEMM_DUAL"); dual_env = e ? atoi(e) : 1; }
+  // K steps of 16 per tile, as the kernel will run them (the fused residual adds ~bn / 64 identity steps of 64)
+  const int nk16 = 4 * (k_chunks + (d->residual ? 4 : 0));
   if (nsplit > 1) {
     bn = 256;
     ctas = 2;
   } else if (bn == 0) {
-    choose_config(d->N, m_tiles, d->flags, sms, force_ctas, &bn, &ctas);
+    // two-accumulator tiles need the TMA-store epilogue (fp16 output): the direct-store path walks 32-column chunks
+    choose_config(d->N, m_tiles, d->flags, sms, force_ctas, nk16, dual_env != 0 && tma_ok, &bn, &ctas, &nsub);
   } else {
-    int bn_unused;
-    choose_config(d->N, m_tiles, d->flags, sms, force_ctas, &bn_unused, &ctas);
+    int bn_unused, nsub_unused;
+    choose_config(d->N, m_tiles, d->flags, sms, force_ctas, nk16, false, &bn_unused, &ctas, &nsub_unused);
     if (ctas == 2 && bn < 64) ctas = 1;
   }
   g->ctas = ctas;
-  LDX_CHECK_ARG(bn >= 32 && bn <= 256 && bn % 32 == 0, "bn %d must be a multiple of 32 in [32,256]", bn);
+  LDX_CHECK_ARG(bn >= 32 && bn <= (nsub == 2 ? 512 : 256) && bn % 32 == 0, "bn %d must be a multiple of 32 in [32,256]", bn);
+  LDX_CHECK_ARG(nsub == 1 || (ctas == 2 && bn % 64 == 0), "two-accumulator tiles need a CTA pair and bn %% 64 == 0");
   if (d->flags & LDX_EPI_GEGLU) {
     LDX_CHECK_ARG(bn % 64 == 0 && d->N % bn == 0, "GEGLU needs bn %% 64 == 0 and N %% bn == 0 (N=%d bn=%d)", d->N, bn);
     LDX_CHECK_ARG(!d->residual && !d->rowadd, "GEGLU epilogue does not take residual/rowadd");
@@ -868,8 +900,10 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.inv_n_tiles = inv32(p.n_tiles);
   p.inv_tiles_x = inv32(p.tiles_x);
   p.inv_tiles_xy = inv32(p.tiles_x * p.tiles_y);
+  p.nsub = nsub;
+  p.single_acc = nsub == 2 ? 1 : 0;
   p.acc_stride = (uint32_t)pow2_ceil(bn < 32 ? 32 : bn);
-  p.tmem_cols = 2 * p.acc_stride;
+  p.tmem_cols = p.single_acc ? (uint32_t)pow2_ceil(bn) : 2 * p.acc_stride;
 
   int nk = 0;
   for (int s = 0; s < d->nseg; ++s) {
@@ -930,16 +964,16 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     if (rc) return rc;
     const void* ident = identity256();
     LDX_CHECK_ARG(ident != nullptr, "identity matrix allocation failed");
-    const uint64_t idims[2] = {256, 256};
-    const uint64_t istr[1] = {256 * 2};
-    const uint32_t ibox[2] = {(uint32_t)BK, (uint32_t)(bn / ctas)};
+    const uint64_t idims[2] = {IDENT_N, IDENT_N};
+    const uint64_t istr[1] = {IDENT_N * 2};
+    const uint32_t ibox[2] = {(uint32_t)BK, (uint32_t)(bn / (ctas * nsub))};
     rc = encode_map_f16(&p.idmap, ident, 2, idims, istr, ibox);
     if (rc) return rc;
   }
   {
     const uint64_t dims[2] = {(uint64_t)k_weights * BK, (uint64_t)d->N};
     const uint64_t str[1] = {(uint64_t)d->ldw * 2};
-    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(bn / ctas)};
+    const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(bn / (ctas * nsub))};
     int rc = encode_map_f16(&p.bmap, d->w, 2, dims, str, box);
     if (rc) return rc;
   }

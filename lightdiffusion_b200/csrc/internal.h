@@ -109,6 +109,9 @@ struct alignas(64) GemmKParams {
   int32_t nsplit, base_tiles, ksplit;
   int64_t split_stride;   // ceil(2^32 / d): tile index -> coordinates without integer division
   int32_t bn, stages;
+  // nsub = 2: the N tile is two bn / 2 wide accumulators fed by the same A stage (bn up to 512, CTA pairs only);
+  // they fill TMEM, so the accumulator is single buffered (single_acc) and the epilogue is not overlapped
+  int32_t nsub, single_acc;
   uint32_t tmem_cols, acc_stride;
   void* out;
   int64_t o_sx, o_sy, o_sb, o_off;

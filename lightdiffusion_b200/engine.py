@@ -45,6 +45,9 @@ SHARE_CFG_PREFIX = os.environ.get("LDX_SHARE_CFG_PREFIX", "1") == "1"
 # A plan owns its activation pool (~0.5 GB for the SD1.5 UNet at B = 16) and a CUDA graph; an engine keeps the most
 # recently used MAX_PLANS of them (an img2img flow over varied tile sizes would otherwise exhaust HBM).
 MAX_PLANS = int(os.environ.get("LDX_MAX_PLANS", "4"))
+# Convolutions with <= 5 output channels (UNet out 320 -> 4, VAE conv_out 128 -> 3) run on the dedicated
+# one-read kernel (ldx_conv3x3_small); LDX_CONV_SMALL=0 sends them through the implicit-GEMM kernel (A/B).
+CONV_SMALL = os.environ.get("LDX_CONV_SMALL", "1") == "1"
 
 
 class _PlanCache:
@@ -149,6 +152,8 @@ class UNetEngine:
         self.kv_total = kvo
         w["out.g"], w["out.beta"] = _f32(sd, "out.0.weight", dev), _f32(sd, "out.0.bias", dev)
         w["out.w"], w["out.b"] = K.pack_conv3x3(sd["out.2.weight"]), _f32(sd, "out.2.bias", dev)
+        if CONV_SMALL and sd["out.2.weight"].shape[0] <= 5:
+            w["out.ws"] = K.pack_conv3x3_small(sd["out.2.weight"])
         torch.cuda.synchronize()
 
     @staticmethod
@@ -474,7 +479,10 @@ class UNetPlan:
             h = nh
         y = self._gn(h, None, w["out.g"], w["out.beta"], 1e-5, True)
         self.eps_buf = torch.zeros(B, H, W, 8, dtype=F16, device=eng.dev)
-        prog.add(K.conv3x3_desc(y, w["out.w"], self.eps_buf[..., :cfg.out_channels], bias=w["out.b"]))
+        if "out.ws" in w:
+            prog.add(K.conv3x3_small_op(y, w["out.ws"], w["out.b"], cfg.out_channels, out16=self.eps_buf))
+        else:
+            prog.add(K.conv3x3_desc(y, w["out.w"], self.eps_buf[..., :cfg.out_channels], bias=w["out.b"]))
         if not self.cfg_pairs:
             prog.add(K.generic_op(L.OP_EPS_TO_DENOISED,
                                   p=[self.eps_buf.data_ptr(), self.x_in.data_ptr(), self.sigma_in.data_ptr(),
@@ -562,6 +570,8 @@ class VAEDecoderEngine:
                 w[n + ".w"], w[n + ".b"] = K.pack_upconv3x3(sd[n + ".weight"]), _f32(sd, n + ".bias", dev)
         w["nout.g"], w["nout.b"] = _f32(sd, "decoder.norm_out.weight", dev), _f32(sd, "decoder.norm_out.bias", dev)
         w["cout.w"], w["cout.b"] = K.pack_conv3x3(sd["decoder.conv_out.weight"]), _f32(sd, "decoder.conv_out.bias", dev)
+        if CONV_SMALL and sd["decoder.conv_out.weight"].shape[0] <= 5:
+            w["cout.ws"] = K.pack_conv3x3_small(sd["decoder.conv_out.weight"])
         torch.cuda.synchronize()
 
     def _pack_res(self, sd, p):
@@ -641,9 +651,15 @@ class VAEPlan:
         y = pool.alloc(Bn, hh, ww, c)
         prog.add(K.group_norm_op(h, None, w["nout.g"], w["nout.b"], y, self.stats, 1e-6, True))
         self.dec_buf = torch.zeros(Bn, hh, ww, 8, dtype=F16, device=dev)
-        prog.add(K.conv3x3_desc(y, w["cout.w"], self.dec_buf[..., :cfg.out_ch], bias=w["cout.b"]))
-        prog.add(K.generic_op(L.OP_VAE_POST, p=[self.dec_buf.data_ptr(), self.img.data_ptr()],
-                              l=[8, Bn * hh * ww]))
+        if "cout.ws" in w and cfg.out_ch == 3:
+            # conv_out and VAE.process_output in one launch: the 128-channel map is read once, the fp16 result
+            # (decode_raw / decode_u8) and the clamped fp32 image are both written from the epilogue
+            prog.add(K.conv3x3_small_op(y, w["cout.ws"], w["cout.b"], cfg.out_ch, out16=self.dec_buf, out_img=self.img,
+                                        post=1))
+        else:
+            prog.add(K.conv3x3_desc(y, w["cout.w"], self.dec_buf[..., :cfg.out_ch], bias=w["cout.b"]))
+            prog.add(K.generic_op(L.OP_VAE_POST, p=[self.dec_buf.data_ptr(), self.img.data_ptr()],
+                                  l=[8, Bn * hh * ww]))
         self.graph = None
         self.use_graph = True
 

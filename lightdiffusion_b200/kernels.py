@@ -226,6 +226,37 @@ def pack_upconv3x3(w_oihw: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def pack_conv3x3_small(w_oihw: torch.Tensor) -> torch.Tensor:
+    """[Cout <= 5, Cin, 3, 3] -> the [ceil16(9 * Cout), ceil64(Cin)] per-tap weight matrix of ldx_conv3x3_small."""
+    cout, cin = w_oihw.shape[:2]
+    n = L.lib().ldx_conv3x3_small_packed_elems(cout, cin)
+    if n < 0:
+        raise L.LdxError(f"conv3x3_small: Cout {cout} unsupported")
+    w16 = _dev16(w_oihw)
+    out = torch.empty(n // ceil64(cin), ceil64(cin), dtype=torch.float16, device="cuda")
+    L.check(L.lib().ldx_pack_conv3x3_small(w16.data_ptr(), out.data_ptr(), cout, cin, _stream()), "ldx_pack_conv3x3_small")
+    return out
+
+
+def conv3x3_small_op(x: torch.Tensor, wp: torch.Tensor, bias: Optional[torch.Tensor], cout: int,
+                     out16: Optional[torch.Tensor] = None, out_img: Optional[torch.Tensor] = None,
+                     post: int = 0) -> L.GenericOp:
+    """x [B,H,W,Cin] fp16 (pixel-contiguous, channel pitch free) -> out16 [B,H,W,>=cout] fp16 and / or out_img
+    [B,H,W,cout] fp32 (post = 1: clamp((v + 1) / 2, 0, 1), the VAE's process_output)."""
+    _check_act(x)
+    b, h, w, cin = x.shape
+    assert x.stride(1) == x.stride(2) * w and x.stride(0) == x.stride(1) * h, "input must be pixel-contiguous"
+    if out16 is not None:
+        assert out16.dtype == torch.float16 and out16.stride(-1) == 1 and out16.shape[:3] == x.shape[:3]
+        assert out16.stride(1) == out16.stride(2) * w and out16.stride(0) == out16.stride(1) * h
+    if out_img is not None:
+        assert out_img.dtype == torch.float32 and out_img.is_contiguous() and tuple(out_img.shape) == (b, h, w, cout)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() == cout
+    return generic_op(L.OP_CONV_SMALL, p=[x.data_ptr(), wp.data_ptr(), _ptr(bias), _ptr(out16), _ptr(out_img)],
+                      i=[b, h, w, cin, cout, post], l=[x.stride(2), 0 if out16 is None else out16.stride(2)])
+
+
 def pack_linear(w: torch.Tensor) -> torch.Tensor:
     """[N, K] (or 1x1 conv [N, K, 1, 1]) -> fp16 [N, ceil64(K)] (zero padded)."""
     w2 = w.detach().reshape(w.shape[0], -1).to(torch.float16)
@@ -322,12 +353,16 @@ class Program:
             if op.kind == L.OP_ATTENTION:
                 b, nq, nk, heads, d = (op.i[j] for j in range(5))
                 flops, tag = 4.0 * b * nq * nk * heads * d, (b, nq, nk, heads, d)
+            elif op.kind == L.OP_CONV_SMALL:
+                b, h, w, cin, cout = (op.i[j] for j in range(5))
+                flops, tag = 2.0 * b * h * w * 9 * cin * cout, (b * h * w, cout, 9 * cin)
             elif op.kind == L.OP_GROUP_NORM:
                 tag = (op.i[2], op.i[3], op.i[0] + op.i[1])         # B, HW, C
             elif op.kind == L.OP_LAYER_NORM:
                 tag = (op.i[0], op.i[1])                            # rows, C
             self.meta.append(({L.OP_ATTENTION: "attention", L.OP_GROUP_NORM: "group_norm",
-                               L.OP_LAYER_NORM: "layer_norm"}.get(op.kind, "other"), flops, tag))
+                               L.OP_LAYER_NORM: "layer_norm", L.OP_CONV_SMALL: "conv_small"}.get(op.kind, "other"),
+                              flops, tag))
         self._keep.extend(keep)
 
     def keep(self, *tensors):

@@ -177,12 +177,20 @@ def test_seam3_reference_ksampler_calls_ldx_sampler(env, recorded, monkeypatch):
         seen.append(k.get("eta"))
         return S.sample_dpmpp_2m_sde(*a, **k)
 
+    # one step first: both runs evaluate the reference UNet on bit-identical inputs, so the outputs differ only by
+    # the update arithmetic (host fp32 coefficients + one fused kernel vs the reference's 0-d CUDA tensor math)
+    sig1 = env["sigmas"][:2]
+    z1_ref = env["run"](env["patcher"], pos, neg, sig1)
     monkeypatch.setattr(R, "sample_dpmpp_2m_sde", spy)
+    z1 = env["run"](env["patcher"], pos, neg, sig1)
     z = env["run"](env["patcher"], pos, neg)
-    assert seen == [0.0]
-    r = rel(z, z_ref)
-    print(f"reference UNet + ldx DPM++ 2M update: final latent {r:.2e}")
-    assert r < 1e-4, r                                      # same fp16 UNet; only the fp32 update arithmetic differs
+    assert seen == [0.0, 0.0]
+    r1, r = rel(z1, z1_ref), rel(z, z_ref)
+    print(f"reference UNet + ldx DPM++ 2M update: after 1 step {r1:.2e}, final latent after {STEPS} steps {r:.2e}")
+    assert r1 < 1e-5, r1
+    # over several steps a 1-ulp difference in x re-rolls the fp16 roundings inside the reference's UNet (its own
+    # noise floor, ~1e-3 per evaluation), so the trajectories agree to the same bound as the other seams
+    assert r < 2e-2, r
 
 
 def test_seams_1_2_reference_unet_built_from_ldx_ops(env, recorded, monkeypatch):

@@ -465,3 +465,63 @@ def test_errors_are_loud():
     q = h16(rnd(1, 64, 8 * 24, seed=82))   # head dim 24 unsupported
     with pytest.raises(L.LdxError):
         K.run_op(K.attention_op(q, q, q, torch.empty_like(q), 8))
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout,pitch", [(2, 40, 24, 128, 3, 128), (3, 64, 64, 320, 4, 320), (1, 8, 8, 64, 1, 64),
+                                                   (2, 17, 29, 72, 5, 80), (1, 14, 14, 64, 3, 64), (1, 15, 43, 128, 2, 136)])
+def test_conv3x3_small_matches_conv2d(B, H, W, cin, cout, pitch):
+    """ldx_conv3x3_small (VAE conv_out 128 -> 3, UNet out 320 -> 4): every input pixel read once, 9 * Cout per-tap
+    partials on the tensor core, taps gathered in the epilogue.  Tile edges (14 x 14 interiors), ragged sizes, a
+    channel pitch wider than Cin and a channel count off the 64 grid are covered; both outputs are checked."""
+    g = torch.Generator().manual_seed(77 + H)
+    buf = torch.randn(B, H, W, pitch, generator=g).half().to(DEV)
+    x = buf[..., :cin]
+    w = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).half().to(DEV)
+    bias = (0.1 * torch.randn(cout, generator=g)).to(DEV)
+    out16 = torch.zeros(B, H, W, 8, dtype=torch.float16, device=DEV)
+    img = torch.zeros(B, H, W, cout, dtype=torch.float32, device=DEV)
+    K.run_op(K.conv3x3_small_op(x, K.pack_conv3x3_small(w), bias, cout, out16=out16, out_img=img, post=1))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert rel(out16[..., :cout], ref) < 1e-3
+    assert float(out16[..., cout:].abs().max()) == 0.0                # channels past Cout are not touched
+    assert torch.equal(img, ((out16[..., :cout].float() + 1) / 2).clamp(0, 1))
+    img2 = torch.zeros_like(img)
+    K.run_op(K.conv3x3_small_op(x, K.pack_conv3x3_small(w), None, cout, out_img=img2))       # no bias, raw fp32 output
+    assert rel(img2, F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, padding=1).permute(0, 2, 3, 1)) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,Kd,res", [(4096, 1280, 1280, True), (4096, 1280, 5120, False), (2048 * 8, 640, 2560, False),
+                                        (4096, 1000, 1280, True), (4096 + 128, 1280, 2560, True), (32768, 320, 2880, False)])
+def test_linear_two_accumulator_tiles(M, N, Kd, res):
+    """N tiles wider than one 256-column accumulator (256 x 320 ... 256 x 512 pair tiles = two tcgen05 accumulators
+    sharing every A stage, single-buffered TMEM): chosen by the cost model where it saves a wave (N = 1280 at
+    M = 4096: 64 tiles on 74 CTA pairs instead of 128).  Ragged N / M and the fused-residual identity steps included."""
+    a, w = h16(rnd(M, Kd, seed=51)), h16(rnd(N, Kd, seed=52, scale=Kd ** -0.5))
+    bias = rnd(N, seed=53)
+    r = h16(rnd(M, N, seed=54)) if res else None
+    out = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    d = K.linear_desc(a, w, out, bias=bias, residual=r)
+    import os
+    if os.environ.get("LDX_GEMM_DUAL", "1") != "0":
+        n_tiles = K.rowstats_parts(d) // 2
+        assert -(-N // n_tiles) > 256, (N, n_tiles)          # the wide-tile path is what this test runs
+    K.run_gemm(d)
+    ref = a.float() @ w.float().t() + bias + (r.float() if res else 0)
+    assert rel(out, ref) < 1e-3, (M, N, Kd, rel(out, ref))
+    st = K.attach_rowstats(d, M)                             # row statistics out of a wide tile (LayerNorm folding)
+    K.run_gemm(d)
+    s = st.sum(1)
+    o32 = out.float()
+    assert rel(s[:, 0], o32.sum(1)) < 1e-3 and rel(s[:, 1], (o32 * o32).sum(1)) < 1e-3
+
+
+def test_conv3x3_two_accumulator_tiles():
+    """3x3 conv 320 -> 320 on a 16 x 64 x 64 map (M = 65536, K = 2880) with the timestep row add: 256 x 320 tiles."""
+    B, H, W, C = 16, 64, 64, 320
+    x = h16(rnd(B, H, W, C, seed=61))
+    w = h16(rnd(C, C, 3, 3, seed=62, scale=(9 * C) ** -0.5))
+    bias, emb = rnd(C, seed=63), rnd(B, C, seed=64)
+    out = torch.empty(B, H, W, C, dtype=torch.float16, device=DEV)
+    K.run_gemm(K.conv3x3_desc(x, K.pack_conv3x3(w), out, bias=bias, rowadd=emb))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + emb[:, :, None, None]
+    assert rel(out.permute(0, 3, 1, 2), ref) < 1e-3
