@@ -99,6 +99,13 @@ typedef struct {
   float ln_eps;             /* LDX_EPI_ROWNORM: LayerNorm eps */
   const float* ln_gsum;     /* LDX_EPI_ROWNORM: [N] fp32 (packed like the bias for LDX_EPI_GEGLU) */
   int32_t ln_c;             /* LDX_EPI_ROWNORM: normalised width C (the A row length before K padding) */
+  float* colstats_out;      /* NULL, or [B, colstats_slots, N, 2] fp32: for every 32-row block ("slot") of a batch
+                               element and every output column the (sum, sum of squares) of the fp16 outputs, taken
+                               from the epilogue's staging tile.  ldx_group_norm_cs reduces them to GroupNorm
+                               statistics, so the normalisation needs no statistics pass over the tensor.  TMA-store
+                               epilogue only (fp16 output), not with split-K / GEGLU; see ldx_gemm_colstats_slots */
+  int32_t colstats_slots;   /* slots per batch element in the buffer */
+  int32_t colstats_slot_base; /* first slot this launch writes (the four phase GEMMs of an upsample conv share one) */
   int32_t rowstats_out_parts; /* 0 = unchecked; else the [rows, parts, 2] extent of rowstats_out: the launch is
                                rejected unless it equals ldx_gemm_rowstats_parts(d) */
 } ldx_gemm_desc_t;
@@ -107,6 +114,10 @@ int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream);
 /* Number of column parts the GEMM described by d writes per row into rowstats_out (depends on the tile
  * configuration the library picks for d); < 0 on error. */
 int ldx_gemm_rowstats_parts(const ldx_gemm_desc_t* d);
+/* Number of 32-row slots per batch element the GEMM described by d writes into colstats_out (depends on the tile
+ * geometry), or -1 when this launch cannot produce column statistics (direct-store epilogue, split-K, maps with
+ * fewer than 32 pixels per batch element). */
+int ldx_gemm_colstats_slots(const ldx_gemm_desc_t* d);
 
 /* One-time weight layout transforms (ldx_pack_weights_* of SURVEY.md §8b). */
 /* torch conv weight [Cout, Cin, 3, 3] fp16 -> [Cout, 9 * ceil64(Cin)] fp16 (tap-major, zero padded). */
@@ -144,6 +155,14 @@ int ldx_pack_geglu(const void* w, const float* bias, void* w_packed, float* bias
 int ldx_group_norm(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1,
                    int B, int HW, float eps, const float* gamma, const float* beta, int silu,
                    void* y, int64_t ldy, float* stats, ldx_stream_t stream);
+/* The same normalisation with the statistics taken from the column partials the producing GEMM(s) wrote
+ * (ldx_gemm_desc_t.colstats_out, [B, slots, C, 2] per source): a reduction over B * slots * C pairs replaces the
+ * statistics pass over the tensor, so GroupNorm moves its algorithmic bytes (one read, one write).  Maps small enough
+ * for the single-launch path ignore the partials. */
+int ldx_group_norm_cs(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1, int B, int HW,
+                      float eps, const float* gamma, const float* beta, int silu, void* y, int64_t ldy,
+                      float* stats, const float* colstats0, int slots0, const float* colstats1, int slots1,
+                      ldx_stream_t stream);
 /* LayerNorm over the last dim (F.layer_norm, LD.py:2403), eps 1e-5, fp16 in/out. */
 int ldx_layer_norm(const void* x, int64_t ldx_, int rows, int C, float eps, const float* gamma,
                    const float* beta, void* y, int64_t ldy, ldx_stream_t stream);

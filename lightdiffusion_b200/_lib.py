@@ -52,7 +52,9 @@ class GemmDesc(C.Structure):
                 ("residual", C.c_void_p), ("ldr", C.c_int64),
                 ("flags", C.c_int32), ("bn", C.c_int32),
                 ("rowstats_out", C.c_void_p), ("rowstats_in", C.c_void_p), ("rowstats_in_parts", C.c_int32),
-                ("ln_eps", C.c_float), ("ln_gsum", C.c_void_p), ("ln_c", C.c_int32), ("rowstats_out_parts", C.c_int32)]
+                ("ln_eps", C.c_float), ("ln_gsum", C.c_void_p), ("ln_c", C.c_int32),
+                ("colstats_out", C.c_void_p), ("colstats_slots", C.c_int32), ("colstats_slot_base", C.c_int32),
+                ("rowstats_out_parts", C.c_int32)]
 
 
 class GenericOp(C.Structure):
@@ -69,6 +71,7 @@ _SIGS = {
     "ldx_device_check": (C.c_int, []),
     "ldx_gemm": (C.c_int, [C.POINTER(GemmDesc), C.c_void_p]),
     "ldx_gemm_rowstats_parts": (C.c_int, [C.POINTER(GemmDesc)]),
+    "ldx_gemm_colstats_slots": (C.c_int, [C.POINTER(GemmDesc)]),
     "ldx_pack_conv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldx_pack_upconv3x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ldx_conv3x3_small": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
@@ -79,6 +82,9 @@ _SIGS = {
     "ldx_group_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int,
                                  C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                                  C.c_void_p]),
+    "ldx_group_norm_cs": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "ldx_layer_norm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int64, C.c_void_p]),
     "ldx_attention": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

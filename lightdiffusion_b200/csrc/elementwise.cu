@@ -257,6 +257,55 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const GnArgs a) {
   }
 }
 
+// GroupNorm statistics from the column partials the producing GEMMs left behind (ldx_gemm_desc_t.colstats_out):
+// one CTA per (group, batch element) sums its channels' (sum, sum of squares) over all 32-row slots in a fixed
+// order, in double, and writes the totals where gn_apply_kernel expects ONE slab of partials.  The tensor itself
+// is not read: bytes = B * slots * C * 8 (1/8 of the fp16 map at 32 rows per slot).
+// The channel concat [x0 | x1] of the UNet's skip connections has one partial buffer per source.
+struct GnCsArgs {
+  const float* cs0; const float* cs1;
+  int c0, c1, slots0, slots1, cpg;
+  float* partial;   // [B][1][32][2]
+};
+
+__global__ void __launch_bounds__(128) gn_colstats_finalize_kernel(const GnCsArgs a) {
+  __shared__ double sh[2][128];
+  pdl_prologue();
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int lo = g * a.cpg, hi = lo + a.cpg;
+  double s = 0.0, ss = 0.0;
+#pragma unroll
+  for (int src = 0; src < 2; ++src) {
+    const float* cs = src ? a.cs1 : a.cs0;
+    const int cw = src ? a.c1 : a.c0, slots = src ? a.slots1 : a.slots0, off = src ? a.c0 : 0;
+    if (!cs) continue;
+    const int clo = max(lo, off) - off, chi = min(hi, off + cw) - off;
+    const int n = chi - clo;
+    if (n <= 0) continue;
+    const float2* base = reinterpret_cast<const float2*>(cs) + (int64_t)b * slots * cw;
+    for (int i = threadIdx.x; i < slots * n; i += 128) {
+      const int slot = i / n, c = clo + i % n;
+      const float2 v = __ldg(base + (int64_t)slot * cw + c);
+      s += (double)v.x;
+      ss += (double)v.y;
+    }
+  }
+  sh[0][threadIdx.x] = s;
+  sh[1][threadIdx.x] = ss;
+  __syncthreads();
+  for (int w = 64; w > 0; w >>= 1) {
+    if (threadIdx.x < w) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + w];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.partial[((size_t)b * 32 + g) * 2 + 0] = (float)sh[0][0];
+    a.partial[((size_t)b * 32 + g) * 2 + 1] = (float)sh[1][0];
+  }
+}
+
 int group_norm_num_launches(int C, int HW) {
   const int cpg = C / 32;
   return (cpg % 8 == 0 && (int64_t)HW * (cpg / 8) <= 256 * GN_SMALL_VPT) ? 1 : 2;
@@ -264,7 +313,8 @@ int group_norm_num_launches(int C, int HW) {
 
 static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1, int B, int HW,
                            float eps, const float* gamma, const float* beta, int silu, void* y, int64_t ldy,
-                           float* stats, cudaStream_t stream) {
+                           float* stats, cudaStream_t stream, const float* cs0 = nullptr, int slots0 = 0,
+                           const float* cs1 = nullptr, int slots1 = 0) {
   const int C = c0 + (x1 ? c1 : 0);
   LDX_CHECK_ARG(x0 && y && stats && gamma && beta, "group_norm: null pointer");
   LDX_CHECK_ARG(C % 32 == 0 && c0 % 8 == 0 && C % 8 == 0, "group_norm: C=%d (c0=%d) must be a multiple of 32 / 8", C, c0);
@@ -305,12 +355,23 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
   a.pix_per_slab = pps; a.nslab = nslab;
   a.eps = eps; a.silu = silu; a.gamma = gamma; a.beta = beta;
   a.y = (__half*)y; a.ldy = ldy; a.partial = stats;
-  const size_t smem = (size_t)a.P * C * 2 * sizeof(float);
-  static std::atomic<uint64_t> attr_done{0};
-  int arc = set_max_dyn_smem_once(gn_stats_kernel, 128 * 1024, attr_done);
-  if (arc) return arc;
-  LDX_CHECK_ARG(smem <= 128 * 1024, "group_norm: smem");
-  LDX_CUDA(launch_k(gn_stats_kernel, dim3(B, nslab), dim3(threads), smem, stream, 1, a));
+  if (cs0 && (!x1 || cs1)) {
+    // statistics from the producers' column partials: a reduction over B * slots * C pairs instead of a pass over x
+    LDX_CHECK_ARG(slots0 >= 1 && (!x1 || slots1 >= 1), "group_norm: colstats slots");
+    GnCsArgs f;
+    f.cs0 = cs0; f.cs1 = x1 ? cs1 : nullptr;
+    f.c0 = c0; f.c1 = x1 ? c1 : 0; f.slots0 = slots0; f.slots1 = slots1; f.cpg = a.cpg;
+    f.partial = stats;
+    a.nslab = 1;
+    LDX_CUDA(launch_k(gn_colstats_finalize_kernel, dim3(32, B), dim3(128), 0, stream, 1, f));
+  } else {
+    const size_t smem = (size_t)a.P * C * 2 * sizeof(float);
+    static std::atomic<uint64_t> attr_done{0};
+    int arc = set_max_dyn_smem_once(gn_stats_kernel, 128 * 1024, attr_done);
+    if (arc) return arc;
+    LDX_CHECK_ARG(smem <= 128 * 1024, "group_norm: smem");
+    LDX_CUDA(launch_k(gn_stats_kernel, dim3(B, nslab), dim3(threads), smem, stream, 1, a));
+  }
   // apply: more slabs for bandwidth
   int occ2 = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, gn_apply_kernel, threads, 0) != cudaSuccess || occ2 < 1) occ2 = 4;
@@ -848,9 +909,11 @@ int run_generic_op(const ldx_generic_op_t* op, cudaStream_t st) {
   const void* const* p = op->p;
   switch (op->kind) {
     case LDX_OP_GROUP_NORM:
-      // p: x0, x1, gamma, beta, y, stats ; i: c0, c1, B, HW, silu ; l: ld0, ld1, ldy ; f: eps
+      // p: x0, x1, gamma, beta, y, stats, colstats0, colstats1 ; i: c0, c1, B, HW, silu, slots0, slots1 ;
+      // l: ld0, ld1, ldy ; f: eps
       return group_norm_impl(p[0], i[0], l[0], p[1], i[1], l[1], i[2], i[3], f[0], (const float*)p[2],
-                             (const float*)p[3], i[4], (void*)p[4], l[2], (float*)p[5], st);
+                             (const float*)p[3], i[4], (void*)p[4], l[2], (float*)p[5], st, (const float*)p[6], i[5],
+                             (const float*)p[7], i[6]);
     case LDX_OP_LAYER_NORM:
       // p: x, gamma, beta, y ; i: rows, C ; l: ldx, ldy ; f: eps
       return layer_norm_impl(p[0], l[0], i[0], i[1], f[0], (const float*)p[1], (const float*)p[2], (void*)p[3], l[1], st);
@@ -949,6 +1012,15 @@ extern "C" int ldx_group_norm(const void* x0, int c0, int64_t ld0, const void* x
                               float eps, const float* gamma, const float* beta, int silu, void* y, int64_t ldy,
                               float* stats, ldx_stream_t stream) {
   return group_norm_impl(x0, c0, ld0, x1, c1, ld1, B, HW, eps, gamma, beta, silu, y, ldy, stats, as_stream(stream));
+}
+
+extern "C" int ldx_group_norm_cs(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1, int B, int HW,
+                                 float eps, const float* gamma, const float* beta, int silu, void* y, int64_t ldy,
+                                 float* stats, const float* colstats0, int slots0, const float* colstats1, int slots1,
+                                 ldx_stream_t stream) {
+  LDX_CHECK_ARG(colstats0 && slots0 >= 1 && (!x1 || (colstats1 && slots1 >= 1)), "group_norm_cs: missing column statistics");
+  return group_norm_impl(x0, c0, ld0, x1, c1, ld1, B, HW, eps, gamma, beta, silu, y, ldy, stats, as_stream(stream),
+                         colstats0, slots0, colstats1, slots1);
 }
 
 extern "C" int ldx_layer_norm(const void* x, int64_t ldx_, int rows, int C, float eps, const float* gamma,

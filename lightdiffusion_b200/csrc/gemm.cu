@@ -182,7 +182,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, uint32_t tm
 // kEpi: epilogue features compiled in (bit 0 GEGLU, bit 1 LayerNorm-folded input rows, bit 2 row statistics
 // out).  They are template parameters because the epilogue is register-bound: a single kernel carrying every
 // path spilled inside the hot loop and slowed the plain GEMMs too.
-constexpr int KEPI_GEGLU = 1, KEPI_ROWNORM = 2, KEPI_ROWSTATS = 4;
+constexpr int KEPI_GEGLU = 1, KEPI_ROWNORM = 2, KEPI_ROWSTATS = 4, KEPI_COLSTATS = 8;
 template <int kCtas, int kEpi>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
     constexpr bool geglu = (kEpi & KEPI_GEGLU) != 0;
     constexpr bool rownorm = (kEpi & KEPI_ROWNORM) != 0;
     constexpr bool rowstats = (kEpi & KEPI_ROWSTATS) != 0;
+    constexpr bool colstats = (kEpi & KEPI_COLSTATS) != 0;
     const bool f32 = (p.flags & LDX_EPI_OUT_F32) != 0;
     const int n_out_tile = geglu ? p.bn / 2 : p.bn;
     const int n_out_total = geglu ? p.N / 2 : p.N;
@@ -427,6 +428,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
           ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
         }
         float rs1 = 0.f, rs2 = 0.f;             // row statistics of this warp's output columns
+        // column statistics: the warp's 32 rows are one slot of one batch element (gemm_prepare checks bw * bh >= 32)
+        int64_t cs_base = -1;
+        if constexpr (colstats) {
+          const int per = p.bw * p.bh;          // rows of one batch element inside the tile
+          const int cs_b = b0 + (q * 32) / per;
+          const int cs_slot = p.cs_slot_base + (ty * p.tiles_x + tx) * p.cs_wps + ((q * 32) % per) / 32;
+          if (cs_b < p.B) cs_base = ((int64_t)cs_b * p.cs_slots + cs_slot) * p.N;
+        }
         int last_ps = grp;                      // this group's last pass of the tile
         while (last_ps + EPI_GROUPS < npass) last_ps += EPI_GROUPS;
         for (int ps = grp; ps < npass; ps += EPI_GROUPS, ++pidx) {
@@ -542,6 +551,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               o.z = pack_h2(v[ch * 8 + 4], v[ch * 8 + 5]);
               o.w = pack_h2(v[ch * 8 + 6], v[ch * 8 + 7]);
               *reinterpret_cast<uint4*>(srow + (((half * 4 + ch) ^ sw) << 4)) = o;
+            }
+          }
+          if constexpr (colstats) {
+            // per-column (sum, sum of squares) over the warp's 32 staged rows, read back as the fp16 values the
+            // consumer will see; lane l owns columns 2l, 2l + 1 of the pass: one conflict-free 4-byte load per row
+            __syncwarp();
+            const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+            const int col = n_out0 + ps * EPI_PASS + 2 * lane;
+            if (cs_base >= 0 && lane < (wide ? 32 : 16) && col < n_out_total) {
+              const uint32_t chunk = (uint32_t)lane >> 2, off = ((uint32_t)lane & 3u) << 2;
+              float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) {
+                const uint32_t a = wide ? (uint32_t)r * 128u + ((chunk ^ ((uint32_t)r & 7u)) << 4) + off
+                                        : (uint32_t)r * 64u + ((chunk ^ (((uint32_t)r >> 1) & 3u)) << 4) + off;
+                const float2 f = unpack_h2(*reinterpret_cast<const uint32_t*>(cbuf + a));
+                if ((vm >> r) & 1u) {
+                  s0 += f.x; q0 = fmaf(f.x, f.x, q0);
+                  s1 += f.y; q1 = fmaf(f.y, f.y, q1);
+                }
+              }
+              *reinterpret_cast<float4*>(p.colstats_out + (cs_base + col) * 2) = make_float4(s0, q0, s1, q1);
             }
           }
           PH(4)
@@ -763,7 +794,8 @@ static bool tma_ok_out_aligned(const ldx_gemm_desc_t* d) {
 // Two-accumulator tiles (CTA pairs, bn in {320, ..., 512} = 2 x bn/2 columns sharing every A stage) exist for the
 // wave count: N = 1280 at M = 4096 is 80 pair tiles of 256 x 256 on 74 CTA pairs -- two waves, the second 8 % full
 // -- but 64 tiles of 256 x 320, ONE wave.  They fill TMEM, so their accumulator is single buffered and the epilogue
-// of a tile (~7 clocks per column) is exposed instead of hidden behind the next tile's main loop.
+// of a tile (~12 clocks per column, measured: 65536 x 320 x 1280 + residual lost 10 % at 7) is exposed instead of
+// hidden behind the next tile's main loop.
 static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas, int nk16, bool allow_dual, int* bn_out,
                           int* ctas_out, int* nsub_out) {
   const bool geglu = (flags & LDX_EPI_GEGLU) != 0;
@@ -786,7 +818,7 @@ static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas
       const double mma = bn / 2.0, fetch = (128 + bn / (double)ctas) * 0.52;
       const double per_k = mma > fetch ? mma : fetch;
       double cost = waves * (per_k + 6.0) * nk16;
-      if (nsub == 2) cost = cost * 1.03 + waves * bn * 7.0;   // exposed epilogue; keep single-accumulator tiles on ties
+      if (nsub == 2) cost = cost * 1.03 + waves * bn * 12.0;  // exposed epilogue; keep single-accumulator tiles on ties
       if (cost < best_cost - 1e-9) {
         best_cost = cost;
         *bn_out = bn;
@@ -854,7 +886,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     const int pair_tiles = ((m_tiles + 1) / 2) * ((d->N + 255) / 256);
     const int workers2 = sms / 2;
     const bool eligible = split_env && d->bn == 0 && osz == 2 && !(d->flags & (LDX_EPI_GEGLU | LDX_EPI_ROWNORM)) &&
-                          !d->rowstats_out && d->N % 8 == 0 && d->N >= 256 && tma_ok_out_aligned(d) &&
+                          !d->rowstats_out && !d->colstats_out && d->N % 8 == 0 && d->N >= 256 && tma_ok_out_aligned(d) &&
                           (!d->residual || ((reinterpret_cast<uintptr_t>(d->residual) % 8 == 0) && d->ldr % 4 == 0)) &&
                           (!d->bias || reinterpret_cast<uintptr_t>(d->bias) % 16 == 0);
     if (eligible && pair_tiles * 2 <= workers2 && k_chunks >= 160) {   // measured: K = 5120 is faster unsplit
@@ -1062,7 +1094,22 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
       p.bias = zeros_f32(d->N);
       LDX_CHECK_ARG(p.bias != nullptr, "zero bias allocation failed");
     }
+    if (d->colstats_out) {
+      const int per = bw * bh;
+      LDX_CHECK_ARG(per >= 32 && !(d->flags & LDX_EPI_GEGLU) && !d->rowstats_out,
+                    "colstats_out: needs >= 32 pixels per batch element in a tile, no GEGLU, no rowstats_out");
+      p.cs_wps = (per < BM ? per : BM) / 32;
+      const int slots = p.tiles_x * p.tiles_y * p.cs_wps;
+      LDX_CHECK_ARG(d->colstats_slot_base >= 0 && d->colstats_slot_base + slots <= d->colstats_slots,
+                    "colstats_out: slots [%d, %d) do not fit the %d slots of the buffer", d->colstats_slot_base,
+                    d->colstats_slot_base + slots, d->colstats_slots);
+      LDX_CHECK_ARG(reinterpret_cast<uintptr_t>(d->colstats_out) % 16 == 0 && d->N % 2 == 0, "colstats_out: alignment");
+      p.colstats_out = d->colstats_out;
+      p.cs_slots = d->colstats_slots;
+      p.cs_slot_base = d->colstats_slot_base;
+    }
   }
+  LDX_CHECK_ARG(p.tma_epi || !d->colstats_out, "colstats_out needs the TMA-store epilogue (fp16 output, no split-K)");
   LDX_CHECK_ARG(p.tma_epi || (!d->rowstats_out && !(d->flags & LDX_EPI_ROWNORM)),
                 "rowstats_out / LDX_EPI_ROWNORM need the TMA-store epilogue (fp16 output, 16-byte aligned strides)");
   return LDX_OK;
@@ -1081,8 +1128,9 @@ static int gemm_launch_t(const GemmLaunch* g, cudaStream_t stream) {
 template <int kCtas>
 static int gemm_launch_c(const GemmLaunch* g, cudaStream_t stream) {
   const int epi = ((g->p.flags & LDX_EPI_GEGLU) ? KEPI_GEGLU : 0) | ((g->p.flags & LDX_EPI_ROWNORM) ? KEPI_ROWNORM : 0) |
-                  (g->p.rowstats_out ? KEPI_ROWSTATS : 0);
+                  (g->p.rowstats_out ? KEPI_ROWSTATS : 0) | (g->p.colstats_out ? KEPI_COLSTATS : 0);
   switch (epi) {
+    case KEPI_COLSTATS: return gemm_launch_t<kCtas, KEPI_COLSTATS>(g, stream);
     case 0: return gemm_launch_t<kCtas, 0>(g, stream);
     case KEPI_GEGLU: return gemm_launch_t<kCtas, KEPI_GEGLU>(g, stream);
     case KEPI_ROWNORM: return gemm_launch_t<kCtas, KEPI_ROWNORM>(g, stream);
@@ -1186,6 +1234,18 @@ extern "C" int ldx_gemm_rowstats_parts(const ldx_gemm_desc_t* d) {
     return -1;
   }
   return g.p.n_tiles * EPI_GROUPS;
+}
+
+extern "C" int ldx_gemm_colstats_slots(const ldx_gemm_desc_t* d) {
+  GemmLaunch g;
+  if (!d) return -1;
+  ldx_gemm_desc_t q = *d;                      // plan the launch exactly as it will run with colstats_out attached
+  q.colstats_out = reinterpret_cast<float*>(static_cast<uintptr_t>(16));
+  q.colstats_slots = 1 << 30;
+  q.colstats_slot_base = 0;
+  q.rowstats_out = nullptr;
+  if (gemm_prepare(&q, &g) != LDX_OK || !g.p.colstats_out) return -1;
+  return g.p.tiles_x * g.p.tiles_y * g.p.cs_wps;
 }
 
 extern "C" int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream) {

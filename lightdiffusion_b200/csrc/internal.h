@@ -126,6 +126,9 @@ struct alignas(64) GemmKParams {
   const float* ln_gsum;
   int32_t rs_in_parts;
   float ln_eps, ln_inv_c;
+  // GroupNorm statistics of the produced tensor: [B][cs_slots][N][2] per-(32-row block, column) partial sums
+  float* colstats_out;
+  int32_t cs_slots, cs_slot_base, cs_wps;   // cs_wps: 32-row blocks of one batch element inside a 128-row tile
   int32_t vec_ok;   // 16-byte vector epilogue allowed (direct-store path)
   int32_t tma_epi;  // 1: stage 32-column chunks in smem and TMA-store them (fp16 outputs)
 };

@@ -48,6 +48,10 @@ MAX_PLANS = int(os.environ.get("LDX_MAX_PLANS", "4"))
 # Convolutions with <= 5 output channels (UNet out 320 -> 4, VAE conv_out 128 -> 3) run on the dedicated
 # one-read kernel (ldx_conv3x3_small); LDX_CONV_SMALL=0 sends them through the implicit-GEMM kernel (A/B).
 CONV_SMALL = os.environ.get("LDX_CONV_SMALL", "1") == "1"
+# GroupNorm statistics come out of the producing GEMM's epilogue (column partials per 32-row slot) instead of a
+# statistics pass over the tensor; LDX_FUSE_GN_STATS=0 keeps the two-pass GroupNorm everywhere (A/B).
+FUSE_GN_STATS = os.environ.get("LDX_FUSE_GN_STATS", "1") == "1"
+GN_STATS_MIN_HW = 256          # smaller maps take the single-launch GroupNorm, which ignores the partials
 
 
 class _PlanCache:
@@ -80,6 +84,7 @@ class _Pool:
         self.free_lists: Dict[Tuple[int, torch.dtype], List[torch.Tensor]] = {}
         self.all: List[torch.Tensor] = []       # owns every allocation for the life of the plan
         self.total_bytes = 0
+        self.on_recycle = None                  # called with a buffer's address when it is freed or handed out again
 
     def alloc(self, *shape, dtype=F16) -> torch.Tensor:
         n = 1
@@ -87,15 +92,66 @@ class _Pool:
             n *= s
         fl = self.free_lists.get((n, dtype))
         if fl:
-            return fl.pop().view(*shape)
-        self.total_bytes += n * torch.empty((), dtype=dtype).element_size()
-        t = torch.empty(n, dtype=dtype, device=self.device)
-        self.all.append(t)
+            t = fl.pop()
+        else:
+            self.total_bytes += n * torch.empty((), dtype=dtype).element_size()
+            t = torch.empty(n, dtype=dtype, device=self.device)
+            self.all.append(t)
+        if self.on_recycle is not None:
+            self.on_recycle(t.data_ptr())
         return t.view(*shape)
 
     def free(self, t: torch.Tensor):
         base = t.reshape(-1)
+        if self.on_recycle is not None:
+            self.on_recycle(base.data_ptr())
         self.free_lists.setdefault((base.numel(), t.dtype), []).append(base)
+
+
+class _GnStatsMixin:
+    """Bookkeeping for GroupNorm statistics fused into producer epilogues: ``_produce`` records a GEMM (or the four
+    phase GEMMs of an upsample conv) and, when its output can feed a two-pass GroupNorm, makes it leave column
+    partials in a pooled fp32 buffer that lives exactly as long as the output tensor; ``_colstats`` hands them to the
+    consuming GroupNorm.  Needs ``self.pool`` and ``self.prog``."""
+
+    def _init_gn_stats(self):
+        self._cs: Dict[int, tuple] = {}          # output address -> (partials [B, slots, C, 2], slots, pooled buffer)
+        self.pool.on_recycle = self._drop_stats
+
+    def _drop_stats(self, ptr: int):
+        e = self._cs.pop(ptr, None)
+        if e is not None:
+            self.pool.free(e[2])
+
+    def _produce(self, descs, out: torch.Tensor):
+        """out: the [B, h, w, C] tensor the launch(es) write."""
+        Bn, h, w, c = out.shape
+        dl = descs if isinstance(descs, (list, tuple)) else [descs]
+        if FUSE_GN_STATS and h * w >= GN_STATS_MIN_HW and c % 32 == 0:
+            flat = dl[0].H == 1 and dl[0].B == 1 and Bn * h * w == dl[0].W      # a [rows, C] GEMM: slots run over all rows
+            per = [K.colstats_slots(d) for d in dl]
+            ok = min(per) >= 1 and (not flat or ((h * w) % 32 == 0 and len(dl) == 1))
+            if ok:
+                total = sum(per)
+                raw = self.pool.alloc((1 if flat else Bn) * total * c * 2, dtype=F32)
+                base = 0
+                for d, n in zip(dl, per):
+                    d.colstats_out, d.colstats_slots, d.colstats_slot_base = raw.data_ptr(), total, base
+                    base += n
+                if flat:
+                    slots = (h * w) // 32          # rows are (b, pixel): the first B * HW / 32 slots, b-major
+                    view = raw[:Bn * slots * c * 2].view(Bn, slots, c, 2)
+                else:
+                    slots, view = total, raw.view(Bn, total, c, 2)
+                self._cs[out.data_ptr()] = (view, slots, raw)
+        self.prog.add(descs)
+
+    def _colstats(self, x0, x1):
+        a = self._cs.get(x0.data_ptr())
+        b = None if x1 is None else self._cs.get(x1.data_ptr())
+        if a is None or (x1 is not None and b is None):
+            return None
+        return (a[0], a[1]), (None if b is None else (b[0], b[1]))
 
 
 def _f32(sd, name, dev):
@@ -241,7 +297,7 @@ class UNetEngine:
         return pl.run(x, sigma, ctx if context_changed else None, cfg_scale=scale).clone()
 
 
-class UNetPlan:
+class UNetPlan(_GnStatsMixin):
     def __init__(self, eng: UNetEngine, B: int, H: int, W: int, cfg_pairs: bool, ctx_len: int = 77):
         self.eng, self.B, self.H, self.W, self.cfg_pairs, self.ctx_len = eng, B, H, W, cfg_pairs, ctx_len
         if ctx_len < 1:
@@ -251,6 +307,7 @@ class UNetPlan:
         if H % down or W % down:
             raise L.LdxError(f"latent {H}x{W} must be a multiple of {down}")
         self.pool = _Pool(dev)
+        self._init_gn_stats()
         nb = B // 2 if cfg_pairs else B          # number of distinct latents fed in
         self.nb = nb
         self.x_in = torch.zeros(nb, cfg.in_channels, H, W, dtype=F32, device=dev)
@@ -274,8 +331,9 @@ class UNetPlan:
     def _gn(self, x0, x1, g, b, eps, silu):
         Bn, h, w, c0 = x0.shape
         c = c0 + (0 if x1 is None else x1.shape[-1])
+        cs = self._colstats(x0, x1)               # looked up before y is allocated (allocation recycles buffers)
         y = self.pool.alloc(Bn, h, w, c)
-        self.prog.add(K.group_norm_op(x0, x1, g, b, y, self.stats, eps, silu))
+        self.prog.add(K.group_norm_op(x0, x1, g, b, y, self.stats, eps, silu, colstats=cs))
         return y
 
     def _res(self, s: ResSpec, x0, x1):
@@ -284,8 +342,8 @@ class UNetPlan:
         y = self._gn(x0, x1, w[p + ".gn1.g"], w[p + ".gn1.b"], 1e-5, True)
         h1 = self.pool.alloc(Bn, h, wd, s.cout)
         off = eng.emb_off[p]
-        self.prog.add(K.conv3x3_desc(y, w[p + ".conv1.w"], h1, bias=w[p + ".conv1.b"],
-                                     rowadd=self.emb_out[:, off:off + s.cout]))
+        self._produce(K.conv3x3_desc(y, w[p + ".conv1.w"], h1, bias=w[p + ".conv1.b"],
+                                     rowadd=self.emb_out[:, off:off + s.cout]), h1)
         self.pool.free(y)
         y2 = self._gn(h1, None, w[p + ".gn2.g"], w[p + ".gn2.b"], 1e-5, True)
         self.pool.free(h1)
@@ -303,7 +361,7 @@ class UNetPlan:
             if x1 is not None:
                 segs.append((2, 0, 0, 0, K.ceil64(x1.shape[-1]) // 64))
             d = K.gemm_desc(srcs, segs, w[p + ".conv2.w"], out, s.cout, bias=w[p + ".conv2.b"])
-        self.prog.add(d)
+        self._produce(d, out)
         self.pool.free(y2)
         return out
 
@@ -392,7 +450,7 @@ class UNetPlan:
         self.prog.add(K.linear_desc(g, w[p + ".ff2.w"], t4, bias=w[p + ".ff2.b"], residual=t3))
         pool.free(g); pool.free(t3)
         out = pool.alloc(Bn, h, wd, c)
-        self.prog.add(K.linear_desc(t4, w[p + ".pout.w"], out, bias=w[p + ".pout.b"], residual=x))
+        self._produce(K.linear_desc(t4, w[p + ".pout.w"], out, bias=w[p + ".pout.b"], residual=x), out)
         pool.free(t4)
         if expand:
             pool.free(x)                       # the duplicated copy made above
@@ -411,15 +469,15 @@ class UNetPlan:
             elif s.kind == "conv_in":
                 Bn, hh, ww, _ = cur.shape
                 nxt = pool.alloc(Bn, hh, ww, s.cout)
-                self.prog.add(K.conv3x3_desc(cur, self.eng.w[s.name + ".w"], nxt, bias=self.eng.w[s.name + ".b"]))
+                self._produce(K.conv3x3_desc(cur, self.eng.w[s.name + ".w"], nxt, bias=self.eng.w[s.name + ".b"]), nxt)
             elif s.kind == "down":
                 Bn, hh, ww, _ = cur.shape
                 nxt = pool.alloc(Bn, hh // 2, ww // 2, s.cout)
-                self.prog.add(K.conv3x3_s2_desc(cur, self.eng.w[s.name + ".w"], nxt, bias=self.eng.w[s.name + ".b"]))
+                self._produce(K.conv3x3_s2_desc(cur, self.eng.w[s.name + ".w"], nxt, bias=self.eng.w[s.name + ".b"]), nxt)
             else:  # up: nearest 2x + conv folded into four phase convs
                 Bn, hh, ww, _ = cur.shape
                 nxt = pool.alloc(Bn, hh * 2, ww * 2, s.cout)
-                self.prog.add(K.upconv3x3_descs(cur, self.eng.w[s.name + ".w"], nxt, bias=self.eng.w[s.name + ".b"]))
+                self._produce(K.upconv3x3_descs(cur, self.eng.w[s.name + ".w"], nxt, bias=self.eng.w[s.name + ".b"]), nxt)
             if owned:
                 pool.free(cur)
             cur, owned = nxt, True
@@ -463,6 +521,11 @@ class UNetPlan:
             pool.free(r1)
             h0b = pool.alloc(B, H, W, h0.shape[-1])
             self._dup(h0, h0b)
+            e = self._cs.get(h0.data_ptr())
+            if e is not None:                                   # the statistics of the duplicated batch are duplicates too
+                raw = pool.alloc(2 * e[0].numel(), dtype=F32)
+                self._dup(e[0], raw)
+                self._cs[h0b.data_ptr()] = (raw.view(B, e[1], h0.shape[-1], 2), e[1], raw)
             pool.free(h0)
             hs += [h0b, h]
             blocks = blocks[2:]
@@ -615,12 +678,13 @@ class VAEDecoderEngine:
         return pl.dec_buf[..., :3].float().permute(0, 3, 1, 2).contiguous()
 
 
-class VAEPlan:
+class VAEPlan(_GnStatsMixin):
     def __init__(self, eng: VAEDecoderEngine, B, H, W):
         self.eng, self.B, self.H, self.W = eng, B, H, W
         dev, cfg, w = eng.dev, eng.cfg, eng.w
         self.pool = pool = _Pool(dev)
         self.prog = prog = K.Program()
+        self._init_gn_stats()
         self.z_in = torch.zeros(B, cfg.z_channels, H, W, dtype=F32, device=dev)
         up = 2 ** (len(cfg.ch_mult) - 1)
         self.img = torch.zeros(B, H * up, W * up, 3, dtype=F32, device=dev)
@@ -632,7 +696,7 @@ class VAEPlan:
         prog.add(K.linear_desc(z0, w["pq.w"], z1[..., :cfg.z_channels], bias=w["pq.b"]))
         top = cfg.ch * cfg.ch_mult[-1]
         h = pool.alloc(B, H, W, top)
-        prog.add(K.conv3x3_desc(z1, w["cin.w"], h, bias=w["cin.b"]))
+        self._produce(K.conv3x3_desc(z1, w["cin.w"], h, bias=w["cin.b"]), h)
         prog.keep(z0, z1)
         h = self._res("decoder.mid.block_1", h, top, top)
         h = self._attn("decoder.mid.attn_1", h)
@@ -644,12 +708,13 @@ class VAEPlan:
                 n = f"decoder.up.{i_level}.upsample.conv"
                 Bn, hh, ww, c = h.shape
                 nh = pool.alloc(Bn, hh * 2, ww * 2, c)
-                prog.add(K.upconv3x3_descs(h, w[n + ".w"], nh, bias=w[n + ".b"]))
+                self._produce(K.upconv3x3_descs(h, w[n + ".w"], nh, bias=w[n + ".b"]), nh)
                 pool.free(h)
                 h = nh
         Bn, hh, ww, c = h.shape
+        cs = self._colstats(h, None)
         y = pool.alloc(Bn, hh, ww, c)
-        prog.add(K.group_norm_op(h, None, w["nout.g"], w["nout.b"], y, self.stats, 1e-6, True))
+        prog.add(K.group_norm_op(h, None, w["nout.g"], w["nout.b"], y, self.stats, 1e-6, True, colstats=cs))
         self.dec_buf = torch.zeros(Bn, hh, ww, 8, dtype=F16, device=dev)
         if "cout.ws" in w and cfg.out_ch == 3:
             # conv_out and VAE.process_output in one launch: the 128-channel map is read once, the fp16 result
@@ -666,22 +731,24 @@ class VAEPlan:
     def _res(self, p, x, cin, cout):
         w, pool, prog = self.eng.w, self.pool, self.prog
         Bn, h, wd, _ = x.shape
+        cs = self._colstats(x, None)
         y = pool.alloc(Bn, h, wd, cin)
-        prog.add(K.group_norm_op(x, None, w[p + ".gn1.g"], w[p + ".gn1.b"], y, self.stats, 1e-6, True))
+        prog.add(K.group_norm_op(x, None, w[p + ".gn1.g"], w[p + ".gn1.b"], y, self.stats, 1e-6, True, colstats=cs))
         h1 = pool.alloc(Bn, h, wd, cout)
-        prog.add(K.conv3x3_desc(y, w[p + ".conv1.w"], h1, bias=w[p + ".conv1.b"]))
+        self._produce(K.conv3x3_desc(y, w[p + ".conv1.w"], h1, bias=w[p + ".conv1.b"]), h1)
         pool.free(y)
+        cs = self._colstats(h1, None)
         y2 = pool.alloc(Bn, h, wd, cout)
-        prog.add(K.group_norm_op(h1, None, w[p + ".gn2.g"], w[p + ".gn2.b"], y2, self.stats, 1e-6, True))
+        prog.add(K.group_norm_op(h1, None, w[p + ".gn2.g"], w[p + ".gn2.b"], y2, self.stats, 1e-6, True, colstats=cs))
         pool.free(h1)
         out = pool.alloc(Bn, h, wd, cout)
         nch = K.ceil64(cout) // 64
         segs = [(0, 0, kx - 1, ky - 1, nch) for ky in range(3) for kx in range(3)]
         if cin == cout:
-            prog.add(K.gemm_desc([y2], segs, w[p + ".conv2.w"], out, cout, bias=w[p + ".conv2.b"], residual=x))
+            self._produce(K.gemm_desc([y2], segs, w[p + ".conv2.w"], out, cout, bias=w[p + ".conv2.b"], residual=x), out)
         else:
             segs.append((1, 0, 0, 0, K.ceil64(cin) // 64))
-            prog.add(K.gemm_desc([y2, x], segs, w[p + ".conv2.w"], out, cout, bias=w[p + ".conv2.b"]))
+            self._produce(K.gemm_desc([y2, x], segs, w[p + ".conv2.w"], out, cout, bias=w[p + ".conv2.b"]), out)
         pool.free(y2); pool.free(x)
         return out
 
@@ -691,8 +758,9 @@ class VAEPlan:
         w, pool, prog = self.eng.w, self.pool, self.prog
         Bn, h, wd, c = x.shape
         n = h * wd
+        cs = self._colstats(x, None)
         y = pool.alloc(Bn, h, wd, c)
-        prog.add(K.group_norm_op(x, None, w[p + ".gn.g"], w[p + ".gn.b"], y, self.stats, 1e-6, False))
+        prog.add(K.group_norm_op(x, None, w[p + ".gn.g"], w[p + ".gn.b"], y, self.stats, 1e-6, False, colstats=cs))
         qk = pool.alloc(Bn * n, 2 * c)
         prog.add(K.linear_desc(y, w[p + ".qk.w"], qk, bias=w[p + ".qk.b"]))
         # P V contracts over the n tokens: its operands' row pitch is padded to a multiple of 64 (the GEMM's K chunk),
@@ -714,7 +782,7 @@ class VAEPlan:
                                   f=[1.0 / math.sqrt(c)]))       # l: lds, ldo, rows
             prog.add(K.linear_desc(pm[:, :n], vt[b], o3[b], bias=w[p + ".v.b"]))      # O = P V + b_v
         out = pool.alloc(Bn, h, wd, c)
-        prog.add(K.linear_desc(o, w[p + ".o.w"], out, bias=w[p + ".o.b"], residual=x))
+        self._produce(K.linear_desc(o, w[p + ".o.w"], out, bias=w[p + ".o.b"], residual=x), out)
         for t in (y, qk, s, pm, o, x) + ((vt,) if n64 == n else ()):
             pool.free(t)
         return out
@@ -806,6 +874,7 @@ class VAEEncodePlan(VAEPlan):
         dev, cfg, w = eng.dev, eng.cfg, eng.w
         self.pool = pool = _Pool(dev)
         self.prog = prog = K.Program()
+        self._init_gn_stats()
         f = 2 ** (len(cfg.ch_mult) - 1)
         zc = cfg.z_channels
         self.pix_in = torch.zeros(B, H, W, 3, dtype=F32, device=dev)
@@ -815,7 +884,7 @@ class VAEEncodePlan(VAEPlan):
         x0 = torch.zeros(B, H, W, 8, dtype=F16, device=dev)
         prog.add(K.generic_op(L.OP_VAE_PRE, p=[self.pix_in.data_ptr(), x0.data_ptr()], l=[B * H * W]))
         h = pool.alloc(B, H, W, cfg.ch)
-        prog.add(K.conv3x3_desc(x0, w["cin.w"], h, bias=w["cin.b"]))
+        self._produce(K.conv3x3_desc(x0, w["cin.w"], h, bias=w["cin.b"]), h)
         prog.keep(x0)
         for i_level, blocks, has_down in vae_encoder_levels(cfg):
             for j, (cin, cout) in enumerate(blocks):
@@ -824,7 +893,7 @@ class VAEEncodePlan(VAEPlan):
                 n = f"encoder.down.{i_level}.downsample.conv"
                 Bn, hh, ww, c = h.shape
                 nh = pool.alloc(Bn, hh // 2, ww // 2, c)
-                prog.add(K.conv3x3_s2_desc(h, w[n + ".w"], nh, pad_end=True, bias=w[n + ".b"]))
+                self._produce(K.conv3x3_s2_desc(h, w[n + ".w"], nh, pad_end=True, bias=w[n + ".b"]), nh)
                 pool.free(h)
                 h = nh
         top = cfg.ch * cfg.ch_mult[-1]
@@ -832,8 +901,9 @@ class VAEEncodePlan(VAEPlan):
         h = self._attn("encoder.mid.attn_1", h)
         h = self._res("encoder.mid.block_2", h, top, top)
         Bn, hh, ww, c = h.shape
+        cs = self._colstats(h, None)
         y = pool.alloc(Bn, hh, ww, c)
-        prog.add(K.group_norm_op(h, None, w["nout.g"], w["nout.b"], y, self.stats, 1e-6, True))
+        prog.add(K.group_norm_op(h, None, w["nout.g"], w["nout.b"], y, self.stats, 1e-6, True, colstats=cs))
         m0 = torch.zeros(Bn, hh, ww, 2 * zc, dtype=F16, device=dev)
         prog.add(K.conv3x3_desc(y, w["cout.w"], m0, bias=w["cout.b"]))
         self.mom = torch.zeros(Bn, hh, ww, 2 * zc, dtype=F32, device=dev)       # mean | logvar, fp32

@@ -122,6 +122,29 @@ def attach_rowstats(d: L.GemmDesc, rows: int) -> torch.Tensor:
     return stats
 
 
+def colstats_slots(d: L.GemmDesc) -> int:
+    """32-row slots per batch element GEMM `d` would write into colstats_out; -1 when it cannot (split-K, direct-store
+    epilogue, fewer than 32 pixels per batch element)."""
+    return L.lib().ldx_gemm_colstats_slots(C.byref(d))
+
+
+def attach_colstats(descs, batch: int, n: int):
+    """Makes the GEMM(s) `descs` (one, or the four phase GEMMs of an upsample conv that together write one tensor)
+    leave the per-(32-row slot, column) sums of their fp16 outputs in a shared [batch, slots, n, 2] fp32 buffer.
+    Returns (buffer, slots) for group_norm_op(colstats=...), or None when a launch cannot produce them."""
+    descs = descs if isinstance(descs, (list, tuple)) else [descs]
+    per = [colstats_slots(d) for d in descs]
+    if min(per) < 1:
+        return None
+    total = sum(per)
+    buf = torch.empty(batch, total, n, 2, dtype=torch.float32, device="cuda")
+    base = 0
+    for d, s in zip(descs, per):
+        d.colstats_out, d.colstats_slots, d.colstats_slot_base = buf.data_ptr(), total, base
+        base += s
+    return buf, total
+
+
 def _dev16(t: torch.Tensor) -> torch.Tensor:
     """fp16 copy on the GPU; host tensors are converted on the host first (one H2D copy, no cast kernel)."""
     return t.detach().to(torch.float16).contiguous().to("cuda")
@@ -294,15 +317,25 @@ def generic_op(kind: int, p=(), i=(), l=(), f=()) -> L.GenericOp:
     return op
 
 
-def group_norm_op(x0, x1, gamma, beta, y, stats, eps: float, silu: bool) -> L.GenericOp:
-    """x0 (and optional x1, channel-concatenated) [B,H,W,C*] -> y [B,H,W,C0+C1]."""
+def group_norm_op(x0, x1, gamma, beta, y, stats, eps: float, silu: bool, colstats=None) -> L.GenericOp:
+    """x0 (and optional x1, channel-concatenated) [B,H,W,C*] -> y [B,H,W,C0+C1].
+    colstats = ((buf0, slots0), (buf1, slots1) | None): column partials written by the GEMMs that produced x0 / x1
+    (attach_colstats); the statistics pass over the tensor is then replaced by a reduction over them."""
     b, h, w, c0 = x0.shape
     assert x0.stride(1) == x0.stride(2) * w and x0.stride(0) == x0.stride(1) * h
     c1 = 0 if x1 is None else x1.shape[-1]
     assert stats.numel() >= b * L.GN_STATS_FLOATS_PER_BATCH and stats.dtype == torch.float32
+    cs0 = cs1 = None
+    s0 = s1 = 0
+    if colstats is not None and colstats[0] is not None and (x1 is None or colstats[1] is not None):
+        (cs0, s0) = colstats[0]
+        assert tuple(cs0.shape) == (b, s0, c0, 2) and cs0.dtype == torch.float32 and cs0.is_contiguous()
+        if x1 is not None:
+            (cs1, s1) = colstats[1]
+            assert tuple(cs1.shape) == (b, s1, c1, 2) and cs1.dtype == torch.float32 and cs1.is_contiguous()
     return generic_op(L.OP_GROUP_NORM, p=[x0.data_ptr(), _ptr(x1), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
-                                          stats.data_ptr()],
-                      i=[c0, c1, b, h * w, int(silu)],
+                                          stats.data_ptr(), _ptr(cs0), _ptr(cs1)],
+                      i=[c0, c1, b, h * w, int(silu), s0, s1],
                       l=[x0.stride(2), 0 if x1 is None else x1.stride(2), y.stride(2)], f=[eps])
 
 

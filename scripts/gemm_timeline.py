@@ -8,7 +8,7 @@ lib = L.lib()
 lib.ldx_debug_gemm_ts.argtypes = [C.POINTER(C.c_ulonglong)]
 names = ["kernel entry", "prologue done (barriers, TMEM)", "griddepcontrol.wait done", "first stage landed", "last stage of tile 0 landed",
          "accumulator 0 complete", "epilogue loop done", "stores drained"]
-for (M, N, Kd, res) in [(65536, 320, 320, True), (65536, 2560, 320, 'geglu'), (16384, 5120, 640, 'geglu'), (65536, 320, 1280, True)]:
+for (M, N, Kd, res) in [(65536, 320, 320, True), (4096, 1280, 1280, True), (16384, 640, 640, True), (4096, 1280, 5120, False), (65536, 2560, 320, 'geglu'), (65536, 320, 1280, True)]:
     a = torch.randn(M, Kd, device=dev).half(); w = (torch.randn(N, Kd, device=dev) * Kd ** -0.5).half()
     b = torch.randn(N, device=dev); r = torch.randn(M, N, device=dev).half() if res is True else None
     out = torch.empty(M, N, dtype=torch.float16, device=dev)

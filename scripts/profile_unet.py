@@ -56,5 +56,21 @@ for (kind, tag), (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     tf = fl / (ms * 1e-3) / 1e12 if ms > 0 else 0
     print(f"{kind:11s} {str(tag):28s} x{n:3d}  {ms:8.3f} ms  {100*ms/tot:5.1f}%  {tf:7.1f} TF/s(exec)")
     out.append({"kind": kind, "tag": tag, "n": n, "ms": ms, "tflops_exec": tf})
+# the number that matters: CUDA-graph replay of the whole program (no events between ops, PDL overlap intact)
+g = torch.cuda.CUDAGraph()
+torch.cuda.synchronize()
+with torch.cuda.graph(g):
+    plan.prog.run()
+for _ in range(3):
+    g.replay()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(20):
+    g.replay()
+e1.record()
+torch.cuda.synchronize()
+graph_ms = e0.elapsed_time(e1) / 20
+print(f"graph replay: {graph_ms:.3f} ms per program")
 os.makedirs(os.path.dirname(args.out), exist_ok=True)
-json.dump({"total_ms": tot, "ops": out}, open(args.out, "w"), indent=1)
+json.dump({"total_ms": tot, "graph_ms": graph_ms, "ops": out}, open(args.out, "w"), indent=1)
