@@ -633,7 +633,12 @@ struct AttnLaunch {
 
 // Query groups per CTA: 4 for the long self-attention streams of narrow heads (K/V read once per 512 queries),
 // 1 when K/V is short (cross-attention over 77 tokens: more, smaller CTAs hide the per-CTA latency chain).
-static int attention_groups(int d, int Nk) { return (d <= 64 && Nk > 256) ? LDX_ATT_NG_SMALL : 1; }
+static int attention_groups(int d, int Nk) {
+  static int short_ng = -1;                     // experiments: LDX_ATT_NG_SHORT=4 runs short K/V (cross-attention) multi-group too
+  if (short_ng < 0) { const char* e = getenv("LDX_ATT_NG_SHORT"); short_ng = e ? atoi(e) : 1; }
+  if (d <= 64 && Nk <= 256 && short_ng == LDX_ATT_NG_SMALL) return LDX_ATT_NG_SMALL;
+  return (d <= 64 && Nk > 256) ? LDX_ATT_NG_SMALL : 1;
+}
 
 static int attention_prepare(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                              void* o, int64_t ldo, int B, int Nq, int Nk, int heads, int d, AttnLaunch* L, int causal = 0) {

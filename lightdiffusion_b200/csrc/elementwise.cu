@@ -257,52 +257,51 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const GnArgs a) {
   }
 }
 
-// GroupNorm statistics from the column partials the producing GEMMs left behind (ldx_gemm_desc_t.colstats_out):
-// one CTA per (group, batch element) sums its channels' (sum, sum of squares) over all 32-row slots in a fixed
-// order, in double, and writes the totals where gn_apply_kernel expects ONE slab of partials.  The tensor itself
-// is not read: bytes = B * slots * C * 8 (1/8 of the fp16 map at 32 rows per slot).
-// The channel concat [x0 | x1] of the UNet's skip connections has one partial buffer per source.
+// GroupNorm statistics from the column partials the producing GEMMs left behind (ldx_gemm_desc_t.colstats_out,
+// [B][slots][C][2] per source): the same reduction as gn_stats_kernel, over 1/32 of the rows and without touching
+// the tensor.  CTA (b, slab) owns a contiguous range of slots; a thread owns one channel of the (virtual) concat
+// [x0 | x1] and one of P slot lanes, so a warp reads 256 contiguous bytes; per-group sums are formed in a fixed
+// order and land where gn_apply_kernel expects slab partials.  bytes = B * slots * C * 8.
 struct GnCsArgs {
   const float* cs0; const float* cs1;
-  int c0, c1, slots0, slots1, cpg;
-  float* partial;   // [B][1][32][2]
+  int c0, c1, slots0, slots1, C, cpg, P, nslab;
+  float* partial;   // [B][nslab][32][2]
 };
 
-__global__ void __launch_bounds__(128) gn_colstats_finalize_kernel(const GnCsArgs a) {
-  __shared__ double sh[2][128];
+__global__ void __launch_bounds__(1024) gn_colstats_reduce_kernel(const GnCsArgs a) {
+  extern __shared__ float sm[];          // [P][C][2]
   pdl_prologue();
-  const int g = blockIdx.x, b = blockIdx.y;
-  const int lo = g * a.cpg, hi = lo + a.cpg;
-  double s = 0.0, ss = 0.0;
-#pragma unroll
-  for (int src = 0; src < 2; ++src) {
-    const float* cs = src ? a.cs1 : a.cs0;
-    const int cw = src ? a.c1 : a.c0, slots = src ? a.slots1 : a.slots0, off = src ? a.c0 : 0;
-    if (!cs) continue;
-    const int clo = max(lo, off) - off, chi = min(hi, off + cw) - off;
-    const int n = chi - clo;
-    if (n <= 0) continue;
-    const float2* base = reinterpret_cast<const float2*>(cs) + (int64_t)b * slots * cw;
-    for (int i = threadIdx.x; i < slots * n; i += 128) {
-      const int slot = i / n, c = clo + i % n;
-      const float2 v = __ldg(base + (int64_t)slot * cw + c);
-      s += (double)v.x;
-      ss += (double)v.y;
+  const int b = blockIdx.x, slab = blockIdx.y;
+  const int c = threadIdx.x % a.C, pl = threadIdx.x / a.C;
+  if (pl < a.P) {
+    const bool second = c >= a.c0;
+    const int cw = second ? a.c1 : a.c0, slots = second ? a.slots1 : a.slots0, cc = second ? c - a.c0 : c;
+    const float2* base = reinterpret_cast<const float2*>(second ? a.cs1 : a.cs0) + (int64_t)b * slots * cw + cc;
+    const int per = (slots + a.nslab - 1) / a.nslab;
+    const int s_begin = slab * per, s_end = min(slots, s_begin + per);
+    float s = 0.f, ss = 0.f;
+    int sl = s_begin + pl;
+    for (; sl + 3 * a.P < s_end; sl += 4 * a.P) {          // four independent loads in flight
+      const float2 v0 = __ldg(base + (int64_t)sl * cw), v1 = __ldg(base + (int64_t)(sl + a.P) * cw);
+      const float2 v2 = __ldg(base + (int64_t)(sl + 2 * a.P) * cw), v3 = __ldg(base + (int64_t)(sl + 3 * a.P) * cw);
+      s += (v0.x + v1.x) + (v2.x + v3.x);
+      ss += (v0.y + v1.y) + (v2.y + v3.y);
     }
+    for (; sl < s_end; sl += a.P) {
+      const float2 v = __ldg(base + (int64_t)sl * cw);
+      s += v.x;
+      ss += v.y;
+    }
+    sm[((size_t)pl * a.C + c) * 2 + 0] = s;
+    sm[((size_t)pl * a.C + c) * 2 + 1] = ss;
   }
-  sh[0][threadIdx.x] = s;
-  sh[1][threadIdx.x] = ss;
   __syncthreads();
-  for (int w = 64; w > 0; w >>= 1) {
-    if (threadIdx.x < w) {
-      sh[0][threadIdx.x] += sh[0][threadIdx.x + w];
-      sh[1][threadIdx.x] += sh[1][threadIdx.x + w];
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    a.partial[((size_t)b * 32 + g) * 2 + 0] = (float)sh[0][0];
-    a.partial[((size_t)b * 32 + g) * 2 + 1] = (float)sh[1][0];
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+    double acc = 0.0;
+    for (int pl2 = 0; pl2 < a.P; ++pl2)
+      for (int ch = g * a.cpg; ch < (g + 1) * a.cpg; ++ch) acc += (double)sm[((size_t)pl2 * a.C + ch) * 2 + which];
+    a.partial[(((size_t)b * a.nslab + slab) * 32 + g) * 2 + which] = (float)acc;
   }
 }
 
@@ -355,15 +354,29 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
   a.pix_per_slab = pps; a.nslab = nslab;
   a.eps = eps; a.silu = silu; a.gamma = gamma; a.beta = beta;
   a.y = (__half*)y; a.ldy = ldy; a.partial = stats;
-  if (cs0 && (!x1 || cs1)) {
+  if (cs0 && (!x1 || cs1) && C <= 1024) {
     // statistics from the producers' column partials: a reduction over B * slots * C pairs instead of a pass over x
     LDX_CHECK_ARG(slots0 >= 1 && (!x1 || slots1 >= 1), "group_norm: colstats slots");
     GnCsArgs f;
-    f.cs0 = cs0; f.cs1 = x1 ? cs1 : nullptr;
-    f.c0 = c0; f.c1 = x1 ? c1 : 0; f.slots0 = slots0; f.slots1 = slots1; f.cpg = a.cpg;
+    f.cs0 = cs0; f.cs1 = x1 ? cs1 : cs0;
+    f.c0 = c0; f.c1 = x1 ? c1 : 0; f.slots0 = slots0; f.slots1 = x1 ? slots1 : slots0;
+    f.C = C; f.cpg = a.cpg;
+    const int max_slots = slots0 > f.slots1 ? slots0 : f.slots1;
+    f.P = 1024 / C;
+    if (f.P > max_slots) f.P = max_slots;
+    if (f.P < 1) f.P = 1;
+    int cs_threads = ((C * f.P + 31) / 32) * 32;
+    if (cs_threads < 64) cs_threads = 64;
+    int ns = 2 * sms / B;                                   // ~two CTAs per SM in flight
+    const int max_ns = (max_slots + f.P - 1) / f.P;
+    if (ns > max_ns) ns = max_ns;
+    if (ns > 64) ns = 64;
+    if (ns < 1) ns = 1;
+    f.nslab = ns;
     f.partial = stats;
-    a.nslab = 1;
-    LDX_CUDA(launch_k(gn_colstats_finalize_kernel, dim3(32, B), dim3(128), 0, stream, 1, f));
+    a.nslab = ns;
+    LDX_CUDA(launch_k(gn_colstats_reduce_kernel, dim3(B, ns), dim3(cs_threads), (size_t)f.P * C * 2 * sizeof(float), stream,
+                      1, f));
   } else {
     const size_t smem = (size_t)a.P * C * 2 * sizeof(float);
     static std::atomic<uint64_t> attr_done{0};

@@ -540,7 +540,8 @@ def test_gemm_colstats_conv(B, H, W, cin, cout):
     x = h16(rnd(B, H, W, cin, seed=71))
     w = h16(rnd(cout, cin, 3, 3, seed=72, scale=(9 * cin) ** -0.5))
     out = torch.empty(B, H, W, cout, dtype=torch.float16, device=DEV)
-    d = K.conv3x3_desc(x, K.pack_conv3x3(w), out, bias=rnd(cout, seed=73))
+    wp, bias = K.pack_conv3x3(w), rnd(cout, seed=73)         # descriptors hold raw pointers: keep the tensors alive
+    d = K.conv3x3_desc(x, wp, out, bias=bias)
     r = K.attach_colstats(d, B, cout)
     assert r is not None
     buf, slots = r
@@ -561,7 +562,8 @@ def test_group_norm_from_colstats_concat(silu):
     xin = h16(rnd(B, H, W, 64, seed=81))
     w0 = h16(rnd(c0, 64, 3, 3, seed=82, scale=(9 * 64) ** -0.5))
     x0 = torch.empty(B, H, W, c0, dtype=torch.float16, device=DEV)
-    d0 = K.conv3x3_desc(xin, K.pack_conv3x3(w0), x0, bias=rnd(c0, seed=83) + 0.5)
+    wp0, b0 = K.pack_conv3x3(w0), rnd(c0, seed=83) + 0.5
+    d0 = K.conv3x3_desc(xin, wp0, x0, bias=b0)
     cs0 = K.attach_colstats(d0, B, c0)
     K.run_gemm(d0)
     a = h16(rnd(B * H * W, 320, seed=84))
@@ -593,7 +595,8 @@ def test_gemm_colstats_upsample_phases_share_a_buffer():
     x = h16(rnd(B, H, W, C, seed=91))
     w = h16(rnd(C, C, 3, 3, seed=92, scale=(9 * C) ** -0.5))
     out = torch.empty(B, 2 * H, 2 * W, C, dtype=torch.float16, device=DEV)
-    descs = K.upconv3x3_descs(x, K.pack_upconv3x3(w), out, bias=rnd(C, seed=93))
+    wp, bias = K.pack_upconv3x3(w), rnd(C, seed=93)
+    descs = K.upconv3x3_descs(x, wp, out, bias=bias)
     buf, slots = K.attach_colstats(descs, B, C)
     buf.fill_(float("nan"))
     for d in descs:
