@@ -50,8 +50,12 @@ MAX_PLANS = int(os.environ.get("LDX_MAX_PLANS", "4"))
 CONV_SMALL = os.environ.get("LDX_CONV_SMALL", "1") == "1"
 # GroupNorm statistics come out of the producing GEMM's epilogue (column partials per 32-row slot) instead of a
 # statistics pass over the tensor; LDX_FUSE_GN_STATS=0 keeps the two-pass GroupNorm everywhere (A/B).
+# Measured on B200 (graph replay): the VAE decoder gains (512^2 b=8: 21.3 -> 20.2 ms, 1024^2 b=4: 45.7 -> 44.0 ms: its
+# statistics passes read 0.27-0.54 GB maps from HBM), the SD1.5 UNet at 64x64 does not (15.54 -> 15.65 ms: its 21-42 MB
+# maps are still in L2 when the 10 us statistics pass reads them, and the epilogue work costs the GEMMs as much as it
+# saves).  Hence the threshold: maps of at least GN_STATS_MIN_HW pixels per sample (LDX_GN_STATS_MIN_HW overrides).
 FUSE_GN_STATS = os.environ.get("LDX_FUSE_GN_STATS", "1") == "1"
-GN_STATS_MIN_HW = 256          # smaller maps take the single-launch GroupNorm, which ignores the partials
+GN_STATS_MIN_HW = int(os.environ.get("LDX_GN_STATS_MIN_HW", "16384"))
 
 
 class _PlanCache:
