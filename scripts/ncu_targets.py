@@ -1,0 +1,45 @@
+"""One hot kernel per invocation, a few launches each, for `ncu --set full` captures (see scripts/gpu_ncu.sh).
+Usage: python scripts/ncu_targets.py <case>"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from lightdiffusion_b200 import _lib as L, kernels as K
+
+dev, case = "cuda", sys.argv[1]
+g = torch.Generator(device=dev).manual_seed(0)
+rnd = lambda *s, sc=1.0: (torch.randn(*s, device=dev, generator=g) * sc)
+keep = []
+if case == "gemm_dual_conv":          # 3x3 conv 1280 -> 1280 on 16 x 16 x 16: 64 pair tiles of 256 x 320, one wave
+    x = rnd(16, 16, 16, 1280).half(); w = rnd(1280, 1280, 3, 3, sc=(9 * 1280) ** -0.5).half()
+    wp, b = K.pack_conv3x3(w), rnd(1280); out = torch.empty(16, 16, 16, 1280, dtype=torch.float16, device=dev)
+    op = K.conv3x3_desc(x, wp, out, bias=b); keep += [x, wp, b, out]
+elif case == "gemm_dual_conv320":     # 3x3 conv 320 -> 320 on 16 x 64 x 64 (the r01 capture's shape): 256 x 320 tiles, 4 waves
+    x = rnd(16, 64, 64, 320).half(); w = rnd(320, 320, 3, 3, sc=(9 * 320) ** -0.5).half()
+    wp, b = K.pack_conv3x3(w), rnd(320); out = torch.empty(16, 64, 64, 320, dtype=torch.float16, device=dev)
+    op = K.conv3x3_desc(x, wp, out, bias=b); keep += [x, wp, b, out]
+elif case == "gemm_dual_lin":         # to_out + residual at the 16 x 16 level
+    a = rnd(4096, 1280).half(); w = rnd(1280, 1280, sc=1280 ** -0.5).half(); b = rnd(1280); r = rnd(4096, 1280).half()
+    out = torch.empty(4096, 1280, dtype=torch.float16, device=dev)
+    op = K.linear_desc(a, w, out, bias=b, residual=r); keep += [a, w, b, r, out]
+elif case == "conv_small_vae":        # VAE conv_out 128 -> 3 at 512^2, b = 8, fused process_output
+    x = rnd(8, 512, 512, 128).half(); w = rnd(3, 128, 3, 3, sc=(9 * 128) ** -0.5).half(); b = rnd(3)
+    wp = K.pack_conv3x3_small(w); o16 = torch.zeros(8, 512, 512, 8, dtype=torch.float16, device=dev)
+    img = torch.empty(8, 512, 512, 3, dtype=torch.float32, device=dev)
+    op = K.conv3x3_small_op(x, wp, b, 3, out16=o16, out_img=img, post=1); keep += [x, wp, b, o16, img]
+elif case == "attention_d40":
+    q, k, v = (rnd(16, 4096, 320).half() for _ in range(3)); o = torch.empty_like(q)
+    op = K.attention_op(q, k, v, o, 8); keep += [q, k, v, o]
+elif case == "gn_colstats_vae":       # GroupNorm + SiLU of a 8 x 512 x 512 x 128 map with producer statistics
+    xin = rnd(8, 512, 512, 128).half(); w = rnd(128, 128, 3, 3, sc=(9 * 128) ** -0.5).half(); wp, b = K.pack_conv3x3(w), rnd(128)
+    x = torch.empty(8, 512, 512, 128, dtype=torch.float16, device=dev)
+    d = K.conv3x3_desc(xin, wp, x, bias=b); cs = K.attach_colstats(d, 8, 128); K.run_gemm(d)
+    gam, bet = rnd(128) * 0.1 + 1, rnd(128) * 0.1; y = torch.empty_like(x)
+    st = torch.empty(8 * L.GN_STATS_FLOATS_PER_BATCH, dtype=torch.float32, device=dev)
+    op = K.group_norm_op(x, None, gam, bet, y, st, 1e-6, True, colstats=(cs, None)); keep += [xin, wp, b, x, cs, gam, bet, y, st]
+else:
+    raise SystemExit("unknown case " + case)
+prog = K.Program(); prog.add(op)
+for _ in range(4):
+    prog.run()
+torch.cuda.synchronize()
+print("ok", case)
