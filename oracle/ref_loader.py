@@ -6,8 +6,12 @@ The recipe is SURVEY.md Appendix B: stub the GUI / detector imports, skip the si
 hf_hub_download blocks (LD.py:53-120), force the CPU state on a GPU-less host
 (LD.py:1380) and inject a stub ``app`` (LD.py:922-927).
 
-/root/reference exists only in the build container; nothing under tests -m gpu,
-smoke() or bench.py calls this.
+Where the reference comes from: $LDX_REFERENCE_DIR, default /root/reference (the build container).  The GPU box
+has no /root/reference; there the unmodified copy that travels with the repo under baseline/_ref/reference
+(git-ignored, not gpurun-ignored) is used -- by tests/test_dropin_gpu.py (the reference drives the ldx seams) and by
+bench.py's reference legs (the reference's own CPU path, and its PyTorch fp16 path on the same GPU).  Both set
+LDX_REFERENCE_DIR before importing this module and skip / fall back to the oracle port when the copy is absent.
+Product code never imports this file.
 """
 from __future__ import annotations
 
