@@ -108,6 +108,21 @@ typedef struct {
   int32_t colstats_slot_base; /* first slot this launch writes (the four phase GEMMs of an upsample conv share one) */
   int32_t rowstats_out_parts; /* 0 = unchecked; else the [rows, parts, 2] extent of rowstats_out: the launch is
                                rejected unless it equals ldx_gemm_rowstats_parts(d) */
+  /* Halo-tile form of a 3x3 stride-1 pad-1 convolution (F.conv2d, LD.py:2382) over the channel concatenation of
+   * src[0 .. halo_nsrc-1] (th.cat([h, hsp], 1), LD.py:5749): per 64-channel chunk ONE (10 x 18)-pixel halo tile is
+   * fetched and the tensor core reads its nine tap views in place, so the operand is read ~1.4x instead of 9x.
+   * The weight matrix is the usual ldx_pack_conv3x3 layout over the concatenated channels ([N][9][halo_cp],
+   * halo_cp = sum of ceil64(C_i); every source but the last needs C_i % 64 == 0); seg[0 .. nseg) (nseg may be 0)
+   * then lists only extra 1x1 K segments (a ResBlock's skip_connection, LD.py:5267) whose weight columns follow at
+   * 9 * halo_cp.  Needs W % 8 == 0, fp16 output with TMA-compatible strides; 0 = off. */
+  int32_t halo_nsrc;
+  /* GroupNorm (+ SiLU) folded into that operand path (ResBlock in_layers / out_layers, LD.py:5220-5261; VAE
+   * ResnetBlock, LD.py:3562-3576): NULL, or [B, gn_ctot, 2] fp32 (scale, shift) per (sample, concatenated channel)
+   * from ldx_group_norm_coef; the landed tile is rewritten in shared memory as fp16(silu?(x * scale + shift)) before the
+   * MMA reads it (out-of-image pixels stay zero: the conv pads the NORMALISED map).  halo_nsrc > 0 only. */
+  const float* gn_coef;
+  int32_t gn_ctot;
+  int32_t gn_silu;
 } ldx_gemm_desc_t;
 
 int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream);
@@ -163,6 +178,14 @@ int ldx_group_norm_cs(const void* x0, int c0, int64_t ld0, const void* x1, int c
                       float eps, const float* gamma, const float* beta, int silu, void* y, int64_t ldy,
                       float* stats, const float* colstats0, int slots0, const float* colstats1, int slots1,
                       ldx_stream_t stream);
+/* GroupNorm statistics only: coef[b, c] = (rstd_g * gamma_c, beta_c - mean_g * rstd_g * gamma_c) as fp32 [B, C, 2]
+ * for a consumer that applies the normalisation itself (ldx_gemm_desc_t.gn_coef).  Same statistics, summation order
+ * and rounding as ldx_group_norm / ldx_group_norm_cs (colstats0 may be NULL).  One launch: the last CTA of each sample
+ * (atomic ticket in `tickets`, B zero-initialised uint32 that the call leaves zeroed) finalises. */
+int ldx_group_norm_coef(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1, int B, int HW,
+                        float eps, const float* gamma, const float* beta, float* stats, uint32_t* tickets,
+                        float* coef, const float* colstats0, int slots0, const float* colstats1, int slots1,
+                        ldx_stream_t stream);
 /* LayerNorm over the last dim (F.layer_norm, LD.py:2403), eps 1e-5, fp16 in/out. */
 int ldx_layer_norm(const void* x, int64_t ldx_, int rows, int C, float eps, const float* gamma,
                    const float* beta, void* y, int64_t ldy, ldx_stream_t stream);
@@ -276,6 +299,8 @@ enum {
   LDX_OP_NCHW_TO_NHWC = 5, LDX_OP_TIMESTEP_EMB = 6, LDX_OP_UPSAMPLE2X = 7, LDX_OP_EPS_TO_DENOISED = 8,
   LDX_OP_CFG_DENOISED = 9, LDX_OP_VAE_POST = 10, LDX_OP_SOFTMAX = 11,
   /* LDX_OP_ATTENTION takes i[5] = 1 for the causal variant (ldx_attention_causal) */
+  LDX_OP_GROUP_NORM_COEF = 17, /* ldx_group_norm_coef.  p: x0, x1, gamma, beta, coef, stats, colstats0, colstats1, tickets ;
+                                  i: c0, c1, B, HW, -, slots0, slots1 ; l: ld0, ld1 ; f: eps */
   LDX_OP_CONV_SMALL = 16,    /* ldx_conv3x3_small.  p: x, w_packed, bias, out16, out_img ; i: B, H, W, Cin, Cout, post ;
                                 l: pixel pitch of x, pixel pitch of out16 */
   LDX_OP_CLIP_EMBED = 15,    /* p: tokens, tok_emb, pos_emb, out ; l: ldo ; i: rows, T, C */

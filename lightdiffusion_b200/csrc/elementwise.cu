@@ -29,7 +29,63 @@ struct GnArgs {
   const float* gamma; const float* beta;
   __half* y; int64_t ldy;
   float* partial;   // [B][nslab][32][2]
+  // statistics-only form (ldx_group_norm_coef): the last CTA of sample b (atomic ticket) reduces the slab partials in
+  // gn_apply_kernel's order and writes coef[b][c] = (rstd * gamma, beta - mean * rstd * gamma) for a consumer that
+  // normalises on its own (the halo-tile conv's operand transform, conv_halo.cu)
+  float* coef;      // [B][C][2] or null
+  unsigned* ticket; // [B], zero before and after the launch
 };
+
+// Every thread of one CTA (>= 256 threads): slab partials -> (mean, rstd) per group -> coefficients of sample b.
+// Same summation order and arithmetic as the prologue of gn_apply_kernel (bit-identical normalisation).
+__device__ __forceinline__ void gn_write_coef(const float* partial, int b, int nslab, int HW, int cpg, int C, float eps,
+                                              const float* gamma, const float* beta, float* coef) {
+  __shared__ float c_mean[32], c_rstd[32];
+  const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  double s = 0.0, ss = 0.0;
+  if (g < 32) {
+    for (int k = sub; k < nslab; k += 8) {
+      const float2 pr = __ldcg(reinterpret_cast<const float2*>(partial + (((size_t)b * nslab + k) * 32 + g) * 2));
+      s += (double)pr.x;
+      ss += (double)pr.y;
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (g < 32 && sub == 0) {
+    const double n = (double)HW * cpg;
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    c_mean[g] = (float)mean;
+    c_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int gg = c / cpg;
+    const float w = __ldg(gamma + c) * c_rstd[gg];
+    *reinterpret_cast<float2*>(coef + ((size_t)b * C + c) * 2) = make_float2(w, fmaf(-c_mean[gg], w, __ldg(beta + c)));
+  }
+}
+
+// Ticket protocol around it: call with all threads after the CTA's partial has been stored.
+__device__ __forceinline__ void gn_finish_coef(const float* partial, unsigned* ticket, int b, int nslab, int HW, int cpg, int C,
+                                               float eps, const float* gamma, const float* beta, float* coef) {
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(ticket + b, 1u) == (unsigned)(nslab - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  gn_write_coef(partial, b, nslab, HW, cpg, C, eps, gamma, beta, coef);
+  if (threadIdx.x == 0) ticket[b] = 0u;
+}
 
 __device__ __forceinline__ uint4 gn_load(const GnArgs& a, int b, int pix, int vec) {
   const int c = vec * 8;
@@ -96,6 +152,7 @@ __global__ void gn_stats_kernel(const GnArgs a) {
       for (int c = g * a.cpg; c < (g + 1) * a.cpg; ++c) acc += sm[((size_t)pl2 * a.C + c) * 2 + which];
     a.partial[(((size_t)b * a.nslab + slab) * 32 + g) * 2 + which] = acc;
   }
+  if (a.coef) gn_finish_coef(a.partial, a.ticket, b, a.nslab, a.HW, a.cpg, a.C, a.eps, a.gamma, a.beta, a.coef);
 }
 
 __global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const GnArgs a, int nslab_apply, int pix_per_slab_apply) {
@@ -156,14 +213,14 @@ __global__ void __launch_bounds__(1024, 1) gn_apply_kernel(const GnArgs a, int n
     const int g = c / a.cpg;
     const float w = gm[j] * s_rstd[g];
     sc[j] = w;
-    sh[j] = bt[j] - s_mean[g] * w;
+    sh[j] = fmaf(-s_mean[g], w, bt[j]);
   }
   auto apply_store = [&](const uint4& vv, int px) {
     const float2 f0 = unpack_h2(vv.x), f1 = unpack_h2(vv.y), f2 = unpack_h2(vv.z), f3 = unpack_h2(vv.w);
     float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      f[j] = f[j] * sc[j] + sh[j];
+      f[j] = fmaf(f[j], sc[j], sh[j]);
       if (a.silu) f[j] = silu_f(f[j]);
     }
     uint4 o;
@@ -233,6 +290,13 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const GnArgs a) {
   }
   __syncthreads();
   const float mean = s_stat[0], rstd = s_stat[1];
+  if (a.coef) {                                   // statistics-only form: this CTA's group of channels
+    for (int c = g * a.cpg + threadIdx.x; c < (g + 1) * a.cpg; c += 256) {
+      const float w = __ldg(a.gamma + c) * rstd;
+      *reinterpret_cast<float2*>(a.coef + ((size_t)b * a.C + c) * 2) = make_float2(w, fmaf(-mean, w, __ldg(a.beta + c)));
+    }
+  }
+  if (!a.y) return;
 #pragma unroll
   for (int u = 0; u < GN_SMALL_VPT; ++u) {
     const int idx = threadIdx.x + u * 256;
@@ -247,7 +311,7 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const GnArgs a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float w = gg[j] * rstd;
-        f[j] = f[j] * w + (bb[j] - mean * w);
+        f[j] = fmaf(f[j], w, fmaf(-mean, w, bb[j]));
         if (a.silu) f[j] = silu_f(f[j]);
       }
       uint4 o;
@@ -266,6 +330,9 @@ struct GnCsArgs {
   const float* cs0; const float* cs1;
   int c0, c1, slots0, slots1, C, cpg, P, nslab;
   float* partial;   // [B][nslab][32][2]
+  // statistics-only form, as in GnArgs
+  float* coef; unsigned* ticket;
+  int HW; float eps; const float* gamma; const float* beta;
 };
 
 __global__ void __launch_bounds__(1024) gn_colstats_reduce_kernel(const GnCsArgs a) {
@@ -303,6 +370,7 @@ __global__ void __launch_bounds__(1024) gn_colstats_reduce_kernel(const GnCsArgs
       for (int ch = g * a.cpg; ch < (g + 1) * a.cpg; ++ch) acc += (double)sm[((size_t)pl2 * a.C + ch) * 2 + which];
     a.partial[(((size_t)b * a.nslab + slab) * 32 + g) * 2 + which] = (float)acc;
   }
+  if (a.coef) gn_finish_coef(a.partial, a.ticket, b, a.nslab, a.HW, a.cpg, a.C, a.eps, a.gamma, a.beta, a.coef);
 }
 
 int group_norm_num_launches(int C, int HW) {
@@ -313,9 +381,11 @@ int group_norm_num_launches(int C, int HW) {
 static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1, int B, int HW,
                            float eps, const float* gamma, const float* beta, int silu, void* y, int64_t ldy,
                            float* stats, cudaStream_t stream, const float* cs0 = nullptr, int slots0 = 0,
-                           const float* cs1 = nullptr, int slots1 = 0) {
+                           const float* cs1 = nullptr, int slots1 = 0, float* coef = nullptr, unsigned* ticket = nullptr) {
   const int C = c0 + (x1 ? c1 : 0);
-  LDX_CHECK_ARG(x0 && y && stats && gamma && beta, "group_norm: null pointer");
+  LDX_CHECK_ARG(x0 && (y || coef) && stats && gamma && beta, "group_norm: null pointer");
+  LDX_CHECK_ARG(!coef || (ticket && !y && reinterpret_cast<uintptr_t>(coef) % 8 == 0),
+                "group_norm_coef: needs tickets, an 8-byte aligned coefficient buffer and no y");
   LDX_CHECK_ARG(C % 32 == 0 && c0 % 8 == 0 && C % 8 == 0, "group_norm: C=%d (c0=%d) must be a multiple of 32 / 8", C, c0);
   LDX_CHECK_ARG(ld0 % 8 == 0 && ldy % 8 == 0 && (!x1 || ld1 % 8 == 0), "group_norm: pitches must be multiples of 8");
   LDX_CHECK_ARG(C <= 8192, "group_norm: C too large");
@@ -323,6 +393,7 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
   a.x0 = (const __half*)x0; a.x1 = (const __half*)x1;
   a.c0 = c0; a.c1 = c1; a.ld0 = ld0; a.ld1 = ld1;
   a.HW = HW; a.C = C; a.cpg = C / 32; a.nvec = C / 8;
+  a.coef = coef; a.ticket = ticket;
   if (a.cpg % 8 == 0 && (int64_t)HW * (a.cpg / 8) <= 256 * GN_SMALL_VPT &&
       reinterpret_cast<uintptr_t>(gamma) % 16 == 0 && reinterpret_cast<uintptr_t>(beta) % 16 == 0) {
     a.P = 1; a.pix_per_slab = HW; a.nslab = 1;
@@ -366,7 +437,8 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
     if (f.P > max_slots) f.P = max_slots;
     if (f.P < 1) f.P = 1;
     int cs_threads = ((C * f.P + 31) / 32) * 32;
-    if (cs_threads < 64) cs_threads = 64;
+    if (cs_threads < 256) cs_threads = 256;                 // the reductions use the first 64 / 256 threads
+    f.coef = coef; f.ticket = ticket; f.HW = HW; f.eps = eps; f.gamma = gamma; f.beta = beta;
     int ns = 2 * sms / B;                                   // ~two CTAs per SM in flight
     const int max_ns = (max_slots + f.P - 1) / f.P;
     if (ns > max_ns) ns = max_ns;
@@ -385,6 +457,7 @@ static int group_norm_impl(const void* x0, int c0, int64_t ld0, const void* x1, 
     LDX_CHECK_ARG(smem <= 128 * 1024, "group_norm: smem");
     LDX_CUDA(launch_k(gn_stats_kernel, dim3(B, nslab), dim3(threads), smem, stream, 1, a));
   }
+  if (coef) return LDX_OK;                                  // statistics-only form: the consumer applies them
   // apply: more slabs for bandwidth
   int occ2 = 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, gn_apply_kernel, threads, 0) != cudaSuccess || occ2 < 1) occ2 = 4;
@@ -927,6 +1000,12 @@ int run_generic_op(const ldx_generic_op_t* op, cudaStream_t st) {
       return group_norm_impl(p[0], i[0], l[0], p[1], i[1], l[1], i[2], i[3], f[0], (const float*)p[2],
                              (const float*)p[3], i[4], (void*)p[4], l[2], (float*)p[5], st, (const float*)p[6], i[5],
                              (const float*)p[7], i[6]);
+    case LDX_OP_GROUP_NORM_COEF:
+      // p: x0, x1, gamma, beta, coef, stats, colstats0, colstats1, tickets ; i: c0, c1, B, HW, -, slots0, slots1 ;
+      // l: ld0, ld1 ; f: eps
+      return group_norm_impl(p[0], i[0], l[0], p[1], i[1], l[1], i[2], i[3], f[0], (const float*)p[2],
+                             (const float*)p[3], 0, nullptr, 0, (float*)p[5], st, (const float*)p[6], i[5],
+                             (const float*)p[7], i[6], (float*)p[4], (unsigned*)p[8]);
     case LDX_OP_LAYER_NORM:
       // p: x, gamma, beta, y ; i: rows, C ; l: ldx, ldy ; f: eps
       return layer_norm_impl(p[0], l[0], i[0], i[1], f[0], (const float*)p[1], (const float*)p[2], (void*)p[3], l[1], st);
@@ -1034,6 +1113,15 @@ extern "C" int ldx_group_norm_cs(const void* x0, int c0, int64_t ld0, const void
   LDX_CHECK_ARG(colstats0 && slots0 >= 1 && (!x1 || (colstats1 && slots1 >= 1)), "group_norm_cs: missing column statistics");
   return group_norm_impl(x0, c0, ld0, x1, c1, ld1, B, HW, eps, gamma, beta, silu, y, ldy, stats, as_stream(stream),
                          colstats0, slots0, colstats1, slots1);
+}
+
+extern "C" int ldx_group_norm_coef(const void* x0, int c0, int64_t ld0, const void* x1, int c1, int64_t ld1, int B, int HW,
+                                   float eps, const float* gamma, const float* beta, float* stats, uint32_t* tickets,
+                                   float* coef, const float* colstats0, int slots0, const float* colstats1, int slots1,
+                                   ldx_stream_t stream) {
+  LDX_CHECK_ARG(coef && tickets, "group_norm_coef: null coefficient / ticket buffer");
+  return group_norm_impl(x0, c0, ld0, x1, c1, ld1, B, HW, eps, gamma, beta, 0, nullptr, 0, stats, as_stream(stream),
+                         colstats0, slots0, colstats1, slots1, coef, tickets);
 }
 
 extern "C" int ldx_layer_norm(const void* x, int64_t ldx_, int rows, int C, float eps, const float* gamma,

@@ -25,23 +25,9 @@
 
 #include <mutex>
 
-#include "common.cuh"
-#include "internal.h"
+#include "gemm_tile.cuh"
 
 namespace ldx {
-
-static constexpr int BM = 128;
-static constexpr int BK = 64;
-static constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
-static constexpr int EPI_GROUPS = 2;                          // epilogue warpgroups (4 warps = 128 TMEM lanes each)
-static constexpr int GEMM_THREADS = 64 + EPI_GROUPS * 128;   // warp 0 TMA, warp 1 MMA, then the epilogue groups
-static constexpr int MAX_STAGES = 6;
-
-static constexpr int EPI_CHUNK = 32;                         // output columns per TMEM load
-static constexpr int EPI_PASS = 64;                          // output columns per staged pass (one fence + one TMA store)
-static constexpr int EPI_SLOT_BYTES = 32 * EPI_PASS * 2;     // 4 KiB: one warp's 32 rows x 128 bytes, SWIZZLE_128B
-static constexpr int EPI_NSLOT = 2;                          // staging slots per epilogue warp
-static constexpr int EPI_SMEM = EPI_GROUPS * 4 * EPI_NSLOT * EPI_SLOT_BYTES;
 
 #ifdef LDX_GEMM_TIMING
 // Variant-build instrumentation: CTA 0 stamps %globaltimer at pipeline milestones (ns).
@@ -73,20 +59,6 @@ struct __align__(8) GemmBarriers {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
-
-// tile index -> (n tile, x / y / batch tile) with multiply-high instead of integer division (exact while
-// index * divisor < 2^32, far beyond any launch here); the divisions cost ~1000 cycles per tile and warp.
-template <int kCtas>
-__device__ __forceinline__ void tile_coords(const GemmKParams& p, int tile, int cta_rank, int& nt, int& tx, int& ty,
-                                            int& tb) {
-  const int mq = p.n_tiles == 1 ? tile : (int)__umulhi((uint32_t)tile, p.inv_n_tiles);
-  nt = tile - mq * p.n_tiles;
-  const int mt = mq * kCtas + cta_rank;
-  tb = p.tiles_x * p.tiles_y == 1 ? mt : (int)__umulhi((uint32_t)mt, p.inv_tiles_xy);
-  const int rem = mt - tb * (p.tiles_x * p.tiles_y);
-  ty = p.tiles_x == 1 ? rem : (int)__umulhi((uint32_t)rem, p.inv_tiles_x);
-  tx = rem - ty * p.tiles_x;
-}
 
 template <bool kGeglu, bool kOutF32>
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, uint32_t tmem_row_addr, int col, int n_glob,
@@ -797,7 +769,7 @@ static bool tma_ok_out_aligned(const ldx_gemm_desc_t* d) {
 // of a tile (~12 clocks per column, measured: 65536 x 320 x 1280 + residual lost 10 % at 7) is exposed instead of
 // hidden behind the next tile's main loop.
 static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas, int nk16, bool allow_dual, int* bn_out,
-                          int* ctas_out, int* nsub_out) {
+                          int* ctas_out, int* nsub_out, bool halo = false, int max_bn_cta = 256) {
   const bool geglu = (flags & LDX_EPI_GEGLU) != 0;
   double best_cost = 1e30;
   *bn_out = 128;
@@ -815,7 +787,9 @@ static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas
       const long long tiles = ((m_tiles + ctas - 1) / ctas) * n_tiles;
       const long long workers = sms / ctas;
       const double waves = (double)((tiles + workers - 1) / workers);
-      const double mma = bn / 2.0, fetch = (128 + bn / (double)ctas) * 0.52;
+      if (bn / ctas > max_bn_cta) continue;
+      // halo-tile convs fetch their A rows once per nine taps (x 1.4 for the halo): ~20 row-equivalents per K step
+      const double mma = bn / 2.0, fetch = ((halo ? 20 : 128) + bn / (double)ctas) * 0.52;
       const double per_k = mma > fetch ? mma : fetch;
       double cost = waves * (per_k + 6.0) * nk16;
       if (nsub == 2) cost = cost * 1.03 + waves * bn * 12.0;  // exposed epilogue; keep single-accumulator tiles on ties
@@ -832,7 +806,22 @@ static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas
 int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   LDX_CHECK_ARG(d && g, "null descriptor");
   LDX_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= LDX_MAX_SRC, "nsrc %d out of range", d->nsrc);
-  LDX_CHECK_ARG(d->nseg >= 1 && d->nseg <= LDX_MAX_SEG, "nseg %d out of range", d->nseg);
+  const bool halo = d->halo_nsrc > 0;
+  LDX_CHECK_ARG(d->nseg >= (halo ? 0 : 1) && d->nseg <= LDX_MAX_SEG, "nseg %d out of range", d->nseg);
+  LDX_CHECK_ARG(halo || !d->gn_coef, "gn_coef needs the halo-tile conv (halo_nsrc > 0)");
+  if (halo) {
+    LDX_CHECK_ARG(d->halo_nsrc <= 2 && d->halo_nsrc <= d->nsrc, "halo_nsrc %d out of range", d->halo_nsrc);
+    LDX_CHECK_ARG(d->W % 8 == 0, "halo conv: W = %d must be a multiple of 8", d->W);
+    LDX_CHECK_ARG(!(d->flags & (LDX_EPI_GEGLU | LDX_EPI_ROWNORM | LDX_EPI_OUT_F32)) && !d->rowstats_out,
+                  "halo conv: fp16 output, no GEGLU / ROWNORM / rowstats_out");
+    for (int i = 0; i < d->halo_nsrc; ++i) {
+      LDX_CHECK_ARG(d->src[i].W == d->W && d->src[i].H == d->H && d->src[i].B == d->B && d->src[i].C % 8 == 0,
+                    "halo conv: source %d must cover the output domain (stride 1) with C %% 8 == 0", i);
+      LDX_CHECK_ARG(i == d->halo_nsrc - 1 || d->src[i].C % 64 == 0, "halo conv: source %d needs C %% 64 == 0", i);
+    }
+    LDX_CHECK_ARG(!d->gn_coef || (reinterpret_cast<uintptr_t>(d->gn_coef) % 16 == 0 && d->gn_ctot % 8 == 0),
+                  "halo conv: gn_coef alignment");
+  }
   LDX_CHECK_ARG(d->N >= 1 && d->W >= 1 && d->H >= 1 && d->B >= 1, "bad output extents");
   LDX_CHECK_ARG(d->w && d->out, "null weight/output pointer");
   GemmKParams& p = g->p;
@@ -840,7 +829,9 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
 
   // tile geometry: 128 output pixels = bw x bh x bb
   int bw, bh, bb;
-  if (d->H == 1 && d->B == 1) {
+  if (halo) {
+    bw = 8; bh = 16; bb = 1;                     // 8-pixel row groups: the unit a shifted tap view can step by
+  } else if (d->H == 1 && d->B == 1) {
     bw = 128; bh = 1; bb = 1;
   } else {
     int div = 1;
@@ -879,13 +870,16 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   // and applies the epilogue.
   int k_chunks = 0;
   for (int s = 0; s < d->nseg; ++s) k_chunks += d->seg[s].nchunks;
+  int halo_chunks = 0;                                          // 64-channel chunks of the halo sources
+  for (int i = 0; i < d->halo_nsrc; ++i) halo_chunks += (d->src[i].C + 63) / 64;
+  k_chunks += 9 * halo_chunks;
   int nsplit = 1;
   {
     static int split_env = -1;
     if (split_env < 0) { const char* e = getenv("LDX_GEMM_SPLITK"); split_env = e ? atoi(e) : 1; }
     const int pair_tiles = ((m_tiles + 1) / 2) * ((d->N + 255) / 256);
     const int workers2 = sms / 2;
-    const bool eligible = split_env && d->bn == 0 && osz == 2 && !(d->flags & (LDX_EPI_GEGLU | LDX_EPI_ROWNORM)) &&
+    const bool eligible = split_env && !halo && d->bn == 0 && osz == 2 && !(d->flags & (LDX_EPI_GEGLU | LDX_EPI_ROWNORM)) &&
                           !d->rowstats_out && !d->colstats_out && d->N % 8 == 0 && d->N >= 256 && tma_ok_out_aligned(d) &&
                           (!d->residual || ((reinterpret_cast<uintptr_t>(d->residual) % 8 == 0) && d->ldr % 4 == 0)) &&
                           (!d->bias || reinterpret_cast<uintptr_t>(d->bias) % 16 == 0);
@@ -908,11 +902,12 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     ctas = 2;
   } else if (bn == 0) {
     // two-accumulator tiles need the TMA-store epilogue (fp16 output): the direct-store path walks 32-column chunks
-    choose_config(d->N, m_tiles, d->flags, sms, force_ctas, nk16, dual_env != 0 && tma_ok, &bn, &ctas, &nsub);
+    choose_config(d->N, m_tiles, d->flags, sms, force_ctas, nk16, dual_env != 0 && tma_ok, &bn, &ctas, &nsub, halo && getenv("LDX_HALO_COST") != nullptr);
   } else {
     int bn_unused, nsub_unused;
     choose_config(d->N, m_tiles, d->flags, sms, force_ctas, nk16, false, &bn_unused, &ctas, &nsub_unused);
     if (ctas == 2 && bn < 64) ctas = 1;
+    if (bn > 256) { ctas = 2; nsub = 2; }       // explicit two-accumulator tile (experiments / tests)
   }
   g->ctas = ctas;
   LDX_CHECK_ARG(bn >= 32 && bn <= (nsub == 2 ? 512 : 256) && bn % 32 == 0, "bn %d must be a multiple of 32 in [32,256]", bn);
@@ -937,6 +932,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.acc_stride = (uint32_t)pow2_ceil(bn < 32 ? 32 : bn);
   p.tmem_cols = p.single_acc ? (uint32_t)pow2_ceil(bn) : 2 * p.acc_stride;
 
+  LDX_CHECK_ARG(!halo || tma_ok, "halo conv: the output needs TMA-compatible strides (fp16, 16-byte aligned)");
   int nk = 0;
   for (int s = 0; s < d->nseg; ++s) {
     const ldx_seg_t& sg = d->seg[s];
@@ -946,8 +942,10 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     nk += sg.nchunks;
   }
   p.nseg = d->nseg;
-  LDX_CHECK_ARG(d->ldw >= (int64_t)nk * BK, "weight pitch %lld < K %d", (long long)d->ldw, nk * BK);
-  const int k_weights = nk;                   // K steps that read the weight matrix
+  LDX_CHECK_ARG(d->ldw >= (int64_t)(nk + 9 * halo_chunks) * BK, "weight pitch %lld < K %d", (long long)d->ldw,
+                (nk + 9 * halo_chunks) * BK);
+  const int k_weights = nk + 9 * halo_chunks;  // K steps that read the weight matrix
+  nk += halo_chunks;                           // pipeline items per tile: a halo chunk is one item of nine taps
   p.diag_src = 0;
   // ceil(bn / 64) identity steps: I's rows stop at bn, so the columns past bn of the last step add nothing
   p.diag_chunks = fuse_res ? (bn + 63) / 64 : 0;
@@ -960,6 +958,30 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   }
 
   const uint32_t b_stage = (uint32_t)(bn / ctas) * BK * 2;
+  g->halo = halo ? 1 : 0;
+  if (halo) {
+    p.halo_nsrc = d->halo_nsrc;
+    p.halo_cp = halo_chunks * BK;
+    int coff = 0;
+    for (int i = 0; i < d->halo_nsrc; ++i) {
+      const ldx_src_t& s = d->src[i];
+      p.halo_nch[i] = (s.C + 63) / 64;
+      p.halo_coff[i] = coff;
+      p.halo_c[i] = s.C;
+      coff += p.halo_nch[i] * BK;
+      const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)s.B};
+      const uint64_t str[3] = {(uint64_t)s.sw * 2, (uint64_t)s.sh * 2, (uint64_t)s.sb * 2};
+      const uint32_t box[4] = {(uint32_t)BK, 10u, 18u, 1u};
+      int rc = encode_map_f16(&p.hmap[i], s.ptr, 4, dims, str, box);
+      if (rc) return rc;
+    }
+    for (int i = d->halo_nsrc; i < 2; ++i) p.hmap[i] = p.hmap[0];
+    p.gn_coef = d->gn_coef;
+    p.gn_ctot = d->gn_ctot;
+    p.gn_silu = d->gn_silu;
+    LDX_CHECK_ARG(!d->gn_coef || d->gn_ctot >= coff - (p.halo_nch[d->halo_nsrc - 1] * BK - p.halo_c[d->halo_nsrc - 1]),
+                  "halo conv: gn_ctot %d smaller than the concatenated channels", d->gn_ctot);
+  }
   int stages = (int)((224 * 1024 - EPI_SMEM - 2048) / (A_STAGE_BYTES + b_stage));
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   {
@@ -971,6 +993,10 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.stages = stages;
   g->smem_bytes = stages * (A_STAGE_BYTES + (int)b_stage) + EPI_SMEM + (int)sizeof(GemmBarriers) + 1024;
   if (g->smem_bytes < 120 * 1024) g->smem_bytes = 120 * 1024;   // keep one CTA per SM: it owns up to all of TMEM
+  if (halo) {
+    g->smem_bytes = conv_halo_smem_bytes(bn / ctas, &p.na_stages, &p.nb_stages);
+    LDX_CHECK_ARG(g->smem_bytes > 0, "halo conv: bn %d does not fit the operand rings", bn);
+  }
   {
     const int workers = sms / ctas;
     g->grid = ctas * (p.num_tiles < workers ? p.num_tiles : workers);
@@ -1152,6 +1178,7 @@ int gemm_launch(const GemmLaunch* g, cudaStream_t stream) {
     set_error("split-K GEMM launched without a workspace");
     return LDX_E_INVALID;
   }
+  if (g->halo) return conv_halo_launch(g, stream);
   int rc = g->ctas == 2 ? gemm_launch_c<2>(g, stream) : gemm_launch_c<1>(g, stream);
   if (rc || g->nsplit == 1) return rc;
   const int64_t vecs = (int64_t)g->red.M * (g->red.N >> 2);

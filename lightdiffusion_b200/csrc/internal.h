@@ -131,6 +131,15 @@ struct alignas(64) GemmKParams {
   int32_t cs_slots, cs_slot_base, cs_wps;   // cs_wps: 32-row blocks of one batch element inside a 128-row tile
   int32_t vec_ok;   // 16-byte vector epilogue allowed (direct-store path)
   int32_t tma_epi;  // 1: stage 32-column chunks in smem and TMA-store them (fp16 outputs)
+  // ---- halo-tile 3x3 conv (conv_halo.cu): the conv's K axis is halo_nsrc sources x 64-channel chunks, each chunk
+  // ONE (64, 10, 18, 1) box whose nine tap views the MMA reads through shifted descriptors; seg[] then holds only the
+  // trailing 1x1 K segments (weight columns from 9 * halo_cp on)
+  CUtensorMap hmap[2];
+  int32_t halo_nsrc, halo_cp;       // halo_cp: weight columns per tap (sum of the sources' padded channel counts)
+  int32_t halo_nch[2], halo_coff[2], halo_c[2];   // chunks, first weight / coefficient column, real channels per source
+  int32_t na_stages, nb_stages;
+  const float* gn_coef;             // [B][gn_ctot][2] (scale, shift) or null: GroupNorm (+SiLU) applied to the landed tile
+  int32_t gn_ctot, gn_silu;
 };
 
 // second launch of a split-K GEMM: out = act(sum_s partial[s] + bias + rowadd + residual) as fp16
@@ -154,6 +163,7 @@ struct GemmLaunch {
   int grid;
   int smem_bytes;
   int ctas;      // 1, or 2 = CTA-pair kernel (cluster of 2, tcgen05 cta_group::2)
+  int halo = 0;               // 1: conv_halo.cu kernel (3x3 conv from halo tiles)
   int nsplit = 1;             // > 1: split-K, two launches (GEMM into the workspace, then SplitReduce)
   size_t ws_bytes = 0;        // fp32 workspace the caller must bind with gemm_bind_workspace()
   SplitReduce red;
@@ -162,6 +172,10 @@ void gemm_bind_workspace(GemmLaunch* g, void* ws);
 
 int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* out);
 int gemm_launch(const GemmLaunch* g, cudaStream_t stream);
+int conv_halo_launch(const GemmLaunch* g, cudaStream_t stream);     // conv_halo.cu
+int conv_halo_smem_bytes(int bn_cta, int* na, int* nb);              // ring depths that fit; total dynamic smem
+int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
 
 int run_generic_op(const ldx_generic_op_t* op, cudaStream_t stream);
 

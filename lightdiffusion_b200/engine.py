@@ -54,6 +54,12 @@ CONV_SMALL = os.environ.get("LDX_CONV_SMALL", "1") == "1"
 # statistics passes read 0.27-0.54 GB maps from HBM), the SD1.5 UNet at 64x64 does not (15.54 -> 15.65 ms: its 21-42 MB
 # maps are still in L2 when the 10 us statistics pass reads them, and the epilogue work costs the GEMMs as much as it
 # saves).  Hence the threshold: maps of at least GN_STATS_MIN_HW pixels per sample (LDX_GN_STATS_MIN_HW overrides).
+# ResBlock convs (GroupNorm -> SiLU -> 3x3 conv, LD.py:5220-5261 / 3562-3576) on maps of at least HALO_MIN_HW pixels
+# run as the halo-tile conv with the normalisation applied in its operand path (csrc/conv_halo.cu): the GroupNorm
+# becomes a statistics-only launch (ldx_group_norm_coef) and its apply pass (one read + one write of the map)
+# disappears.  LDX_HALO=0 keeps the two-pass GroupNorm + implicit-GEMM conv everywhere (A/B).
+HALO = os.environ.get("LDX_HALO", "1") == "1"
+HALO_MIN_HW = int(os.environ.get("LDX_HALO_MIN_HW", "256"))
 FUSE_GN_STATS = os.environ.get("LDX_FUSE_GN_STATS", "1") == "1"
 GN_STATS_MIN_HW = int(os.environ.get("LDX_GN_STATS_MIN_HW", "16384"))
 
@@ -121,6 +127,7 @@ class _GnStatsMixin:
     def _init_gn_stats(self):
         self._cs: Dict[int, tuple] = {}          # output address -> (partials [B, slots, C, 2], slots, pooled buffer)
         self.pool.on_recycle = self._drop_stats
+        self.tickets = torch.zeros(max(self.B, 1), dtype=torch.int32, device=self.pool.device)
 
     def _drop_stats(self, ptr: int):
         e = self._cs.pop(ptr, None)
@@ -149,6 +156,20 @@ class _GnStatsMixin:
                     slots, view = total, raw.view(Bn, total, c, 2)
                 self._cs[out.data_ptr()] = (view, slots, raw)
         self.prog.add(descs)
+
+    def _gn_coef(self, x0, x1, g, b, eps):
+        """Statistics-only GroupNorm of [x0 | x1]: per-(sample, channel) (scale, shift) for a halo conv's operand path."""
+        c = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
+        cs = self._colstats(x0, x1)
+        coef = self.pool.alloc(x0.shape[0], c, 2, dtype=F32)
+        self.prog.add(K.group_norm_coef_op(x0, x1, g, b, coef, self.stats, self.tickets, eps, colstats=cs))
+        return coef
+
+    @staticmethod
+    def _use_halo(x0, x1):
+        _, h, w, c0 = x0.shape
+        return (HALO and h * w >= HALO_MIN_HW and w % 8 == 0 and h % 16 == 0 and c0 % 8 == 0 and
+                (x1 is None or (c0 % 64 == 0 and x1.shape[-1] % 8 == 0)))
 
     def _colstats(self, x0, x1):
         a = self._cs.get(x0.data_ptr())
@@ -343,6 +364,8 @@ class UNetPlan(_GnStatsMixin):
     def _res(self, s: ResSpec, x0, x1):
         eng, w, p = self.eng, self.eng.w, s.name
         Bn, h, wd, _ = x0.shape
+        if self._use_halo(x0, x1):
+            return self._res_halo(s, x0, x1)
         y = self._gn(x0, x1, w[p + ".gn1.g"], w[p + ".gn1.b"], 1e-5, True)
         h1 = self.pool.alloc(Bn, h, wd, s.cout)
         off = eng.emb_off[p]
@@ -367,6 +390,31 @@ class UNetPlan(_GnStatsMixin):
             d = K.gemm_desc(srcs, segs, w[p + ".conv2.w"], out, s.cout, bias=w[p + ".conv2.b"])
         self._produce(d, out)
         self.pool.free(y2)
+        return out
+
+    def _res_halo(self, s: ResSpec, x0, x1):
+        """ResBlock1 with both GroupNorm + SiLU applications inside the convs' operand paths: two statistics launches
+        and two halo-tile convs; the normalised maps never exist in HBM."""
+        eng, w, p, pool = self.eng, self.eng.w, s.name, self.pool
+        Bn, h, wd, c0 = x0.shape
+        xs = [x0] + ([x1] if x1 is not None else [])
+        coef1 = self._gn_coef(x0, x1, w[p + ".gn1.g"], w[p + ".gn1.b"], 1e-5)
+        h1 = pool.alloc(Bn, h, wd, s.cout)
+        off = eng.emb_off[p]
+        self._produce(K.conv3x3_halo_desc(xs, w[p + ".conv1.w"], h1, gn=(coef1, True), bias=w[p + ".conv1.b"],
+                                          rowadd=self.emb_out[:, off:off + s.cout]), h1)
+        pool.free(coef1)
+        coef2 = self._gn_coef(h1, None, w[p + ".gn2.g"], w[p + ".gn2.b"], 1e-5)
+        out = pool.alloc(Bn, h, wd, s.cout)
+        if s.cin == s.cout:
+            assert x1 is None
+            d = K.conv3x3_halo_desc([h1], w[p + ".conv2.w"], out, gn=(coef2, True), bias=w[p + ".conv2.b"], residual=x0)
+        else:
+            segs = [(i, 0, 0, 0, K.ceil64(t.shape[-1]) // 64) for i, t in enumerate(xs)]
+            d = K.conv3x3_halo_desc([h1], w[p + ".conv2.w"], out, gn=(coef2, True), bias=w[p + ".conv2.b"],
+                                    extra_srcs=xs, extra_segs=segs)
+        self._produce(d, out)
+        pool.free(coef2); pool.free(h1)
         return out
 
     def _rowstats(self, d, rows: int, slot: int):
@@ -735,6 +783,22 @@ class VAEPlan(_GnStatsMixin):
     def _res(self, p, x, cin, cout):
         w, pool, prog = self.eng.w, self.pool, self.prog
         Bn, h, wd, _ = x.shape
+        if self._use_halo(x, None):
+            # ResnetBlock (LD.py:3562-3576) with the two GroupNorm + SiLU applications in the convs' operand paths
+            coef1 = self._gn_coef(x, None, w[p + ".gn1.g"], w[p + ".gn1.b"], 1e-6)
+            h1 = pool.alloc(Bn, h, wd, cout)
+            self._produce(K.conv3x3_halo_desc([x], w[p + ".conv1.w"], h1, gn=(coef1, True), bias=w[p + ".conv1.b"]), h1)
+            pool.free(coef1)
+            coef2 = self._gn_coef(h1, None, w[p + ".gn2.g"], w[p + ".gn2.b"], 1e-6)
+            out = pool.alloc(Bn, h, wd, cout)
+            if cin == cout:
+                d = K.conv3x3_halo_desc([h1], w[p + ".conv2.w"], out, gn=(coef2, True), bias=w[p + ".conv2.b"], residual=x)
+            else:
+                d = K.conv3x3_halo_desc([h1], w[p + ".conv2.w"], out, gn=(coef2, True), bias=w[p + ".conv2.b"],
+                                        extra_srcs=[x], extra_segs=[(0, 0, 0, 0, K.ceil64(cin) // 64)])
+            self._produce(d, out)
+            pool.free(coef2); pool.free(h1); pool.free(x)
+            return out
         cs = self._colstats(x, None)
         y = pool.alloc(Bn, h, wd, cin)
         prog.add(K.group_norm_op(x, None, w[p + ".gn1.g"], w[p + ".gn1.b"], y, self.stats, 1e-6, True, colstats=cs))

@@ -192,6 +192,32 @@ def conv3x3_desc(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, **kw) -> 
     return gemm_desc([x], segs, wp, out, wp.shape[0], **kw)
 
 
+def conv3x3_halo_desc(xs: Sequence[torch.Tensor], wp: torch.Tensor, out: torch.Tensor, gn: Optional[tuple] = None,
+                      extra_srcs: Sequence[torch.Tensor] = (), extra_segs: Sequence[tuple] = (), **kw) -> L.GemmDesc:
+    """3x3 stride-1 pad-1 conv over the channel concat of ``xs`` (one or two [B,H,W,C_i] tensors) in the halo-tile
+    form (ldx_gemm_desc_t.halo_nsrc): every 64-channel chunk is fetched once as a 10 x 18 halo tile and read by all
+    nine taps.  wp: pack_conv3x3 of the conv weight over the concatenated channels, optionally followed by the columns
+    of extra 1x1 K segments (``extra_srcs`` / ``extra_segs`` = (index into extra_srcs, c0, dx, dy, nchunks)).
+    gn = (coef [B, Ctot, 2] fp32 from group_norm_coef_op, silu): GroupNorm (+ SiLU) applied to the landed tiles."""
+    assert 1 <= len(xs) <= 2
+    srcs = list(xs) + list(extra_srcs)
+    segs = [(len(xs) + si, c0, dx, dy, nch) for (si, c0, dx, dy, nch) in extra_segs]
+    d = gemm_desc(srcs, segs, wp, out, wp.shape[0], **kw)
+    d.halo_nsrc = len(xs)
+    if gn is not None:
+        coef, silu = gn
+        ctot = sum(t.shape[-1] for t in xs)
+        assert coef.dtype == torch.float32 and coef.is_contiguous() and tuple(coef.shape) == (xs[0].shape[0], ctot, 2)
+        d.gn_coef, d.gn_ctot, d.gn_silu = coef.data_ptr(), ctot, int(bool(silu))
+    return d
+
+
+def halo_ok(x: torch.Tensor, out: torch.Tensor) -> bool:
+    """Shapes the halo-tile conv serves well: 8 x 16-pixel tiles that the map fills (W % 8 == 0, H % 16 == 0)."""
+    _, h, w, _ = x.shape
+    return w % 8 == 0 and h % 16 == 0 and out.dtype == torch.float16 and out.stride(2) % 8 == 0
+
+
 def conv3x3_s2_desc(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, pad_end: bool = False, **kw) -> L.GemmDesc:
     """3x3 stride-2 conv via four parity-strided views of x: pad 1 on every side (Downsample1, LD.py:5173-5186) or,
     with ``pad_end``, the VAE encoder's F.pad(x, (0,1,0,1)) + padding-0 conv (Downsample, LD.py:3514-3528), where
@@ -339,6 +365,30 @@ def group_norm_op(x0, x1, gamma, beta, y, stats, eps: float, silu: bool, colstat
                       l=[x0.stride(2), 0 if x1 is None else x1.stride(2), y.stride(2)], f=[eps])
 
 
+def group_norm_coef_op(x0, x1, gamma, beta, coef, stats, tickets, eps: float, colstats=None) -> L.GenericOp:
+    """GroupNorm statistics of x0 (and optional x1, channel-concatenated) as per-(sample, channel) coefficients
+    coef [B, C0+C1, 2] fp32 = (rstd * gamma, beta - mean * rstd * gamma) for conv3x3_halo_desc(gn=...): the normalisation
+    itself happens in the consuming conv's operand path.  tickets: B zero-initialised int32 (left zeroed)."""
+    b, h, w, c0 = x0.shape
+    assert x0.stride(1) == x0.stride(2) * w and x0.stride(0) == x0.stride(1) * h
+    c1 = 0 if x1 is None else x1.shape[-1]
+    assert stats.numel() >= b * L.GN_STATS_FLOATS_PER_BATCH and stats.dtype == torch.float32
+    assert coef.dtype == torch.float32 and coef.is_contiguous() and tuple(coef.shape) == (b, c0 + c1, 2)
+    assert tickets.dtype == torch.int32 and tickets.numel() >= b
+    cs0 = cs1 = None
+    s0 = s1 = 0
+    if colstats is not None and colstats[0] is not None and (x1 is None or colstats[1] is not None):
+        (cs0, s0) = colstats[0]
+        assert tuple(cs0.shape) == (b, s0, c0, 2) and cs0.dtype == torch.float32 and cs0.is_contiguous()
+        if x1 is not None:
+            (cs1, s1) = colstats[1]
+            assert tuple(cs1.shape) == (b, s1, c1, 2) and cs1.dtype == torch.float32 and cs1.is_contiguous()
+    return generic_op(L.OP_GROUP_NORM_COEF, p=[x0.data_ptr(), _ptr(x1), gamma.data_ptr(), beta.data_ptr(), coef.data_ptr(),
+                                               stats.data_ptr(), _ptr(cs0), _ptr(cs1), tickets.data_ptr()],
+                      i=[c0, c1, b, h * w, 0, s0, s1],
+                      l=[x0.stride(2), 0 if x1 is None else x1.stride(2)], f=[eps])
+
+
 def layer_norm_op(x2, gamma, beta, y2, eps=1e-5) -> L.GenericOp:
     rows, c = x2.shape
     return generic_op(L.OP_LAYER_NORM, p=[x2.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y2.data_ptr()],
@@ -376,6 +426,7 @@ class Program:
         if isinstance(op, L.GemmDesc):
             L.check(L.lib().ldx_program_add_gemm(self._h, C.byref(op)), "ldx_program_add_gemm")
             k = 64 * sum(op.seg[i].nchunks for i in range(op.nseg))
+            k += 9 * sum(ceil64(op.src[i].C) for i in range(op.halo_nsrc))
             self.meta.append(("gemm", 2.0 * op.W * op.H * op.B * op.N * k, (op.W * op.H * op.B, op.N, k)))
         elif isinstance(op, (list, tuple)):
             for o in op:
@@ -389,11 +440,12 @@ class Program:
             elif op.kind == L.OP_CONV_SMALL:
                 b, h, w, cin, cout = (op.i[j] for j in range(5))
                 flops, tag = 2.0 * b * h * w * 9 * cin * cout, (b * h * w, cout, 9 * cin)
-            elif op.kind == L.OP_GROUP_NORM:
+            elif op.kind in (L.OP_GROUP_NORM, L.OP_GROUP_NORM_COEF):
                 tag = (op.i[2], op.i[3], op.i[0] + op.i[1])         # B, HW, C
             elif op.kind == L.OP_LAYER_NORM:
                 tag = (op.i[0], op.i[1])                            # rows, C
             self.meta.append(({L.OP_ATTENTION: "attention", L.OP_GROUP_NORM: "group_norm",
+                               L.OP_GROUP_NORM_COEF: "group_norm",
                                L.OP_LAYER_NORM: "layer_norm", L.OP_CONV_SMALL: "conv_small"}.get(op.kind, "other"),
                               flops, tag))
         self._keep.extend(keep)
