@@ -77,7 +77,9 @@ LDX_DEVICE void halo_for_each_item(const GemmKParams& p, int nt, F&& f) {
   for (int dk = 0; dk < p.diag_chunks; ++dk) f(2, p.diag_src, nt * p.bn + dk * BK, 0, 0, dk * BK, 1, 0);
 }
 
-template <int kCtas, bool kColstats>
+// kStats: 0 none, 1 GroupNorm column statistics of the produced tile (colstats_out), 2 LayerNorm row statistics
+// (rowstats_out, for a LayerNorm folded into the consuming GEMM)
+template <int kCtas, int kStats>
 __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __grid_constant__ GemmKParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -171,21 +173,23 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
       const int n0 = nt * p.bn + (int)cta_rank * sub_rows;
       halo_for_each_item(p, nt, [&](int kind, int, int, int, int, int kcol, int ntaps, int) {
         const CUtensorMap* bm = kind == 2 ? &p.idmap : &p.bmap;
-        const int brow = kind == 2 ? (int)cta_rank * sub_rows : n0;
+        const bool d64 = kind == 2 && p.diag64;            // 64 x 64 identity block (see gemm.cu)
+        const int brow = d64 ? (int)cta_rank * (64 / kCtas) : kind == 2 ? (int)cta_rank * sub_rows : n0;
+        const uint32_t bbytes = d64 ? (uint32_t)(64 / kCtas) * BK * 2 : b_stage_bytes;
         for (int t = 0; t < ntaps; ++t) {
-          const int bk = kind == 0 ? t * p.halo_cp + kcol : kcol;
+          const int bk = kind == 0 ? t * p.halo_cp + kcol : d64 ? 0 : kcol;
           mbar_wait(&bars->b_empty[stage], phase ^ 1);
           uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
           if constexpr (kCtas == 2) {
             const uint32_t lbar = mapa_shared(smem_u32(&bars->b_full[stage]), 0);
             if (elect_one()) {
-              if (cta_rank == 0) mbar_arrive_expect_tx(&bars->b_full[stage], 2 * b_stage_bytes);
+              if (cta_rank == 0) mbar_arrive_expect_tx(&bars->b_full[stage], 2 * bbytes);
               tma_load_2d_pair(dB, bm, lbar, bk, brow);
-              if (nsub == 2) tma_load_2d_pair(dB + b_sub_bytes, bm, lbar, bk, brow + sub_step);
+              if (nsub == 2 && !d64) tma_load_2d_pair(dB + b_sub_bytes, bm, lbar, bk, brow + sub_step);
             }
           } else {
             if (elect_one()) {
-              mbar_arrive_expect_tx(&bars->b_full[stage], b_stage_bytes);
+              mbar_arrive_expect_tx(&bars->b_full[stage], bbytes);
               tma_load_2d(dB, bm, &bars->b_full[stage], bk, brow);
             }
           }
@@ -198,6 +202,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
     // ------------------------------------------------------------------ MMA issuer (leader CTA)
     if (cta_rank == 0) {
       const uint32_t idesc = umma_idesc_f16(BM * kCtas, p.bn / nsub);
+      const uint32_t idesc64 = umma_idesc_f16(BM * kCtas, 64);
       const uint32_t sub_cols = (uint32_t)(p.bn / nsub);
       int astage = 0, bstage = 0;
       uint32_t aphase = 0, bphase = 0;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
         const uint32_t d_tmem = tmem_base + as * p.acc_stride;
         int items_left = p.nk;                      // items of this tile (halo chunks + plain steps + identity steps)
         uint32_t acc = 0;
-        halo_for_each_item(p, 0, [&](int kind, int, int, int, int, int, int ntaps, int) {
+        halo_for_each_item(p, 0, [&](int kind, int, int, int, int, int kcol, int ntaps, int) {
           mbar_wait(&bars->a_ready[astage], aphase);
           tc_fence_after();
           --items_left;
@@ -222,6 +227,15 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
             const uint32_t sbo = kind == 0 ? (uint32_t)HALO_W * 128u : 1024u;
             const uint32_t b_addr = smem_u32(sB + (size_t)bstage * b_stage_bytes);
             if (elect_one()) {
+              if (kind == 2 && p.diag64) {
+                const uint32_t dcol = d_tmem + (uint32_t)kcol;      // kcol = 64 * (identity step index)
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  const uint64_t ad = umma_desc_kmajor_sw128(a_addr + k * 32), bd = umma_desc_kmajor_sw128(b_addr + k * 32);
+                  if constexpr (kCtas == 2) umma_f16_ss_pair(dcol, ad, bd, idesc64, 1u);
+                  else umma_f16_ss(dcol, ad, bd, idesc64, 1u);
+                }
+              } else
 #pragma unroll
               for (int k = 0; k < BK / 16; ++k) {
                 const uint64_t ad = umma_desc_kmajor_sw128_sbo(a_addr + k * 32, sbo);
@@ -262,10 +276,40 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
       int nt, tx, ty, tb;
       tile_coords<kCtas>(p, tile, (int)cta_rank, nt, tx, ty, tb);
       const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb;
-      halo_for_each_item(p, nt, [&](int kind, int, int c0, int, int, int kcol, int, int src) {
+      halo_for_each_item(p, nt, [&](int kind, int map, int c0, int, int, int kcol, int, int src) {
         mbar_wait(&bars->a_full[stage], phase);
         const int cch = c0 + chunk * 8;            // first channel (inside the source) of this thread's piece
-        if (kind == 0 && p.gn_coef != nullptr && b0 < p.B && cch < p.halo_c[src]) {
+        if (kind == 1 && map == 0 && p.halo_nsrc == 0 && p.gn_coef != nullptr && b0 < p.B && cch < p.halo_c[0]) {
+          // normalised 1x1 conv: the plain 128-pixel tile [16 rows][8 pixels] of source 0
+          float sc[8], sh[8];
+          {
+            const float4* cf = reinterpret_cast<const float4*>(p.gn_coef + ((int64_t)b0 * p.gn_ctot + cch) * 2);
+            const float4 q0 = __ldg(cf), q1 = __ldg(cf + 1), q2 = __ldg(cf + 2), q3 = __ldg(cf + 3);
+            sc[0] = q0.x; sh[0] = q0.y; sc[1] = q0.z; sh[1] = q0.w; sc[2] = q1.x; sh[2] = q1.y; sc[3] = q1.z; sh[3] = q1.w;
+            sc[4] = q2.x; sh[4] = q2.y; sc[5] = q2.z; sh[5] = q2.w; sc[6] = q3.x; sh[6] = q3.y; sc[7] = q3.z; sh[7] = q3.w;
+          }
+          uint8_t* slot = sA + (size_t)stage * HA_STAGE_BYTES;
+          const bool do_silu = p.gn_silu != 0;
+#pragma unroll 4
+          for (int i = 0; i < BM * 8 / XF_THREADS; ++i) {
+            const int pix = (t + XF_THREADS * i) >> 3;
+            if (y0 + (pix >> 3) < p.H) {             // rows past the image stay zero (never stored)
+              uint4* ptr = reinterpret_cast<uint4*>(slot + pix * 128 + ((chunk ^ (pix & 7)) << 4));
+              const uint4 vv = *ptr;
+              const float2 f0 = unpack_h2(vv.x), f1 = unpack_h2(vv.y), f2 = unpack_h2(vv.z), f3 = unpack_h2(vv.w);
+              float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                f[j] = fmaf(f[j], sc[j], sh[j]);
+                if (do_silu) f[j] = silu_f(f[j]);
+              }
+              uint4 o;
+              o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+              *ptr = o;
+            }
+          }
+          fence_proxy_async_smem();
+        } else if (kind == 0 && p.gn_coef != nullptr && b0 < p.B && cch < p.halo_c[src]) {
           float sc[8], sh[8];
           {
             const float4* cf = reinterpret_cast<const float4*>(p.gn_coef + ((int64_t)b0 * p.gn_ctot + kcol + chunk * 8) * 2);
@@ -349,10 +393,15 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
         tc_fence_before();
         __syncwarp();
         if (lane == 0) release_tmem(as);
+        if (kStats == 2 && valid)
+          *reinterpret_cast<float2*>(p.rowstats_out + ((((int64_t)b * p.H + y) * p.W + x) * (p.n_tiles * EPI_GROUPS) + nt * EPI_GROUPS + grp) * 2) = make_float2(0.f, 0.f);
         continue;
       }
+      float rs1 = 0.f, rs2 = 0.f;               // row statistics of this warp's output columns
+      const int64_t m_lin = ((int64_t)b * p.H + y) * p.W + x;
+      const int rs_parts = p.n_tiles * EPI_GROUPS;
       int64_t cs_base = -1;
-      if constexpr (kColstats) {
+      if constexpr (kStats == 1) {
         const int cs_slot = p.cs_slot_base + (ty * p.tiles_x + tx) * p.cs_wps + q;
         if (b0 < p.B) cs_base = ((int64_t)b0 * p.cs_slots + cs_slot) * p.N;
       }
@@ -410,6 +459,11 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
               for (int j = 0; j < 32; ++j) v[j] = sigmoid_gate_f(v[j], nk);
             }
           }
+          if constexpr (kStats == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n_glob + j < n_out_total) { rs1 += v[j]; rs2 = fmaf(v[j], v[j], rs2); }
+          }
           uint8_t* srow = wide ? cbuf + lane * 128 : cbuf + lane * 64;
           const int sw = wide ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
@@ -422,7 +476,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
             *reinterpret_cast<uint4*>(srow + (((half * 4 + ch) ^ sw) << 4)) = o;
           }
         }
-        if constexpr (kColstats) {
+        if constexpr (kStats == 1) {
           __syncwarp();
           const uint32_t vm = __ballot_sync(0xffffffffu, valid);
           const int col = n_out0 + ps * EPI_PASS + 2 * lane;
@@ -449,6 +503,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
           tma_store_commit();
         }
       }
+      if (kStats == 2 && valid)
+        *reinterpret_cast<float2*>(p.rowstats_out + (m_lin * rs_parts + nt * EPI_GROUPS + grp) * 2) = make_float2(rs1, rs2);
     }
     if (elected) tma_store_wait_all();
   }
@@ -463,20 +519,21 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
   }
 }
 
-template <int kCtas, bool kColstats>
+template <int kCtas, int kStats>
 static int conv_halo_launch_t(const GemmLaunch* g, cudaStream_t stream) {
   static std::atomic<uint64_t> attr_done{0};
-  int arc = set_max_dyn_smem_once(ldx_conv_halo_kernel<kCtas, kColstats>, 227 * 1024, attr_done);
+  int arc = set_max_dyn_smem_once(ldx_conv_halo_kernel<kCtas, kStats>, 227 * 1024, attr_done);
   if (arc) return arc;
-  LDX_CUDA(launch_k(ldx_conv_halo_kernel<kCtas, kColstats>, dim3(g->grid), dim3(HALO_THREADS), (size_t)g->smem_bytes, stream,
+  LDX_CUDA(launch_k(ldx_conv_halo_kernel<kCtas, kStats>, dim3(g->grid), dim3(HALO_THREADS), (size_t)g->smem_bytes, stream,
                     kCtas, g->p));
   return LDX_OK;
 }
 
 int conv_halo_launch(const GemmLaunch* g, cudaStream_t stream) {
-  const bool cs = g->p.colstats_out != nullptr;
-  if (g->ctas == 2) return cs ? conv_halo_launch_t<2, true>(g, stream) : conv_halo_launch_t<2, false>(g, stream);
-  return cs ? conv_halo_launch_t<1, true>(g, stream) : conv_halo_launch_t<1, false>(g, stream);
+  const int st = g->p.colstats_out ? 1 : (g->p.rowstats_out ? 2 : 0);
+  if (g->ctas == 2)
+    return st == 1 ? conv_halo_launch_t<2, 1>(g, stream) : st == 2 ? conv_halo_launch_t<2, 2>(g, stream) : conv_halo_launch_t<2, 0>(g, stream);
+  return st == 1 ? conv_halo_launch_t<1, 1>(g, stream) : st == 2 ? conv_halo_launch_t<1, 2>(g, stream) : conv_halo_launch_t<1, 0>(g, stream);
 }
 
 }  // namespace ldx

@@ -224,7 +224,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
         const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * p.bn + (int)cta_rank * sub_rows;
         const int sub_step = p.bn / nsub;
         int kcol = 0;
-        auto load_step = [&](const CUtensorMap* am, int ac0, int ax, int ay, const CUtensorMap* bm, int bk, int bn0) {
+        // b_bytes: bytes of B this CTA loads for the step (the whole stage, or the 64-column identity block)
+        auto load_step = [&](const CUtensorMap* am, int ac0, int ax, int ay, const CUtensorMap* bm, int bk, int bn0,
+                             uint32_t b_bytes, bool second) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* dA = sA + (size_t)stage * A_STAGE_BYTES;
           uint8_t* dB = sB + (size_t)stage * b_stage_bytes;
@@ -232,14 +234,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
             // both CTAs' loads complete on the leader's barrier, which the leader arms for the pair
             const uint32_t lbar = mapa_shared(smem_u32(&bars->full[stage]), 0);
             if (elect_one()) {
-              if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2 * (A_STAGE_BYTES + b_stage_bytes));
+              if (cta_rank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2 * (A_STAGE_BYTES + b_bytes));
               tma_load_4d_pair(dA, am, lbar, ac0, ax, ay, b0);
               tma_load_2d_pair(dB, bm, lbar, bk, bn0);
-              if (nsub == 2) tma_load_2d_pair(dB + b_sub_bytes, bm, lbar, bk, bn0 + sub_step);
+              if (second) tma_load_2d_pair(dB + b_sub_bytes, bm, lbar, bk, bn0 + sub_step);
             }
           } else {
             if (elect_one()) {
-              mbar_arrive_expect_tx(&bars->full[stage], A_STAGE_BYTES + b_stage_bytes);
+              mbar_arrive_expect_tx(&bars->full[stage], A_STAGE_BYTES + b_bytes);
               tma_load_4d(dA, am, &bars->full[stage], ac0, ax, ay, b0);
               tma_load_2d(dB, bm, &bars->full[stage], bk, bn0);
             }
@@ -257,12 +259,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
           }
           for (int ch = 0; ch < sg.nchunks; ++ch, ++step, kcol += BK)
             if (step >= k_lo && step < k_hi)
-              load_step(&p.amap[sg.map], sg.c0 + ch * BK, x0 + sg.dx, y0 + sg.dy, &p.bmap, kcol, n0);
+              load_step(&p.amap[sg.map], sg.c0 + ch * BK, x0 + sg.dx, y0 + sg.dy, &p.bmap, kcol, n0, b_stage_bytes, nsub == 2);
         }
         // residual fused as an identity K segment (see gemm_prepare): A = the residual tile's own column
         // range, B = the matching rows of I
-        for (int dk = 0; dk < p.diag_chunks; ++dk)
-          load_step(&p.amap[p.diag_src], nt * p.bn + dk * BK, x0, y0, &p.idmap, dk * BK, (int)cta_rank * sub_rows);
+        // (diag64: the identity is applied per 64-column block of the tile -- A = the residual's columns of that
+        // block, B = the 64 x 64 identity, D = that block's accumulator columns -- so a step costs an N = 64 MMA
+        // chain instead of an N = bn one)
+        for (int dk = 0; dk < p.diag_chunks; ++dk) {
+          if (p.diag64)
+            load_step(&p.amap[p.diag_src], nt * p.bn + dk * BK, x0, y0, &p.idmap, 0, (int)cta_rank * (64 / kCtas),
+                      (uint32_t)(64 / kCtas) * BK * 2, false);
+          else
+            load_step(&p.amap[p.diag_src], nt * p.bn + dk * BK, x0, y0, &p.idmap, dk * BK, (int)cta_rank * sub_rows,
+                      b_stage_bytes, nsub == 2);
+        }
       }
     }
   } else if (warp == 1) {
@@ -270,6 +281,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
     // loop, one elected lane issues)
     if (cta_rank == 0) {
       const uint32_t idesc = umma_idesc_f16(BM * kCtas, p.bn / nsub);
+      const uint32_t idesc64 = umma_idesc_f16(BM * kCtas, 64);
       const uint32_t sub_cols = (uint32_t)(p.bn / nsub);
       int stage = 0;
       uint32_t phase = 0;
@@ -289,7 +301,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
           if (lane == 0 && it == 0 && kb == nk_tile - 1) TS_MARK(4);
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
-          if (elect_one()) {
+          const int dk = kb - (nk_tile - p.diag_chunks);       // >= 0: fused-residual identity step
+          if (p.diag64 && dk >= 0) {
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < BK / 16; ++k) {
+                const uint64_t ad = umma_desc_kmajor_sw128(a_addr + k * 32), bd = umma_desc_kmajor_sw128(b_addr + k * 32);
+                if constexpr (kCtas == 2) umma_f16_ss_pair(d_tmem + (uint32_t)dk * 64u, ad, bd, idesc64, 1u);
+                else umma_f16_ss(d_tmem + (uint32_t)dk * 64u, ad, bd, idesc64, 1u);
+              }
+              if constexpr (kCtas == 2) umma_commit_pair(&bars->empty[stage], 3); else umma_commit(&bars->empty[stage]);
+              if (kb == nk_tile - 1) {
+                if constexpr (kCtas == 2) umma_commit_pair(&bars->tmem_full[as], 3); else umma_commit(&bars->tmem_full[as]);
+              }
+            }
+          } else if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               const uint64_t ad = umma_desc_kmajor_sw128(a_addr + k * 32), bd = umma_desc_kmajor_sw128(b_addr + k * 32);
@@ -806,14 +832,18 @@ static void choose_config(int N, int m_tiles, int flags, int sms, int force_ctas
 int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   LDX_CHECK_ARG(d && g, "null descriptor");
   LDX_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= LDX_MAX_SRC, "nsrc %d out of range", d->nsrc);
-  const bool halo = d->halo_nsrc > 0;
-  LDX_CHECK_ARG(d->nseg >= (halo ? 0 : 1) && d->nseg <= LDX_MAX_SEG, "nseg %d out of range", d->nseg);
-  LDX_CHECK_ARG(halo || !d->gn_coef, "gn_coef needs the halo-tile conv (halo_nsrc > 0)");
+  // the halo-tile kernel (conv_halo.cu) also serves 1x1 convs whose input is normalised in the operand path
+  // (halo_nsrc == 0, gn_coef set: SpatialTransformer.norm + proj_in, LD.py:4246-4251): its K items are then seg[] only
+  const bool halo = d->halo_nsrc > 0 || d->gn_coef != nullptr;
+  LDX_CHECK_ARG(d->nseg >= (d->halo_nsrc > 0 ? 0 : 1) && d->nseg <= LDX_MAX_SEG, "nseg %d out of range", d->nseg);
   if (halo) {
-    LDX_CHECK_ARG(d->halo_nsrc <= 2 && d->halo_nsrc <= d->nsrc, "halo_nsrc %d out of range", d->halo_nsrc);
+    LDX_CHECK_ARG(d->halo_nsrc >= 0 && d->halo_nsrc <= 2 && d->halo_nsrc <= d->nsrc, "halo_nsrc %d out of range", d->halo_nsrc);
     LDX_CHECK_ARG(d->W % 8 == 0, "halo conv: W = %d must be a multiple of 8", d->W);
-    LDX_CHECK_ARG(!(d->flags & (LDX_EPI_GEGLU | LDX_EPI_ROWNORM | LDX_EPI_OUT_F32)) && !d->rowstats_out,
-                  "halo conv: fp16 output, no GEGLU / ROWNORM / rowstats_out");
+    LDX_CHECK_ARG(!(d->flags & (LDX_EPI_GEGLU | LDX_EPI_ROWNORM | LDX_EPI_OUT_F32)) && !(d->rowstats_out && d->colstats_out),
+                  "halo conv: fp16 output, no GEGLU / ROWNORM, at most one of rowstats_out / colstats_out");
+    if (d->halo_nsrc == 0)
+      LDX_CHECK_ARG(d->src[0].W == d->W && d->src[0].H == d->H && d->src[0].B == d->B && d->src[0].C % 8 == 0,
+                    "normalised 1x1 conv: source 0 must cover the output domain with C %% 8 == 0");
     for (int i = 0; i < d->halo_nsrc; ++i) {
       LDX_CHECK_ARG(d->src[i].W == d->W && d->src[i].H == d->H && d->src[i].B == d->B && d->src[i].C % 8 == 0,
                     "halo conv: source %d must cover the output domain (stride 1) with C %% 8 == 0", i);
@@ -949,6 +979,12 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
   p.diag_src = 0;
   // ceil(bn / 64) identity steps: I's rows stop at bn, so the columns past bn of the last step add nothing
   p.diag_chunks = fuse_res ? (bn + 63) / 64 : 0;
+  {
+    // 64-column identity blocks need the accumulator's TMEM allocation to cover ceil64(bn) columns
+    static int d64_env = -1;
+    if (d64_env < 0) { const char* e = getenv("LDX_DIAG64"); d64_env = e ? atoi(e) : 1; }
+    p.diag64 = (fuse_res && d64_env && (bn + 63) / 64 * 64 <= (int)p.acc_stride) ? 1 : 0;
+  }
   nk += p.diag_chunks;
   p.nk = nk;
   p.ksplit = nsplit > 1 ? (nk + nsplit - 1) / nsplit : nk;
@@ -976,11 +1012,19 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
       if (rc) return rc;
     }
     for (int i = d->halo_nsrc; i < 2; ++i) p.hmap[i] = p.hmap[0];
+    if (d->halo_nsrc == 0) {                     // normalised 1x1 conv: the transform applies to source 0's K steps
+      p.halo_c[0] = d->src[0].C;
+      coff = (d->src[0].C + 63) / 64 * BK;
+      p.halo_nch[0] = coff / BK;
+    }
     p.gn_coef = d->gn_coef;
     p.gn_ctot = d->gn_ctot;
     p.gn_silu = d->gn_silu;
-    LDX_CHECK_ARG(!d->gn_coef || d->gn_ctot >= coff - (p.halo_nch[d->halo_nsrc - 1] * BK - p.halo_c[d->halo_nsrc - 1]),
-                  "halo conv: gn_ctot %d smaller than the concatenated channels", d->gn_ctot);
+    {
+      const int last = d->halo_nsrc > 0 ? d->halo_nsrc - 1 : 0;
+      LDX_CHECK_ARG(!d->gn_coef || d->gn_ctot >= coff - (p.halo_nch[last] * BK - p.halo_c[last]),
+                    "halo conv: gn_ctot %d smaller than the normalised channels", d->gn_ctot);
+    }
   }
   int stages = (int)((224 * 1024 - EPI_SMEM - 2048) / (A_STAGE_BYTES + b_stage));
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -1024,7 +1068,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     LDX_CHECK_ARG(ident != nullptr, "identity matrix allocation failed");
     const uint64_t idims[2] = {IDENT_N, IDENT_N};
     const uint64_t istr[1] = {IDENT_N * 2};
-    const uint32_t ibox[2] = {(uint32_t)BK, (uint32_t)(bn / (ctas * nsub))};
+    const uint32_t ibox[2] = {(uint32_t)BK, p.diag64 ? (uint32_t)(64 / ctas) : (uint32_t)(bn / (ctas * nsub))};
     rc = encode_map_f16(&p.idmap, ident, 2, idims, istr, ibox);
     if (rc) return rc;
   }
@@ -1035,6 +1079,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     int rc = encode_map_f16(&p.bmap, d->w, 2, dims, str, box);
     if (rc) return rc;
   }
+  if (halo && d->halo_nsrc == 0) p.hmap[0] = p.hmap[1] = p.bmap;   // never dereferenced, but prefetched: keep them valid
 
   p.out = d->out;
   p.o_sx = d->o_sx; p.o_sy = d->o_sy; p.o_sb = d->o_sb; p.o_off = d->o_off;

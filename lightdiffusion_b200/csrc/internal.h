@@ -100,6 +100,7 @@ struct alignas(64) GemmKParams {
   KSeg seg[LDX_MAX_SEG];
   int32_t nseg, nk;    // nk = K steps per tile, including diag_chunks
   int32_t diag_src, diag_chunks;   // residual fused as an identity K segment: amap index, bn / 64 steps (0 = none)
+  int32_t diag64;                  // 1: each identity step is an N = 64 MMA chain on its own 64 accumulator columns
   int32_t N, W, H, B;
   int32_t bw, bh, bb;
   int32_t tiles_x, tiles_y, tiles_b, n_tiles, num_tiles;

@@ -60,6 +60,10 @@ CONV_SMALL = os.environ.get("LDX_CONV_SMALL", "1") == "1"
 # disappears.  LDX_HALO=0 keeps the two-pass GroupNorm + implicit-GEMM conv everywhere (A/B).
 HALO = os.environ.get("LDX_HALO", "1") == "1"
 HALO_MIN_HW = int(os.environ.get("LDX_HALO_MIN_HW", "256"))
+# SpatialTransformer.norm folded into proj_in's operand path the same way (a 1x1 conv through the halo kernel).  Measured
+# slower on B200 (UNet step +0.17 ms: with one MMA chain of 5-20 K steps per item instead of nine, the three-deep
+# operand ring cannot cover TMA latency + transform), so it is off by default; LDX_HALO_1X1=1 enables it.
+HALO_1X1 = os.environ.get("LDX_HALO_1X1", "0") == "1"
 FUSE_GN_STATS = os.environ.get("LDX_FUSE_GN_STATS", "1") == "1"
 GN_STATS_MIN_HW = int(os.environ.get("LDX_GN_STATS_MIN_HW", "16384"))
 
@@ -447,12 +451,20 @@ class UNetPlan(_GnStatsMixin):
         eng, w, p, pool = self.eng, self.eng.w, s.name, self.pool
         Bn, h, wd, c = x.shape
         n, m = h * wd, Bn * h * wd
-        y = self._gn(x, None, w[p + ".gn.g"], w[p + ".gn.b"], 1e-6, False)
         t = pool.alloc(m, c)
-        d = K.linear_desc(y, w[p + ".pin.w"], t, bias=w[p + ".pin.b"])
-        st1 = self._rowstats(d, m, 0)          # row statistics of t for norm1, folded into the QKV GEMM
-        self.prog.add(d)
-        pool.free(y)
+        if HALO_1X1 and self._use_halo(x, None):
+            # SpatialTransformer.norm folded into proj_in's operand path (statistics-only GroupNorm launch)
+            coef = self._gn_coef(x, None, w[p + ".gn.g"], w[p + ".gn.b"], 1e-6)
+            d = K.conv1x1_gn_desc(x, w[p + ".pin.w"], t.view(Bn, h, wd, c), gn=(coef, False), bias=w[p + ".pin.b"])
+            st1 = self._rowstats(d, m, 0)      # row statistics of t for norm1, folded into the QKV GEMM
+            self.prog.add(d)
+            pool.free(coef)
+        else:
+            y = self._gn(x, None, w[p + ".gn.g"], w[p + ".gn.b"], 1e-6, False)
+            d = K.linear_desc(y, w[p + ".pin.w"], t, bias=w[p + ".pin.b"])
+            st1 = self._rowstats(d, m, 0)      # row statistics of t for norm1, folded into the QKV GEMM
+            self.prog.add(d)
+            pool.free(y)
         # attn1 (self)
         qkv = pool.alloc(m, 3 * c)
         self.prog.add(K.linear_desc(t, w[p + ".qkv.w"], qkv, bias=w[p + ".qkv.b"], rownorm=(st1, w[p + ".qkv.g"], 1e-5, c)))

@@ -212,6 +212,18 @@ def conv3x3_halo_desc(xs: Sequence[torch.Tensor], wp: torch.Tensor, out: torch.T
     return d
 
 
+def conv1x1_gn_desc(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, gn: tuple, **kw) -> L.GemmDesc:
+    """1x1 conv (a Linear over the channels) of x [B,H,W,C] with GroupNorm (+ SiLU) applied to the operand tiles in shared
+    memory (SpatialTransformer.norm + proj_in, LD.py:4246-4251); out [B,H,W,N].  gn = (coef [B, C, 2], silu)."""
+    assert x.dim() == 4 and out.dim() == 4 and x.shape[:3] == out.shape[:3]
+    c = x.shape[-1]
+    d = gemm_desc([x], [(0, 0, 0, 0, ceil64(c) // 64)], w, out, w.shape[0], **kw)
+    coef, silu = gn
+    assert coef.dtype == torch.float32 and coef.is_contiguous() and tuple(coef.shape) == (x.shape[0], c, 2)
+    d.gn_coef, d.gn_ctot, d.gn_silu = coef.data_ptr(), c, int(bool(silu))
+    return d
+
+
 def halo_ok(x: torch.Tensor, out: torch.Tensor) -> bool:
     """Shapes the halo-tile conv serves well: 8 x 16-pixel tiles that the map fills (W % 8 == 0, H % 16 == 0)."""
     _, h, w, _ = x.shape

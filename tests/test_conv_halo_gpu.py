@@ -190,6 +190,26 @@ def test_conv3x3_halo_colstats_chain():
     assert rel(c2, c1) < 1e-5
 
 
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 64, 64, 320, 320), (3, 32, 32, 640, 640), (2, 16, 16, 1280, 1280),
+                                       (1, 24, 16, 64, 96)])
+def test_conv1x1_group_norm_rowstats(B, H, W, C, N):
+    """SpatialTransformer.norm + proj_in (LD.py:4246-4251): GroupNorm without SiLU folded into the operand path of a
+    1x1 conv that also leaves the LayerNorm row statistics of its output."""
+    x = h16(rnd(B, H, W, C, seed=60) * 1.2 - 0.4)
+    gamma, beta = 1.0 + 0.2 * rnd(C, seed=61), 0.3 * rnd(C, seed=62)
+    w, bias = h16(rnd(N, C, seed=63, scale=C ** -0.5)), rnd(N, seed=64)
+    coef = _coef(x, None, gamma, beta, 1e-6)
+    out = torch.zeros(B, H, W, N, dtype=torch.float16, device=DEV)
+    d = K.conv1x1_gn_desc(x, K.pack_linear(w), out, gn=(coef, False), bias=bias)
+    stats = K.attach_rowstats(d, B * H * W)
+    K.run_gemm(d)
+    ref = h16(_gn_ref(x, gamma, beta, 1e-6, False)).float() @ w.float().t() + bias
+    assert rel(out, ref) < 1.5e-3, rel(out, ref)
+    o = out.float().reshape(B * H * W, N)
+    assert rel(stats[:, :, 0].sum(1), o.sum(1)) < 2e-3
+    assert rel(stats[:, :, 1].sum(1), (o * o).sum(1)) < 2e-3
+
+
 def test_halo_argument_errors():
     x = h16(rnd(1, 16, 12, 64, seed=50))             # W % 8 != 0
     w = K.pack_conv3x3(h16(rnd(64, 64, 3, 3, seed=51)))
