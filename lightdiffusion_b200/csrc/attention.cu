@@ -629,7 +629,15 @@ struct AttnLaunch {
   AttnParams p;
   dim3 grid;
   int d, ng;
+  void* xa = nullptr;          // short-context cross-attention: the dedicated kernel's launch record (xattn.cu)
 };
+
+// xattn.cu
+bool xattn_eligible(int Nk, int d, int heads, int causal);
+int xattn_prepare(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                  int B, int Nq, int Nk, int heads, int d, void** handle);
+int xattn_run(void* handle, cudaStream_t st);
+void xattn_free(void* handle);
 
 // Query groups per CTA: 4 for the long self-attention streams of narrow heads (K/V read once per 512 queries),
 // 1 when K/V is short (cross-attention over 77 tokens: more, smaller CTAs hide the per-CTA latency chain).
@@ -647,6 +655,11 @@ static int attention_prepare(const void* q, int64_t ldq, const void* k, int64_t 
   LDX_CHECK_ARG(B >= 1 && Nq >= 1 && Nk >= 1 && heads >= 1, "attention: bad extents");
   LDX_CHECK_ARG(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention: output must be 16-byte aligned");
   memset(&L->p, 0, sizeof(L->p));
+  L->xa = nullptr;
+  if (xattn_eligible(Nk, d, heads, causal)) {
+    L->d = d;
+    return xattn_prepare(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, heads, d, &L->xa);
+  }
   auto enc = [&](CUtensorMap* m, const void* ptr, int64_t ld, int N, int rows) {
     const uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ld * 2, (uint64_t)ld * 2 * (uint64_t)N};
@@ -680,6 +693,7 @@ static int attention_launch_t(const AttnLaunch* L, cudaStream_t st) {
 }
 
 static int attention_launch(const AttnLaunch* L, cudaStream_t st) {
+  if (L->xa) return xattn_run(L->xa, st);
   if (L->p.causal) {
     if (L->d == 64 && L->ng == 1) return attention_launch_t<64, 1, true>(L, st);
     set_error("attention: the causal variant exists for d = 64 and Nk <= 256 (CLIP text tower), got d = %d, Nk = %d", L->d,
@@ -711,7 +725,11 @@ int attention_prepare_op(const ldx_generic_op_t* op, void** handle) {
   return LDX_OK;
 }
 int attention_run_handle(void* handle, cudaStream_t st) { return attention_launch((AttnLaunch*)handle, st); }
-void attention_free_handle(void* handle) { delete (AttnLaunch*)handle; }
+void attention_free_handle(void* handle) {
+  AttnLaunch* L = (AttnLaunch*)handle;
+  if (L->xa) xattn_free(L->xa);
+  delete L;
+}
 
 }  // namespace ldx
 
@@ -722,7 +740,9 @@ extern "C" int ldx_attention(const void* q, int64_t ldq, const void* k, int64_t 
   AttnLaunch L;
   int rc = attention_prepare(q, ldq, k, ldk, v, ldv, o, ldo, B, Nq, Nk, heads, d, &L);
   if (rc) return rc;
-  return attention_launch(&L, as_stream(stream));
+  rc = attention_launch(&L, as_stream(stream));
+  if (L.xa) xattn_free(L.xa);
+  return rc;
 }
 
 extern "C" int ldx_attention_causal(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,

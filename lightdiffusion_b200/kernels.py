@@ -439,7 +439,8 @@ class Program:
             L.check(L.lib().ldx_program_add_gemm(self._h, C.byref(op)), "ldx_program_add_gemm")
             k = 64 * sum(op.seg[i].nchunks for i in range(op.nseg))
             k += 9 * sum(ceil64(op.src[i].C) for i in range(op.halo_nsrc))
-            self.meta.append(("gemm", 2.0 * op.W * op.H * op.B * op.N * k, (op.W * op.H * op.B, op.N, k)))
+            kind = "conv_halo" if (op.halo_nsrc > 0 or op.gn_coef) else "gemm"      # which kernel runs it
+            self.meta.append((kind, 2.0 * op.W * op.H * op.B * op.N * k, (op.W * op.H * op.B, op.N, k)))
         elif isinstance(op, (list, tuple)):
             for o in op:
                 self.add(o)

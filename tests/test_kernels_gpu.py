@@ -272,6 +272,30 @@ def test_attention(B, Nq, Nk, heads, d):
     assert rel(o, ref) < 2e-3, rel(o, ref)
 
 
+@pytest.mark.parametrize("B,Nq,Nk,heads,d", [(2, 4096, 77, 8, 40), (3, 1024, 77, 8, 80), (1, 130, 77, 2, 40), (5, 256, 80, 3, 80),
+                                             (2, 1000, 1, 4, 40), (1, 64, 13, 8, 40), (150, 128, 77, 1, 40)])
+def test_cross_attention_short_context(B, Nq, Nk, heads, d):
+    """The dedicated short-context kernel (csrc/xattn.cu: Nk <= 80, d in {40, 80}): one 80-key tile, persistent CTAs
+    walking (batch, query tile, head) units; ragged Nq, Nk below / at the tile size, odd unit counts, peaked scores."""
+    q = h16(rnd(B, Nq, heads * d, seed=56) * 2.0)
+    k = h16(rnd(B, Nk, heads * d, seed=57) * 2.0)
+    v = h16(rnd(B, Nk, heads * d, seed=58))
+    o = torch.full_like(q, 9.0)
+    K.run_op(K.attention_op(q, k, v, o, heads))
+    qf, kf, vf = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Nq, heads * d)
+    assert rel(o, ref) < 2e-3, rel(o, ref)
+    # strided views: q / o as channel slices of wider buffers, k / v as slices of one context projection
+    wide = h16(rnd(B, Nq, heads * d + 64, seed=59))
+    kv = h16(rnd(B, Nk, 2 * heads * d, seed=60))
+    ow = torch.zeros(B, Nq, heads * d + 32, dtype=torch.float16, device=DEV)
+    K.run_op(K.attention_op(wide[:, :, 64:], kv[:, :, :heads * d], kv[:, :, heads * d:], ow[:, :, 32:], heads))
+    qf, kf, vf = (t.float().reshape(B, -1, heads, d).transpose(1, 2) for t in (wide[:, :, 64:], kv[:, :, :heads * d], kv[:, :, heads * d:]))
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B, Nq, heads * d)
+    assert rel(ow[:, :, 32:], ref) < 2e-3
+    assert float(ow[:, :, :32].abs().max()) == 0.0
+
+
 def test_attention_peaked_scores_rescale_path():
     # large-magnitude q/k make the running max jump by more than the lazy-rescale threshold
     B, N, heads, d = 1, 512, 2, 40
