@@ -26,6 +26,19 @@ elif case == "conv_small_vae":        # VAE conv_out 128 -> 3 at 512^2, b = 8, f
     wp = K.pack_conv3x3_small(w); o16 = torch.zeros(8, 512, 512, 8, dtype=torch.float16, device=dev)
     img = torch.empty(8, 512, 512, 3, dtype=torch.float32, device=dev)
     op = K.conv3x3_small_op(x, wp, b, 3, out16=o16, out_img=img, post=1); keep += [x, wp, b, o16, img]
+elif case in ("halo_conv320", "halo_conv1280", "halo_vae128"):   # GroupNorm + SiLU + 3x3 conv through the halo-tile kernel
+    B, H, C = {"halo_conv320": (16, 64, 320), "halo_conv1280": (16, 16, 1280), "halo_vae128": (8, 512, 128)}[case]
+    x = (rnd(B, H, H, C) * 1.3 + 0.3).half(); w = rnd(C, C, 3, 3, sc=(9 * C) ** -0.5).half()
+    wp, b = K.pack_conv3x3(w), rnd(C); out = torch.empty(B, H, H, C, dtype=torch.float16, device=dev)
+    gam, bet = rnd(C) * 0.1 + 1, rnd(C) * 0.1
+    coef = torch.empty(B, C, 2, dtype=torch.float32, device=dev)
+    st = torch.empty(B * L.GN_STATS_FLOATS_PER_BATCH, dtype=torch.float32, device=dev)
+    tk = torch.zeros(B, dtype=torch.int32, device=dev)
+    K.run_op(K.group_norm_coef_op(x, None, gam, bet, coef, st, tk, 1e-5))
+    op = K.conv3x3_halo_desc([x], wp, out, gn=(coef, True), bias=b); keep += [x, wp, b, out, gam, bet, coef, st, tk]
+elif case == "xattn40":               # cross-attention over the 77 context tokens at the 64 x 64 level
+    q = rnd(16, 4096, 320).half(); k, v = rnd(16, 77, 320).half(), rnd(16, 77, 320).half(); o = torch.empty_like(q)
+    op = K.attention_op(q, k, v, o, 8); keep += [q, k, v, o]
 elif case == "attention_d40":
     q, k, v = (rnd(16, 4096, 320).half() for _ in range(3)); o = torch.empty_like(q)
     op = K.attention_op(q, k, v, o, 8); keep += [q, k, v, o]
