@@ -46,8 +46,36 @@ static constexpr int ATT_MAX_ST = 6;        // K / V ring depth bound
 #ifndef LDX_ATT_SLEEP_NS
 #define LDX_ATT_SLEEP_NS 64       // poll back-off of the producer / patcher / MMA-issuer warps
 #endif
+// The four softmax warps that share an SM sub-partition (one per query group) contend for its MUFU unit: started in
+// phase they all run their 64 exponentials together (4 x 512 clocks of MUFU work) and then all do their MUFU-free work
+// (TMEM load, row maximum, barriers: ~1.2 k clocks) together, leaving the unit idle.  With LDX_ATT_TOKENS = T > 0 the
+// exponentials of (tile j, group g) may start only when those of the T-th previous (tile, group) in round-robin order
+// have been issued, which staggers the groups so that at most T warps per sub-partition are in their exponentials.
+// Measured (d = 40, 16 x 8 x 4096^2, scripts/attn_timeline.py on the -DLDX_ATT_TIMING build): a softmax warp spends
+// 2.74 k clocks per 64-key tile -- 1.54 k in the exponential / pack / store phase (0.51 k of MUFU work of its own, the
+// rest queueing behind its three neighbours), 1.2 k in TMEM load, row maximum and barriers.  T = 2 shortens the
+// exponential phase to 1.24 k but adds 0.34 k of token wait: the same 2.74 k, 700 vs 675 us; T = 1 serialises (898 us).
+// So the stagger is not what the kernel lacks: per tile round a CTA also moves ~256 KB through shared memory (Q re-read
+// by every S = Q K^T, K / V / P operand reads, P stores) against 128 B/clk = 2.0 k of those 2.74 k clocks, MUFU is 75 %
+// busy and the schedulers 52 %: three resources within a third of each other.  Kept as a knob, default off.
+#ifndef LDX_ATT_TOKENS
+#define LDX_ATT_TOKENS 0
+#endif
+static_assert(LDX_ATT_TOKENS >= 0 && LDX_ATT_TOKENS <= 2, "with three tokens a group can lap its successor's barrier phase");
 #ifndef LDX_ATT_POLY_MOD
 #define LDX_ATT_POLY_MOD 0      // every POLY_MOD-th exponential runs on the FMA pipe (0 = all on MUFU); measured: no gain
+#endif
+
+#ifdef LDX_ATT_TIMING
+// variant-build instrumentation: cycles per phase of the first softmax warp of CTA (0, 0, 0), summed over its K/V tiles
+__device__ unsigned long long g_att_ts[16];
+#define AT_DECL long long at_t = clock64(), at_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define AT(i) { const long long at_now = clock64(); at_acc[i] += at_now - at_t; at_t = at_now; }
+#define AT_FLUSH(n) if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && warp == C::HELPERS && lane == 0) { for (int i = 0; i < 8; ++i) g_att_ts[i] = (unsigned long long)at_acc[i]; g_att_ts[8] = (unsigned long long)(n); }
+#else
+#define AT_DECL
+#define AT(i)
+#define AT_FLUSH(n)
 #endif
 
 template <int D, int NG_>
@@ -91,7 +119,7 @@ struct AttnCfg {
   static constexpr int P_BYTES = BQ * BKV * 2;      // per group and buffer
   static constexpr int TMEM_NEED = NG * (BKV + DN);
   static constexpr int TMEM_COLS = TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512);
-  static constexpr int SMEM = NG * (Q_BYTES + PB * P_BYTES) + (KST + VST) * KV_BYTES + 512 + 1024;
+  static constexpr int SMEM = NG * (Q_BYTES + PB * P_BYTES) + (KST + VST) * KV_BYTES + 768 + 1024;
   static constexpr int BY_TMEM = 512 / TMEM_COLS;
   static constexpr int BY_SMEM = (227 * 1024) / (SMEM + 1024);
   static constexpr int BY_THREADS = 2048 / THREADS;
@@ -105,11 +133,13 @@ struct AttnCfg {
   static_assert(KST <= ATT_MAX_ST && VST <= ATT_MAX_ST, "ring depth");
 };
 
-struct AttnBarriers {           // must fit the 512 bytes reserved in AttnCfg::SMEM
+struct AttnBarriers {           // must fit the 768 bytes reserved in AttnCfg::SMEM
   uint64_t q_full[ATT_MAX_NG], s_full[ATT_MAX_NG], s_free[ATT_MAX_NG], p_full[ATT_MAX_NG][2], pv_done[ATT_MAX_NG][2];
   uint64_t k_full[ATT_MAX_ST], k_empty[ATT_MAX_ST], v_full[ATT_MAX_ST], v_empty[ATT_MAX_ST], v_ready[ATT_MAX_ST];
+  uint64_t tok[4][ATT_MAX_NG];  // MUFU turn-taking among the softmax warps that share a scheduler (see LDX_ATT_TOKENS)
   uint32_t tmem_base;
 };
+static_assert(sizeof(AttnBarriers) <= 768, "AttnBarriers must fit its reserved shared memory");
 
 struct alignas(64) AttnParams {
   CUtensorMap qmap, kmap, vmap;
@@ -166,6 +196,7 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
         mbar_init(&bars->p_full[g][i], 4);
         mbar_init(&bars->pv_done[g][i], 1);
       }
+      for (int qq = 0; qq < 4; ++qq) mbar_init(&bars->tok[qq][g], 1);
     }
     for (int i = 0; i < ATT_MAX_ST; ++i) {
       mbar_init(&bars->k_full[i], 1);
@@ -342,17 +373,21 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
         tmem_ld_wait();
         release_s();
       }
+      AT_DECL
       for (int j = 0; j < nkv; ++j) {
         const int pb = j % C::PB;
         uint8_t* prow = prow0 + pb * C::P_BYTES;
         const int kv_left = p.Nk - j * BKV;
+        AT(7)
         if constexpr (!PF) {
           mbar_wait_a(a_sfull, j & 1);
+          AT(0)
           tc_fence_after();
           tmem_ld32(tSg, ra);
           tmem_ld32(tSg + 32, rb);
           tmem_ld_wait();
           release_s();
+          AT(1)
         }
         const uint32_t ninf = 0xff800000u;
         if (kv_left < BKV) {
@@ -412,7 +447,16 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
           tmem_st_wait();
         }
         const float mc = m_used * c;
+        AT(2)
         if (j >= C::PB) mbar_wait_a(a_pvdone + 8 * pb, ((j - C::PB) / C::PB) & 1);   // P V(j - PB) has read this buffer
+        AT(3)
+        if constexpr (LDX_ATT_TOKENS > 0 && NG > 1) {
+          if (ng_act == NG && (j > 0 || g >= LDX_ATT_TOKENS)) {
+            const int wcount = g >= LDX_ATT_TOKENS ? j : j - 1;
+            mbar_wait(&bars->tok[qd][g], (uint32_t)(wcount & 1));
+          }
+        }
+        AT(6)
         float l0 = 0.f, l1 = 0.f;
         // 64 keys = 8 16-byte chunks; chunk index XOR (row % 8) = SWIZZLE_128B
         auto half = [&](const uint32_t (&r)[32], int ch0) {
@@ -452,11 +496,16 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
           }
         }
         half(rb, 4);
+        if constexpr (LDX_ATT_TOKENS > 0 && NG > 1) {
+          if (ng_act == NG && lane == 0) mbar_arrive(&bars->tok[qd][(g + LDX_ATT_TOKENS) % NG]);
+        }
         l += l0 + l1;
+        AT(4)
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_a(a_pfull + 8 * pb);
+        AT(5)
         if constexpr (PF) {
           if (more) {
             tmem_ld32(tSg + 32, rb);
@@ -465,6 +514,7 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
           }
         }
       }
+      AT_FLUSH(nkv)
     } else
     for (int j = 0; j < nkv; ++j) {
       mbar_wait(s_full, j & 1);
@@ -734,6 +784,12 @@ void attention_free_handle(void* handle) {
 }  // namespace ldx
 
 using namespace ldx;
+
+#ifdef LDX_ATT_TIMING
+extern "C" int ldx_debug_att_ts(unsigned long long* out) {
+  return cudaMemcpyFromSymbol(out, ldx::g_att_ts, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" int ldx_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                              void* o, int64_t ldo, int B, int Nq, int Nk, int heads, int d, ldx_stream_t stream) {
