@@ -189,28 +189,24 @@ class _ESRGANPlan:
                 p = f"model.1.sub.{i}.RDB{j}"
                 for c in range(1, 5):
                     cin = nf + (c - 1) * gc
-                    prog.add(K.conv3x3_desc(cur[..., :cin], w[f"{p}.c{c}.w"], cur[..., cin:cin + gc], bias=w[f"{p}.c{c}.b"],
-                                            flags=L.EPI_LRELU))
+                    prog.add(K.conv3x3_auto_desc(cur[..., :cin], w[f"{p}.c{c}.w"], cur[..., cin:cin + gc], bias=w[f"{p}.c{c}.b"],
+                                                 flags=L.EPI_LRELU))
                 nxt = next(b for b in bufs if b is not cur and b is not rrdb_in)
-                nch = K.ceil64(cw) // 64
-                segs = [(0, 0, kx - 1, ky - 1, nch) for ky in range(3) for kx in range(3)]
                 if j < 3:
-                    prog.add(K.gemm_desc([cur], segs, w[f"{p}.c5.w"], nxt[..., :nf], nf, bias=w[f"{p}.c5.b"],
-                                         residual=cur[..., :nf]))
+                    prog.add(K.conv3x3_auto_desc(cur, w[f"{p}.c5.w"], nxt[..., :nf], bias=w[f"{p}.c5.b"], residual=cur[..., :nf]))
                 else:
-                    segs.append((1, 0, 0, 0, 1))
-                    prog.add(K.gemm_desc([cur, cur[..., :nf]], segs, w[f"{p}.c5.w"], nxt[..., :nf], nf, bias=w[f"{p}.c5.b"],
-                                         residual=rrdb_in[..., :nf]))
+                    prog.add(K.conv3x3_auto_desc(cur, w[f"{p}.c5.w"], nxt[..., :nf], bias=w[f"{p}.c5.b"], residual=rrdb_in[..., :nf],
+                                                 extra_srcs=[cur[..., :nf]], extra_segs=[(0, 0, 0, 0, 1)]))
                 cur = nxt
         trunk = pool.alloc(B, H, W, nf)
-        prog.add(K.conv3x3_desc(cur[..., :nf], w["trunk.w"], trunk, bias=w["trunk.b"], residual=fea))   # ShortcutBlock
+        prog.add(K.conv3x3_auto_desc(cur[..., :nf], w["trunk.w"], trunk, bias=w["trunk.b"], residual=fea))   # ShortcutBlock
         h, hh, ww = trunk, H, W
         for n in eng.up_names:
             up = pool.alloc(B, hh * 2, ww * 2, nf)
             prog.add(K.upconv3x3_descs(h, w[n + ".w"], up, bias=w[n + ".b"], flags=L.EPI_LRELU))
             h, hh, ww = up, hh * 2, ww * 2
         hr = pool.alloc(B, hh, ww, nf)
-        prog.add(K.conv3x3_desc(h, w["hr.w"], hr, bias=w["hr.b"], flags=L.EPI_LRELU))
+        prog.add(K.conv3x3_auto_desc(h, w["hr.w"], hr, bias=w["hr.b"], flags=L.EPI_LRELU))
         self.out_buf = torch.zeros(B, hh, ww, 8, dtype=F16, device=dev)
         prog.add(K.conv3x3_desc(hr, w["last.w"], self.out_buf[..., :eng.out_nc], bias=w["last.b"]))
 

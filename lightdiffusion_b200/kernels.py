@@ -7,6 +7,7 @@ tensor is [rows, C].  Every function enqueues on the current torch CUDA stream.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -228,6 +229,21 @@ def halo_ok(x: torch.Tensor, out: torch.Tensor) -> bool:
     """Shapes the halo-tile conv serves well: 8 x 16-pixel tiles that the map fills (W % 8 == 0, H % 16 == 0)."""
     _, h, w, _ = x.shape
     return w % 8 == 0 and h % 16 == 0 and out.dtype == torch.float16 and out.stride(2) % 8 == 0
+
+
+HALO_GENERIC = os.environ.get("LDX_HALO_GENERIC", "1") == "1"
+
+
+def conv3x3_auto_desc(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, extra_srcs: Sequence[torch.Tensor] = (),
+                      extra_segs: Sequence[tuple] = (), **kw) -> L.GemmDesc:
+    """3x3 stride-1 pad-1 conv (+ optional extra 1x1 K segments whose weight columns follow the nine taps') through the
+    halo-tile kernel when the map tiles into 8 x 16 pixels, else through the implicit GEMM."""
+    if HALO_GENERIC and halo_ok(x, out) and x.shape[-1] % 8 == 0:
+        return conv3x3_halo_desc([x], wp, out, extra_srcs=extra_srcs, extra_segs=extra_segs, **kw)
+    nch = ceil64(x.shape[-1]) // 64
+    segs = [(0, 0, kx - 1, ky - 1, nch) for ky in range(3) for kx in range(3)]
+    segs += [(1 + si, c0, dx, dy, n) for (si, c0, dx, dy, n) in extra_segs]
+    return gemm_desc([x] + list(extra_srcs), segs, wp, out, wp.shape[0], **kw)
 
 
 def conv3x3_s2_desc(x: torch.Tensor, wp: torch.Tensor, out: torch.Tensor, pad_end: bool = False, **kw) -> L.GemmDesc:

@@ -110,9 +110,9 @@ class _TAESDPlan:
                 h = o
             elif kind == "block":
                 a, b_ = pool.alloc(B, hh, ww, NF), pool.alloc(B, hh, ww, NF)
-                prog.add(K.conv3x3_desc(h, w[f"{i}.0.w"], a, bias=w[f"{i}.0.b"], flags=L.EPI_RELU))
-                prog.add(K.conv3x3_desc(a, w[f"{i}.2.w"], b_, bias=w[f"{i}.2.b"], flags=L.EPI_RELU))
-                prog.add(K.conv3x3_desc(b_, w[f"{i}.4.w"], a, bias=w[f"{i}.4.b"], residual=h, flags=L.EPI_RELU))
+                prog.add(K.conv3x3_auto_desc(h, w[f"{i}.0.w"], a, bias=w[f"{i}.0.b"], flags=L.EPI_RELU))
+                prog.add(K.conv3x3_auto_desc(a, w[f"{i}.2.w"], b_, bias=w[f"{i}.2.b"], flags=L.EPI_RELU))
+                prog.add(K.conv3x3_auto_desc(b_, w[f"{i}.4.w"], a, bias=w[f"{i}.4.b"], residual=h, flags=L.EPI_RELU))
                 pool.free(b_); pool.free(h) if h is not x0 else None
                 h = a
             elif kind == "upconv":
