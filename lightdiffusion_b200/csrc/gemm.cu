@@ -1116,6 +1116,7 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     if (dbg < 0) { const char* e = getenv("LDX_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
     if (dbg == 1) p.flags |= (1 << 16);
     if (dbg == 2) p.flags |= (1 << 17);
+    if (dbg == 3) p.num_tiles = 0;              // timing experiments: launch skeleton only (prologue, TMEM, teardown)
   }
   const int n_out = (d->flags & LDX_EPI_GEGLU) ? d->N / 2 : d->N;
   bool vec = (n_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(d->out) + (uint64_t)d->o_off * osz) % 16 == 0) &&
