@@ -60,6 +60,7 @@ CONV_SMALL = os.environ.get("LDX_CONV_SMALL", "1") == "1"
 # disappears.  LDX_HALO=0 keeps the two-pass GroupNorm + implicit-GEMM conv everywhere (A/B).
 HALO = os.environ.get("LDX_HALO", "1") == "1"
 HALO_MIN_HW = int(os.environ.get("LDX_HALO_MIN_HW", "256"))
+HALO_MIN_TILES = int(os.environ.get("LDX_HALO_MIN_TILES", "32"))
 # SpatialTransformer.norm folded into proj_in's operand path the same way (a 1x1 conv through the halo kernel).  Measured
 # slower on B200 (UNet step +0.17 ms: with one MMA chain of 5-20 K steps per item instead of nine, the three-deep
 # operand ring cannot cover TMA latency + transform), so it is off by default; LDX_HALO_1X1=1 enables it.
@@ -171,8 +172,12 @@ class _GnStatsMixin:
 
     @staticmethod
     def _use_halo(x0, x1):
-        _, h, w, c0 = x0.shape
+        """The halo-tile conv has no split-K: below HALO_MIN_TILES 128-pixel tiles (small batches on the 16 x 16 / 32 x 32
+        levels) the implicit GEMM's K split fills the GPU and wins (batch 1 at 64 x 64: 5.43 vs 4.90 ms per UNet step with
+        the halo conv everywhere)."""
+        bn, h, w, c0 = x0.shape
         return (HALO and h * w >= HALO_MIN_HW and w % 8 == 0 and h % 16 == 0 and c0 % 8 == 0 and
+                bn * (h // 16) * (w // 8) >= HALO_MIN_TILES and
                 (x1 is None or (c0 % 64 == 0 and x1.shape[-1] % 8 == 0)))
 
     def _colstats(self, x0, x1):
