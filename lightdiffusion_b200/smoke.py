@@ -47,6 +47,17 @@ def _kernels(dev):
     stats = torch.empty(2 * L.GN_STATS_FLOATS_PER_BATCH, dtype=torch.float32, device=dev)
     K.run_op(K.group_norm_op(gx, None, gam, bet, gy, stats, 1e-5, True))
     out["group_norm"] = _rel(gy, F.silu(F.group_norm(gx.float().permute(0, 3, 1, 2), 32, gam, bet, 1e-5)).permute(0, 2, 3, 1))
+    # the ResBlock form: GroupNorm(32) + SiLU applied in the operand path of the halo-tile 3x3 conv (statistics-only
+    # GroupNorm launch + ldx_conv_halo_kernel), against the torch ops on the same fp16 inputs
+    hx = (rnd(2, 32, 32, 128) * 1.3 + 0.4).half().to(dev)
+    hw, hb = (rnd(128, 128, 3, 3) / 34).half().to(dev), rnd(128).to(dev)
+    coef = torch.empty(2, 128, 2, dtype=torch.float32, device=dev)
+    tickets = torch.zeros(2, dtype=torch.int32, device=dev)
+    K.run_op(K.group_norm_coef_op(hx, None, gam, bet, coef, stats, tickets, 1e-5))
+    hy = torch.empty(2, 32, 32, 128, dtype=torch.float16, device=dev)
+    K.run_gemm(K.conv3x3_halo_desc([hx], K.pack_conv3x3(hw), hy, gn=(coef, True), bias=hb))
+    hn = F.silu(F.group_norm(hx.float().permute(0, 3, 1, 2), 32, gam, bet, 1e-5)).half().float()
+    out["gn+conv_halo"] = _rel(hy, F.conv2d(hn, hw.float(), hb, padding=1).permute(0, 2, 3, 1))
     # attention: 1024-token self-attention (d = 40, 8 heads) and 77-key cross-attention
     for name, nk in (("self_attn", 1024), ("cross_attn", 77)):
         q, k, v = rnd(2, 1024, 320).half().to(dev), rnd(2, nk, 320).half().to(dev), rnd(2, nk, 320).half().to(dev)
