@@ -210,6 +210,30 @@ def test_conv1x1_group_norm_rowstats(B, H, W, C, N):
     assert rel(stats[:, :, 1].sum(1), (o * o).sum(1)) < 2e-3
 
 
+def test_halo_conv_is_repeatable():
+    """The operand transform rewrites shared memory between the TMA landing and the MMA (generic-proxy stores, proxy
+    fence, cross-CTA arrive): a missing fence or barrier shows up as run-to-run differences.  40 launches of the
+    up-path shape (two sources, GroupNorm + SiLU, CTA pairs, several tiles per CTA) must be bit-identical."""
+    B, H, W, C0, C1, Cout = 4, 64, 64, 320, 320, 320
+    h0, h1 = h16(rnd(B, H, W, C0, seed=70) + 0.3), h16(rnd(B, H, W, C1, seed=71))
+    gamma, beta = 1.0 + 0.2 * rnd(C0 + C1, seed=72), 0.3 * rnd(C0 + C1, seed=73)
+    w = K.pack_conv3x3(h16(rnd(Cout, C0 + C1, 3, 3, seed=74, scale=(9 * (C0 + C1)) ** -0.5)))
+    temb = rnd(B, Cout, seed=75)
+    coef = _coef(h0, h1, gamma, beta, 1e-5)
+    prog = K.Program()
+    out = torch.zeros(B, H, W, Cout, dtype=torch.float16, device=DEV)
+    prog.add(K.conv3x3_halo_desc([h0, h1], w, out, gn=(coef, True), rowadd=temb))
+    prog.run()
+    first = out.clone()
+    for _ in range(40):
+        out.zero_()
+        prog.run()
+        assert torch.equal(out, first)
+    # the coefficients themselves: atomic ticket + last-CTA finish, fixed summation order
+    for _ in range(10):
+        assert torch.equal(_coef(h0, h1, gamma, beta, 1e-5), coef)
+
+
 def test_halo_argument_errors():
     x = h16(rnd(1, 16, 12, 64, seed=50))             # W % 8 != 0
     w = K.pack_conv3x3(h16(rnd(64, 64, 3, 3, seed=51)))
