@@ -61,6 +61,31 @@ LDX_DEVICE uint64_t umma_desc_kmajor_sw128_sbo(uint32_t saddr, uint32_t sbo_byte
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 
+// GroupNorm coefficients of the eight channels a transform thread owns, and the in-place rewrite of one 16-byte piece:
+// fp16(silu?(x * scale + shift)) with the same fmaf / ex2 / rcp sequence as gn_apply_kernel (bit-identical operand).
+struct XfCoef {
+  float sc[8], sh[8];
+  LDX_DEVICE void load(const float* coef) {      // [8][2] = (scale, shift) pairs, 64-byte aligned
+    const float4* cf = reinterpret_cast<const float4*>(coef);
+    const float4 q0 = __ldg(cf), q1 = __ldg(cf + 1), q2 = __ldg(cf + 2), q3 = __ldg(cf + 3);
+    sc[0] = q0.x; sh[0] = q0.y; sc[1] = q0.z; sh[1] = q0.w; sc[2] = q1.x; sh[2] = q1.y; sc[3] = q1.z; sh[3] = q1.w;
+    sc[4] = q2.x; sh[4] = q2.y; sc[5] = q2.z; sh[5] = q2.w; sc[6] = q3.x; sh[6] = q3.y; sc[7] = q3.z; sh[7] = q3.w;
+  }
+  LDX_DEVICE void apply(uint4* ptr, bool do_silu) const {
+    const uint4 vv = *ptr;
+    const float2 f0 = unpack_h2(vv.x), f1 = unpack_h2(vv.y), f2 = unpack_h2(vv.z), f3 = unpack_h2(vv.w);
+    float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (do_silu) f[j] = silu_f(f[j]);
+    }
+    uint4 o;
+    o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
+    *ptr = o;
+  }
+};
+
 // The K loop of one output tile as a list of items; every role walks it with its own functor.
 //   f(kind, map, c0, dx, dy, kcol, ntaps, src):  kind 0 = halo chunk (A: hmap[map]; B column of tap t: t * halo_cp + kcol),
 //   1 = plain 1x1 K step (A: amap[map] shifted by (dx, dy); B column kcol), 2 = fused-residual identity step
@@ -279,67 +304,31 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
       halo_for_each_item(p, nt, [&](int kind, int map, int c0, int, int, int kcol, int, int src) {
         mbar_wait(&bars->a_full[stage], phase);
         const int cch = c0 + chunk * 8;            // first channel (inside the source) of this thread's piece
-        if (kind == 1 && map == 0 && p.halo_nsrc == 0 && p.gn_coef != nullptr && b0 < p.B && cch < p.halo_c[0]) {
-          // normalised 1x1 conv: the plain 128-pixel tile [16 rows][8 pixels] of source 0
-          float sc[8], sh[8];
-          {
-            const float4* cf = reinterpret_cast<const float4*>(p.gn_coef + ((int64_t)b0 * p.gn_ctot + cch) * 2);
-            const float4 q0 = __ldg(cf), q1 = __ldg(cf + 1), q2 = __ldg(cf + 2), q3 = __ldg(cf + 3);
-            sc[0] = q0.x; sh[0] = q0.y; sc[1] = q0.z; sh[1] = q0.w; sc[2] = q1.x; sh[2] = q1.y; sc[3] = q1.z; sh[3] = q1.w;
-            sc[4] = q2.x; sh[4] = q2.y; sc[5] = q2.z; sh[5] = q2.w; sc[6] = q3.x; sh[6] = q3.y; sc[7] = q3.z; sh[7] = q3.w;
-          }
+        // which items are normalised: the halo chunks, or (normalised 1x1 conv, halo_nsrc == 0) source 0's plain tiles
+        const bool xf_plain = kind == 1 && map == 0 && p.halo_nsrc == 0 && cch < p.halo_c[0];
+        const bool xf_halo = kind == 0 && cch < p.halo_c[src];
+        if (p.gn_coef != nullptr && b0 < p.B && (xf_plain || xf_halo)) {
+          XfCoef k8;
+          k8.load(p.gn_coef + ((int64_t)b0 * p.gn_ctot + (xf_halo ? kcol + chunk * 8 : cch)) * 2);
           uint8_t* slot = sA + (size_t)stage * HA_STAGE_BYTES;
           const bool do_silu = p.gn_silu != 0;
+          if (xf_halo) {
 #pragma unroll 4
-          for (int i = 0; i < BM * 8 / XF_THREADS; ++i) {
-            const int pix = (t + XF_THREADS * i) >> 3;
-            if (y0 + (pix >> 3) < p.H) {             // rows past the image stay zero (never stored)
-              uint4* ptr = reinterpret_cast<uint4*>(slot + pix * 128 + ((chunk ^ (pix & 7)) << 4));
-              const uint4 vv = *ptr;
-              const float2 f0 = unpack_h2(vv.x), f1 = unpack_h2(vv.y), f2 = unpack_h2(vv.z), f3 = unpack_h2(vv.w);
-              float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                f[j] = fmaf(f[j], sc[j], sh[j]);
-                if (do_silu) f[j] = silu_f(f[j]);
+            for (int i = 0; i < (HALO_PIX * 8 + XF_THREADS - 1) / XF_THREADS; ++i) {
+              const int pix = (t + XF_THREADS * i) >> 3;
+              if (pix < HALO_PIX) {
+                const int hy = pix / HALO_W, hx = pix - hy * HALO_W;
+                const int iy = y0 - 1 + hy, ix = x0 - 1 + hx;
+                if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)        // out-of-image pixels stay zero (conv padding)
+                  k8.apply(reinterpret_cast<uint4*>(slot + pix * 128 + ((chunk ^ (pix & 7)) << 4)), do_silu);
               }
-              uint4 o;
-              o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
-              *ptr = o;
             }
-          }
-          fence_proxy_async_smem();
-        } else if (kind == 0 && p.gn_coef != nullptr && b0 < p.B && cch < p.halo_c[src]) {
-          float sc[8], sh[8];
-          {
-            const float4* cf = reinterpret_cast<const float4*>(p.gn_coef + ((int64_t)b0 * p.gn_ctot + kcol + chunk * 8) * 2);
-            const float4 q0 = __ldg(cf), q1 = __ldg(cf + 1), q2 = __ldg(cf + 2), q3 = __ldg(cf + 3);
-            sc[0] = q0.x; sh[0] = q0.y; sc[1] = q0.z; sh[1] = q0.w; sc[2] = q1.x; sh[2] = q1.y; sc[3] = q1.z; sh[3] = q1.w;
-            sc[4] = q2.x; sh[4] = q2.y; sc[5] = q2.z; sh[5] = q2.w; sc[6] = q3.x; sh[6] = q3.y; sc[7] = q3.z; sh[7] = q3.w;
-          }
-          uint8_t* slot = sA + (size_t)stage * HA_STAGE_BYTES;
-          const bool do_silu = p.gn_silu != 0;
+          } else {                                  // the plain 128-pixel tile [16 rows][8 pixels]
 #pragma unroll 4
-          for (int i = 0; i < (HALO_PIX * 8 + XF_THREADS - 1) / XF_THREADS; ++i) {
-            const int v = t + XF_THREADS * i;
-            const int pix = v >> 3;
-            if (pix < HALO_PIX) {
-              const int hy = pix / HALO_W, hx = pix - hy * HALO_W;
-              const int iy = y0 - 1 + hy, ix = x0 - 1 + hx;
-              if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) {      // out-of-image pixels stay zero (conv padding)
-                uint4* ptr = reinterpret_cast<uint4*>(slot + pix * 128 + ((chunk ^ (pix & 7)) << 4));
-                const uint4 vv = *ptr;
-                const float2 f0 = unpack_h2(vv.x), f1 = unpack_h2(vv.y), f2 = unpack_h2(vv.z), f3 = unpack_h2(vv.w);
-                float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  f[j] = fmaf(f[j], sc[j], sh[j]);
-                  if (do_silu) f[j] = silu_f(f[j]);
-                }
-                uint4 o;
-                o.x = pack_h2(f[0], f[1]); o.y = pack_h2(f[2], f[3]); o.z = pack_h2(f[4], f[5]); o.w = pack_h2(f[6], f[7]);
-                *ptr = o;
-              }
+            for (int i = 0; i < BM * 8 / XF_THREADS; ++i) {
+              const int pix = (t + XF_THREADS * i) >> 3;
+              if (y0 + (pix >> 3) < p.H)            // rows past the image stay zero (never stored)
+                k8.apply(reinterpret_cast<uint4*>(slot + pix * 128 + ((chunk ^ (pix & 7)) << 4)), do_silu);
             }
           }
           fence_proxy_async_smem();
