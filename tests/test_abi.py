@@ -88,6 +88,39 @@ def test_argument_validation_returns_error_codes(lib):
         lib.check(bad[0], "ldx_dpm_eps")
 
 
+def test_halo_conv_descriptor_validation(lib):
+    """The halo-tile conv's descriptor rules (include/ldx.h: halo_nsrc, gn_coef) are checked before any device work."""
+    l = lib.lib()
+    buf = ctypes.create_string_buffer(4096)
+    addr = ctypes.addressof(buf)
+
+    def desc(W=16, H=16, C=64, halo=1, flags=0, coef=None, nseg=0):
+        d = lib.GemmDesc()
+        d.nsrc = 1
+        d.src[0].ptr, d.src[0].C, d.src[0].W, d.src[0].H, d.src[0].B = addr, C, W, H, 1
+        d.src[0].sw, d.src[0].sh, d.src[0].sb = C, C * W, C * W * H
+        d.nseg, d.w, d.ldw, d.N = nseg, addr, 9 * 64, 64
+        d.W, d.H, d.B, d.out = W, H, 1, addr
+        d.o_sx, d.o_sy, d.o_sb = 64, 64 * W, 64 * W * H
+        d.flags, d.halo_nsrc = flags, halo
+        if coef:
+            d.gn_coef, d.gn_ctot = coef, C
+        return d
+
+    bad = [
+        l.ldx_gemm(ctypes.byref(desc(W=12)), None),                         # W % 8 != 0
+        l.ldx_gemm(ctypes.byref(desc(halo=3)), None),                       # at most two halo sources
+        l.ldx_gemm(ctypes.byref(desc(flags=lib.EPI_OUT_F32)), None),        # fp16 output only
+        l.ldx_gemm(ctypes.byref(desc(flags=lib.EPI_GEGLU)), None),
+        l.ldx_gemm(ctypes.byref(desc(C=60)), None),                         # C % 8 != 0
+        l.ldx_gemm(ctypes.byref(desc(coef=addr + 4)), None),                # coefficient table alignment
+        l.ldx_gemm(ctypes.byref(desc(halo=0, nseg=0)), None),               # a plain GEMM needs at least one segment
+        l.ldx_group_norm_coef(addr, 64, 64, None, 0, 0, 1, 256, 1e-5, addr, addr, addr, None, addr, None, 0, None, 0, None),
+        l.ldx_group_norm_coef(addr, 64, 64, None, 0, 0, 1, 256, 1e-5, addr, addr, addr, addr, None, None, 0, None, 0, None),
+    ]
+    assert all(rc == -1 for rc in bad), bad                                 # LDX_E_INVALID, nothing launched
+
+
 def test_product_never_imports_oracle():
     """The oracle is test infrastructure: nothing under lightdiffusion_b200/ may import it, except
     smoke.py, which uses it only as the checker."""
