@@ -27,11 +27,15 @@
 
 namespace ldx {
 
+#ifndef LDX_HALO_XF_UNROLL
+#define LDX_HALO_XF_UNROLL 4      // 16-byte pieces a transform thread keeps in flight (12 per halo tile and thread)
+#endif
 static constexpr int HALO_W = 10, HALO_H = 18, HALO_PIX = HALO_W * HALO_H;
 static constexpr int HA_STAGE_BYTES = 23 * 1024;            // 23 040 used, 1024-aligned slots
 static constexpr int HALO_THREADS = 512;
 static constexpr int HALO_MAX_A = 4, HALO_MAX_B = 8;
 static constexpr int XF_THREADS = 128;
+static constexpr int XF_UNROLL = LDX_HALO_XF_UNROLL;
 
 struct __align__(8) HaloBarriers {
   uint64_t a_full[HALO_MAX_A];    // TMA landed (local to each CTA)
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) ldx_conv_halo_kernel(const __
           uint8_t* slot = sA + (size_t)stage * HA_STAGE_BYTES;
           const bool do_silu = p.gn_silu != 0;
           if (xf_halo) {
-#pragma unroll 4
+#pragma unroll XF_UNROLL
             for (int i = 0; i < (HALO_PIX * 8 + XF_THREADS - 1) / XF_THREADS; ++i) {
               const int pix = (t + XF_THREADS * i) >> 3;
               if (pix < HALO_PIX) {
