@@ -156,6 +156,17 @@ int ldx_conv3x3_small(const void* x, int B, int H, int W, int Cin, int64_t ldx_p
 int ldx_pack_conv3x3_small(const void* w_oihw, void* w_packed, int cout, int cin, ldx_stream_t stream);
 /* number of fp16 elements ldx_pack_conv3x3_small writes (-1: unsupported Cout) */
 int ldx_conv3x3_small_packed_elems(int cout, int cin);
+/* The feed-forward of BasicTransformerBlock in one launch (x + ff(norm3(x)), LD.py:4155-4162; FeedForward / GEGLU,
+ * LD.py:4508-4536) for C = 320:  out = x + W2 . (a * gelu_erf(g)) + b2 with [a | g] = LayerNorm(x) . W1^T + b1.  The 4C-wide
+ * intermediate stays on chip (GEGLU epilogue -> shared memory -> operand of the second GEMM).
+ *   x          fp16 [M, ldx]  (also the residual)            out   fp16 [M, ldo]
+ *   w1_packed  ldx_pack_geglu(w1 * gamma, ..., half_bn = 64): [8C, ldw1] fp16, LayerNorm folded like LDX_EPI_ROWNORM
+ *   bias1, gsum1  fp32 [8C] in the same packed order (bias + w1 @ beta, rowsum(w1 * gamma))
+ *   w2 fp16 [C, ldw2] (F = 4C columns), bias2 fp32 [C]
+ *   rowstats   [M, parts, 2] fp32 (sum, sum of squares) of x's rows, written by the GEMM that produced x */
+int ldx_ff_geglu_fused(const void* x, int64_t ldx_, int M, const void* w1_packed, int64_t ldw1, const float* bias1,
+                       const float* gsum1, const void* w2, int64_t ldw2, const float* bias2, const float* rowstats,
+                       int parts, float eps, int C, int F, void* out, int64_t ldo, ldx_stream_t stream);
 /* GEGLU proj weight [2*F, K] (+ bias[2*F]) -> rows interleaved in blocks of `half_bn` so that one
  * output tile holds matching value/gate columns. */
 int ldx_pack_geglu(const void* w, const float* bias, void* w_packed, float* bias_packed, int two_f, int k,
@@ -301,6 +312,8 @@ enum {
   /* LDX_OP_ATTENTION takes i[5] = 1 for the causal variant (ldx_attention_causal) */
   LDX_OP_GROUP_NORM_COEF = 17, /* ldx_group_norm_coef.  p: x0, x1, gamma, beta, coef, stats, colstats0, colstats1, tickets ;
                                   i: c0, c1, B, HW, -, slots0, slots1 ; l: ld0, ld1 ; f: eps */
+  LDX_OP_FF_FUSED = 18,      /* ldx_ff_geglu_fused.  p: x, w1_packed, bias1, gsum1, w2, bias2, rowstats, out ;
+                                l: ldx, ldw1, ldw2, ldo ; i: M, C, F, parts ; f: eps */
   LDX_OP_CONV_SMALL = 16,    /* ldx_conv3x3_small.  p: x, w_packed, bias, out16, out_img ; i: B, H, W, Cin, Cout, post ;
                                 l: pixel pitch of x, pixel pitch of out16 */
   LDX_OP_CLIP_EMBED = 15,    /* p: tokens, tok_emb, pos_emb, out ; l: ldo ; i: rows, T, C */

@@ -24,6 +24,7 @@ OP_GEMM, OP_GROUP_NORM, OP_LAYER_NORM, OP_ATTENTION = 1, 2, 3, 4
 OP_NCHW_TO_NHWC, OP_TIMESTEP_EMB, OP_UPSAMPLE2X, OP_EPS_TO_DENOISED = 5, 6, 7, 8
 OP_CFG_DENOISED, OP_VAE_POST, OP_SOFTMAX = 9, 10, 11
 OP_DUP, OP_VAE_PRE, OP_VAE_SAMPLE, OP_CLIP_EMBED, OP_CONV_SMALL, OP_GROUP_NORM_COEF = 12, 13, 14, 15, 16, 17
+OP_FF_FUSED = 18
 
 GN_STATS_FLOATS_PER_BATCH = 64 * 32 * 2      # ldx_group_norm workspace: B * this many floats
 
@@ -89,6 +90,9 @@ _SIGS = {
     "ldx_group_norm_coef": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int,
                                       C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "ldx_ff_geglu_fused": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_int64, C.c_void_p]),
     "ldx_layer_norm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int64, C.c_void_p]),
     "ldx_attention": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

@@ -46,12 +46,16 @@ void attention_free_handle(void* handle);
 int conv_small_prepare_op(const ldx_generic_op_t* op, void** handle);
 int conv_small_run_handle(void* handle, cudaStream_t st);
 void conv_small_free_handle(void* handle);
+int ff_fused_prepare_op(const ldx_generic_op_t* op, void** handle);
+int ff_fused_run_handle(void* handle, cudaStream_t st);
+void ff_fused_free_handle(void* handle);
 
 struct ProgOp {
   int kind;
   GemmLaunch* gemm = nullptr;
   void* attn = nullptr;
   void* conv_small = nullptr;
+  void* ff = nullptr;
   ldx_generic_op_t gen;
   int launches = 1;
   void* ws = nullptr;          // split-K workspace (cudaMalloc)
@@ -135,6 +139,9 @@ extern "C" int ldx_program_add_op(ldx_program_t* prog, const ldx_generic_op_t* g
   } else if (gop->kind == LDX_OP_CONV_SMALL) {
     int rc = conv_small_prepare_op(gop, &op.conv_small);
     if (rc) return rc;
+  } else if (gop->kind == LDX_OP_FF_FUSED) {
+    int rc = ff_fused_prepare_op(gop, &op.ff);
+    if (rc) return rc;
   } else if (gop->kind == LDX_OP_GROUP_NORM) {
     op.launches = group_norm_num_launches(gop->i[0] + gop->i[1], gop->i[3]);
   } else if (gop->kind == LDX_OP_DUP) {
@@ -163,6 +170,7 @@ extern "C" int ldx_program_run(ldx_program_t* prog, ldx_stream_t stream) {
     if (op.kind == LDX_OP_GEMM) rc = gemm_launch(op.gemm, st);
     else if (op.kind == LDX_OP_ATTENTION) rc = attention_run_handle(op.attn, st);
     else if (op.kind == LDX_OP_CONV_SMALL) rc = conv_small_run_handle(op.conv_small, st);
+    else if (op.kind == LDX_OP_FF_FUSED) rc = ff_fused_run_handle(op.ff, st);
     else rc = run_generic_op(&op.gen, st);
     if (rc) return rc;
   }
@@ -191,6 +199,7 @@ extern "C" int ldx_program_run_timed(ldx_program_t* prog, ldx_stream_t stream, f
     if (op.kind == LDX_OP_GEMM) rc = gemm_launch(op.gemm, st);
     else if (op.kind == LDX_OP_ATTENTION) rc = attention_run_handle(op.attn, st);
     else if (op.kind == LDX_OP_CONV_SMALL) rc = conv_small_run_handle(op.conv_small, st);
+    else if (op.kind == LDX_OP_FF_FUSED) rc = ff_fused_run_handle(op.ff, st);
     else rc = run_generic_op(&op.gen, st);
     if (rc == LDX_OK && cudaEventRecord(ev[i + 1], st) != cudaSuccess) rc = LDX_E_CUDA;
   }
@@ -212,6 +221,7 @@ extern "C" void ldx_program_destroy(ldx_program_t* prog) {
     if (op.ws) cudaFree(op.ws);
     if (op.attn) attention_free_handle(op.attn);
     if (op.conv_small) conv_small_free_handle(op.conv_small);
+    if (op.ff) ff_fused_free_handle(op.ff);
   }
   delete prog;
 }

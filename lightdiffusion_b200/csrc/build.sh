@@ -7,7 +7,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompil
 OBJS=""
 PIDS=""
 mkdir -p build
-for f in api gemm elementwise attention conv_small conv_halo xattn; do
+for f in api gemm elementwise attention conv_small conv_halo xattn ff_fused; do
   if [ ! -f build/$f.o ] || [ $f.cu -nt build/$f.o ] || [ common.cuh -nt build/$f.o ] || [ internal.h -nt build/$f.o ] || [ gemm_tile.cuh -nt build/$f.o ] || [ ../../include/ldx.h -nt build/$f.o ]; then
     rm -f build/$f.o
     ( $NVCC $FLAGS -c $f.cu -o build/$f.o 2> build/$f.log || { cat build/$f.log; exit 1; } ) &

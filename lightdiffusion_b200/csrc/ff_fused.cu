@@ -1,0 +1,462 @@
+// Fused feed-forward of BasicTransformerBlock at C = 320 (LD.py:4155-4162 with FeedForward / GEGLU, LD.py:4508-4536):
+//
+//     out = x + W2 · ( a * gelu_erf(g) ) + b2,   [a | g] = LayerNorm(x) · W1^T + b1      (x: [M, C], W1: [8C, C], W2: [C, 4C])
+//
+// in ONE kernel, so that the 4C-wide GEGLU intermediate (168 MB per launch at the 64 x 64 level of the SD1.5 UNet,
+// written by one GEMM and re-read by the next) never reaches HBM.  The GEGLU GEMM there is epilogue bound (the erf-GELU
+// on 128 outputs per row and tile is ~5.8 k clocks against 2.6 k of MMA) and the second GEMM is bound by re-reading the
+// intermediate; fused, the second GEMM's MMAs hide under the first one's epilogue.
+//
+// A CTA pair (cta_group::2) owns 256 rows.  Per pair tile:
+//   * A1 = the 256 x 320 input rows stay resident in shared memory (5 K-major SWIZZLE_128B chunks per CTA); they are also
+//     the residual: five N = 64 identity MMA chains initialise the output accumulator with them;
+//   * for each of the 4C / 64 = 20 chunks of the intermediate: S = A1 · W1_j^T (N = 128: 64 value + 64 gate columns, W1
+//     rows interleaved by ldx_pack_geglu(half_bn = 64)) into TMEM; eight epilogue warps apply the folded LayerNorm
+//     (rstd * (acc - mean * gsum) + bias', statistics from the producer of x), the GEGLU gate and round to fp16 INTO
+//     SHARED MEMORY as the A operand of the second GEMM (K-major SWIZZLE_128B, double buffered); then
+//     O += A2_j · W2[:, 64j : 64j + 64]^T (two N = 160 chains: UMMA N <= 256) accumulates the 320 output columns in TMEM;
+//   * a final epilogue adds b2 and stores the fp16 rows by TMA.
+// warp 0: TMA producer of A1 and the W1 ring; warp 2: TMA producer of the W2 ring and the identity; warp 1: MMA issuer
+// (leader CTA); warps 4-11: epilogue.  TMEM: S 128 columns + O 320 columns.  Shared memory per CTA: A1 80 KB, W1 ring
+// 4 x 8 KB, W2 ring 2 x 20 KB, A2 2 x 16 KB, identity 4 KB, store staging 8 x 4 KB = 220 KB.
+// Roofline: the GEGLU epilogue (issue / MUFU) and the tensor pipe (2 * M * (8C * C + 4C * C) FLOPs); HBM traffic is x in,
+// out, and the weights once per pair tile from L2.
+#include <stdlib.h>
+
+#include "gemm_tile.cuh"
+
+namespace ldx {
+
+const void* identity_matrix();        // gemm.cu: IDENT_N x IDENT_N fp16 identity of the current device
+int identity_matrix_n();
+
+static constexpr int FF_C = 320;                      // model width this kernel is built for
+static constexpr int FF_KCH = FF_C / 64;              // K chunks of the first GEMM = 64-column blocks of the output
+static constexpr int FF_THREADS = 384;
+static constexpr int FF_NW1 = 4, FF_NW2 = 2;
+static constexpr int FF_A1_BYTES = FF_KCH * BM * 128;         // 80 KB
+static constexpr int FF_W1_STAGE = 64 * 128;                  // this CTA's 64 of the chunk's 128 rows x 64 K
+static constexpr int FF_W2_STAGE = 160 * 128;                 // this CTA's 2 x 80 of the 320 output rows x 64 K
+static constexpr int FF_A2_BYTES = BM * 128;
+static constexpr int FF_ID_BYTES = 32 * 128;
+static constexpr int FF_OUT_SLOT = 32 * 128;
+static constexpr int FF_TMEM_S = 0, FF_TMEM_O = 128;
+
+struct __align__(8) FfBarriers {
+  uint64_t a1_full, a1_empty, id_full;
+  uint64_t w1_full[FF_NW1], w1_empty[FF_NW1], w2_full[FF_NW2], w2_empty[FF_NW2];
+  uint64_t s_full, s_free, a2_full[2], a2_empty[2], o_full, o_free;
+  uint32_t tmem_base;
+};
+
+static constexpr int FF_SMEM = FF_A1_BYTES + FF_NW1 * FF_W1_STAGE + FF_NW2 * FF_W2_STAGE + 2 * FF_A2_BYTES + FF_ID_BYTES +
+                               8 * FF_OUT_SLOT + (int)sizeof(FfBarriers) + 1024;
+static_assert(FF_SMEM <= 227 * 1024, "smem budget");
+
+struct alignas(64) FfParams {
+  CUtensorMap xmap;    // x [M, C]: box (64, 128)
+  CUtensorMap w1map;   // packed W1' [8C, C]: box (64, 64)
+  CUtensorMap w2map;   // W2 [C, 4C]: box (64, 80)
+  CUtensorMap idmap;   // identity: box (64, 32)
+  CUtensorMap omap;    // out [M, C]: box (64, 32), store
+  const float* bias1;  // [8C] packed like W1'
+  const float* gsum1;  // [8C] packed like W1'
+  const float* bias2;  // [C]
+  const float* rowstats;   // [M][parts][2]
+  int32_t parts, M, nchunks, num_tiles;
+  float ln_eps, ln_inv_c;
+};
+
+__global__ void __launch_bounds__(FF_THREADS, 1) ldx_ff_fused_kernel(const __grid_constant__ FfParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* sA1 = smem;
+  uint8_t* sW1 = sA1 + FF_A1_BYTES;
+  uint8_t* sW2 = sW1 + FF_NW1 * FF_W1_STAGE;
+  uint8_t* sA2 = sW2 + FF_NW2 * FF_W2_STAGE;
+  uint8_t* sI = sA2 + 2 * FF_A2_BYTES;
+  uint8_t* sOut = sI + FF_ID_BYTES;
+  FfBarriers* bars = reinterpret_cast<FfBarriers*>(sOut + 8 * FF_OUT_SLOT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const int worker = (int)blockIdx.x / 2, nworkers = (int)gridDim.x / 2;
+  const int nch = p.nchunks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.xmap);
+    tma_prefetch_desc(&p.w1map);
+    tma_prefetch_desc(&p.w2map);
+    tma_prefetch_desc(&p.idmap);
+    tma_prefetch_desc(&p.omap);
+    mbar_init(&bars->a1_full, 1);
+    mbar_init(&bars->a1_empty, 1);
+    mbar_init(&bars->id_full, 1);
+    for (int i = 0; i < FF_NW1; ++i) { mbar_init(&bars->w1_full[i], 1); mbar_init(&bars->w1_empty[i], 1); }
+    for (int i = 0; i < FF_NW2; ++i) { mbar_init(&bars->w2_full[i], 1); mbar_init(&bars->w2_empty[i], 1); }
+    mbar_init(&bars->s_full, 1);
+    mbar_init(&bars->s_free, 16);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->a2_full[i], 16); mbar_init(&bars->a2_empty[i], 1); }
+    mbar_init(&bars->o_full, 1);
+    mbar_init(&bars->o_free, 16);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(&bars->tmem_base, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  pdl_prologue();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ producer: A1 per tile, W1 ring
+    int st = 0;
+    uint32_t ph = 0;
+    int it = 0;
+    for (int tile = worker; tile < p.num_tiles; tile += nworkers, ++it) {
+      mbar_wait(&bars->a1_empty, (uint32_t)((it & 1) ^ 1));
+      {
+        const uint32_t lbar = mapa_shared(smem_u32(&bars->a1_full), 0);
+        if (elect_one()) {
+          if (cta_rank == 0) mbar_arrive_expect_tx(&bars->a1_full, 2 * FF_A1_BYTES);
+          for (int c = 0; c < FF_KCH; ++c)
+            tma_load_2d_pair(sA1 + c * (BM * 128), &p.xmap, lbar, c * 64, tile * 256 + (int)cta_rank * BM);
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < nch; ++j)
+        for (int ks = 0; ks < FF_KCH; ++ks) {
+          mbar_wait(&bars->w1_empty[st], ph ^ 1);
+          const uint32_t lbar = mapa_shared(smem_u32(&bars->w1_full[st]), 0);
+          if (elect_one()) {
+            if (cta_rank == 0) mbar_arrive_expect_tx(&bars->w1_full[st], 2 * FF_W1_STAGE);
+            tma_load_2d_pair(sW1 + st * FF_W1_STAGE, &p.w1map, lbar, ks * 64, j * 128 + (int)cta_rank * 64);
+          }
+          __syncwarp();
+          if (++st == FF_NW1) { st = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ producer: identity once, W2 ring
+    {
+      const uint32_t lbar = mapa_shared(smem_u32(&bars->id_full), 0);
+      if (elect_one()) {
+        if (cta_rank == 0) mbar_arrive_expect_tx(&bars->id_full, 2 * FF_ID_BYTES);
+        tma_load_2d_pair(sI, &p.idmap, lbar, 0, (int)cta_rank * 32);
+      }
+      __syncwarp();
+    }
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = worker; tile < p.num_tiles; tile += nworkers)
+      for (int j = 0; j < nch; ++j) {
+        mbar_wait(&bars->w2_empty[st], ph ^ 1);
+        const uint32_t lbar = mapa_shared(smem_u32(&bars->w2_full[st]), 0);
+        if (elect_one()) {
+          if (cta_rank == 0) mbar_arrive_expect_tx(&bars->w2_full[st], 2 * FF_W2_STAGE);
+          tma_load_2d_pair(sW2 + st * FF_W2_STAGE, &p.w2map, lbar, j * 64, (int)cta_rank * 80);
+          tma_load_2d_pair(sW2 + st * FF_W2_STAGE + 80 * 128, &p.w2map, lbar, j * 64, 160 + (int)cta_rank * 80);
+        }
+        __syncwarp();
+        if (++st == FF_NW2) { st = 0; ph ^= 1; }
+      }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA)
+    if (cta_rank == 0) {
+      const uint32_t idesc_s = umma_idesc_f16(256, 128), idesc_o = umma_idesc_f16(256, 160), idesc_i = umma_idesc_f16(256, 64);
+      const uint32_t tS = tmem_base + FF_TMEM_S, tO = tmem_base + FF_TMEM_O;
+      const uint32_t a1 = smem_u32(sA1), a2 = smem_u32(sA2), w1 = smem_u32(sW1), w2 = smem_u32(sW2), idb = smem_u32(sI);
+      int st1 = 0, st2 = 0;
+      uint32_t ph1 = 0, ph2 = 0;
+      int gch = 0;                                   // running chunk index over all tiles of this pair
+      int it = 0;
+      auto mma1 = [&](int g) {                       // S = A1 . W1_j^T
+        if (g >= 1) mbar_wait(&bars->s_free, (uint32_t)((g - 1) & 1));
+        for (int ks = 0; ks < FF_KCH; ++ks) {
+          mbar_wait(&bars->w1_full[st1], ph1);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss_pair(tS, umma_desc_kmajor_sw128(a1 + ks * (BM * 128) + k * 32),
+                               umma_desc_kmajor_sw128(w1 + st1 * FF_W1_STAGE + k * 32), idesc_s, (uint32_t)((ks | k) != 0));
+            umma_commit_pair(&bars->w1_empty[st1], 3);
+            if (ks == FF_KCH - 1) umma_commit_pair(&bars->s_full, 3);
+          }
+          __syncwarp();
+          if (++st1 == FF_NW1) { st1 = 0; ph1 ^= 1; }
+        }
+      };
+      auto mma2 = [&](int g) {                       // O += A2_j . W2_j^T
+        const int buf = g & 1;
+        mbar_wait(&bars->a2_full[buf], (uint32_t)((g >> 1) & 1));
+        mbar_wait(&bars->w2_full[st2], ph2);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = umma_desc_kmajor_sw128(a2 + buf * FF_A2_BYTES + k * 32);
+            umma_f16_ss_pair(tO, ad, umma_desc_kmajor_sw128(w2 + st2 * FF_W2_STAGE + k * 32), idesc_o, 1u);
+            umma_f16_ss_pair(tO + 160, ad, umma_desc_kmajor_sw128(w2 + st2 * FF_W2_STAGE + 80 * 128 + k * 32), idesc_o, 1u);
+          }
+          umma_commit_pair(&bars->a2_empty[buf], 3);
+          umma_commit_pair(&bars->w2_empty[st2], 3);
+        }
+        __syncwarp();
+        if (++st2 == FF_NW2) { st2 = 0; ph2 ^= 1; }
+      };
+      mbar_wait(&bars->id_full, 0);
+      for (int tile = worker; tile < p.num_tiles; tile += nworkers, ++it) {
+        mbar_wait(&bars->a1_full, (uint32_t)(it & 1));
+        tc_fence_after();
+        mma1(gch);
+        // the residual: O = x through five 64-column identity chains (after the previous tile's output has been read)
+        if (it >= 1) mbar_wait(&bars->o_free, (uint32_t)((it - 1) & 1));
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int dk = 0; dk < FF_KCH; ++dk)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss_pair(tO + dk * 64, umma_desc_kmajor_sw128(a1 + dk * (BM * 128) + k * 32),
+                               umma_desc_kmajor_sw128(idb + k * 32), idesc_i, (uint32_t)(k != 0));
+        }
+        __syncwarp();
+        for (int j = 1; j < nch; ++j) {
+          mma1(gch + j);
+          if (j == nch - 1) {                        // A1 has been read for the last time
+            if (elect_one()) umma_commit_pair(&bars->a1_empty, 3);
+            __syncwarp();
+          }
+          mma2(gch + j - 1);
+        }
+        if (nch == 1) {
+          if (elect_one()) umma_commit_pair(&bars->a1_empty, 3);
+          __syncwarp();
+        }
+        mma2(gch + nch - 1);
+        if (elect_one()) umma_commit_pair(&bars->o_full, 3);
+        __syncwarp();
+        gch += nch;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue warps
+    const int e = warp - 4;
+    const int q = warp & 3, hsel = e >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t tS = tmem_base + FF_TMEM_S + lane_off, tO = tmem_base + FF_TMEM_O + lane_off;
+    const uint32_t r_sfree = mapa_shared(smem_u32(&bars->s_free), 0);
+    const uint32_t r_a2full0 = mapa_shared(smem_u32(&bars->a2_full[0]), 0);
+    const uint32_t r_ofree = mapa_shared(smem_u32(&bars->o_free), 0);
+    uint8_t* slot = sOut + e * FF_OUT_SLOT;
+    int gch = 0, it = 0;
+    for (int tile = worker; tile < p.num_tiles; tile += nworkers, ++it) {
+      const int m = tile * 256 + (int)cta_rank * BM + row;
+      // LayerNorm statistics of this row (left by the GEMM that produced x), fixed summation order
+      float ln_a = 1.f, ln_b = 0.f;
+      if (m < p.M) {
+        float s1 = 0.f, s2 = 0.f;
+        const float2* stp = reinterpret_cast<const float2*>(p.rowstats) + (int64_t)m * p.parts;
+        for (int i = 0; i < p.parts; ++i) {
+          const float2 t2 = __ldg(stp + i);
+          s1 += t2.x;
+          s2 += t2.y;
+        }
+        const float mean = s1 * p.ln_inv_c;
+        const float rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - mean * mean, 0.f) + p.ln_eps);
+        ln_a = rstd;
+        ln_b = -mean * rstd;
+      }
+      for (int j = 0; j < nch; ++j) {
+        const int g = gch + j, buf = g & 1;
+        uint32_t ra[32], rg[32];
+        mbar_wait(&bars->s_full, (uint32_t)(g & 1));
+        tc_fence_after();
+        tmem_ld32(tS + 32 * hsel, ra);
+        tmem_ld32(tS + 64 + 32 * hsel, rg);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(r_sfree);
+        const float4* bv = reinterpret_cast<const float4*>(p.bias1 + j * 128 + 32 * hsel);
+        const float4* gv = reinterpret_cast<const float4*>(p.gsum1 + j * 128 + 32 * hsel);
+        if (g >= 2) mbar_wait(&bars->a2_empty[buf], (uint32_t)(((g >> 1) - 1) & 1));   // O += A2(g - 2) has read the buffer
+        uint8_t* arow = sA2 + buf * FF_A2_BYTES + row * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float v[8];
+#pragma unroll
+          for (int h4 = 0; h4 < 2; ++h4) {
+            const int j4 = ch * 2 + h4;
+            float4 ba = __ldg(bv + j4), bg = __ldg(bv + 16 + j4);
+            const float4 ga = __ldg(gv + j4), gg = __ldg(gv + 16 + j4);
+            ba.x = fmaf(ga.x, ln_b, ba.x); ba.y = fmaf(ga.y, ln_b, ba.y); ba.z = fmaf(ga.z, ln_b, ba.z); ba.w = fmaf(ga.w, ln_b, ba.w);
+            bg.x = fmaf(gg.x, ln_b, bg.x); bg.y = fmaf(gg.y, ln_b, bg.y); bg.z = fmaf(gg.z, ln_b, bg.z); bg.w = fmaf(gg.w, ln_b, bg.w);
+            v[h4 * 4 + 0] = fmaf(__uint_as_float(ra[j4 * 4 + 0]), ln_a, ba.x) * gelu_erf_fast(fmaf(__uint_as_float(rg[j4 * 4 + 0]), ln_a, bg.x));
+            v[h4 * 4 + 1] = fmaf(__uint_as_float(ra[j4 * 4 + 1]), ln_a, ba.y) * gelu_erf_fast(fmaf(__uint_as_float(rg[j4 * 4 + 1]), ln_a, bg.y));
+            v[h4 * 4 + 2] = fmaf(__uint_as_float(ra[j4 * 4 + 2]), ln_a, ba.z) * gelu_erf_fast(fmaf(__uint_as_float(rg[j4 * 4 + 2]), ln_a, bg.z));
+            v[h4 * 4 + 3] = fmaf(__uint_as_float(ra[j4 * 4 + 3]), ln_a, ba.w) * gelu_erf_fast(fmaf(__uint_as_float(rg[j4 * 4 + 3]), ln_a, bg.w));
+          }
+          uint4 o;
+          o.x = pack_h2(v[0], v[1]); o.y = pack_h2(v[2], v[3]); o.z = pack_h2(v[4], v[5]); o.w = pack_h2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(arow + (((hsel * 4 + ch) ^ (row & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(r_a2full0 + (uint32_t)buf * 8u);
+      }
+      gch += nch;
+      // ---- output rows: O (already holds x + sum_j A2_j W2_j^T) + b2 -> fp16 -> TMA store
+      mbar_wait(&bars->o_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      const int npass = FF_KCH;                      // 64-column passes; this warp takes hsel, hsel + 2, ...
+      for (int ps = hsel; ps < npass; ps += 2) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(tO + ps * 64, r0);
+        tmem_ld32(tO + ps * 64 + 32, r1);
+        const float4* b2 = reinterpret_cast<const float4*>(p.bias2 + ps * 64);
+        if (lane == 0) tma_store_wait_read<0>();     // the slot's previous store has drained it
+        tmem_ld_wait();
+        if (ps + 2 >= npass) {                       // all of this warp's columns are out of TMEM
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(r_ofree);
+        } else {
+          __syncwarp();
+        }
+        uint8_t* srow = slot + lane * 128;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t* r = ch < 4 ? r0 : r1;
+          const int c0 = (ch & 3) * 8;
+          const float4 ba = __ldg(b2 + ch * 2), bb = __ldg(b2 + ch * 2 + 1);
+          uint4 o;
+          o.x = pack_h2(__uint_as_float(r[c0 + 0]) + ba.x, __uint_as_float(r[c0 + 1]) + ba.y);
+          o.y = pack_h2(__uint_as_float(r[c0 + 2]) + ba.z, __uint_as_float(r[c0 + 3]) + ba.w);
+          o.z = pack_h2(__uint_as_float(r[c0 + 4]) + bb.x, __uint_as_float(r[c0 + 5]) + bb.y);
+          o.w = pack_h2(__uint_as_float(r[c0 + 6]) + bb.z, __uint_as_float(r[c0 + 7]) + bb.w);
+          *reinterpret_cast<uint4*>(srow + ((ch ^ (lane & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&p.omap)),
+                       "r"(smem_u32(slot)), "r"(ps * 64), "r"(tile * 256 + (int)cta_rank * BM + q * 32)
+                       : "memory");
+          tma_store_commit();
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+struct FfLaunch {
+  FfParams p;
+  int grid;
+};
+
+int encode_map_f16(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+static int ff_fused_prepare(const void* x, int64_t ldx_, int M, const void* w1p, int64_t ldw1, const float* bias1,
+                            const float* gsum1, const void* w2, int64_t ldw2, const float* bias2, const float* rowstats,
+                            int parts, float eps, int C, int F, void* out, int64_t ldo, FfLaunch* L) {
+  LDX_CHECK_ARG(x && w1p && bias1 && gsum1 && w2 && bias2 && rowstats && out, "ff_fused: null pointer");
+  LDX_CHECK_ARG(C == FF_C, "ff_fused: built for C = %d, got %d", FF_C, C);
+  LDX_CHECK_ARG(F >= 64 && F % 64 == 0 && M >= 1 && parts >= 1 && parts <= 256, "ff_fused: bad extents");
+  LDX_CHECK_ARG(reinterpret_cast<uintptr_t>(bias1) % 16 == 0 && reinterpret_cast<uintptr_t>(gsum1) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(bias2) % 16 == 0,
+                "ff_fused: bias / gsum vectors must be 16-byte aligned");
+  memset(&L->p, 0, sizeof(L->p));
+  FfParams& p = L->p;
+  int rc;
+  {
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)M};
+    const uint64_t str[1] = {(uint64_t)ldx_ * 2};
+    const uint32_t box[2] = {64, (uint32_t)BM};
+    if ((rc = encode_map_f16(&p.xmap, x, 2, dims, str, box))) return rc;
+    const uint64_t ostr[1] = {(uint64_t)ldo * 2};
+    const uint32_t obox[2] = {64, 32};
+    if ((rc = encode_map_f16(&p.omap, out, 2, dims, ostr, obox))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)(2 * F)};
+    const uint64_t str[1] = {(uint64_t)ldw1 * 2};
+    const uint32_t box[2] = {64, 64};
+    if ((rc = encode_map_f16(&p.w1map, w1p, 2, dims, str, box))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)F, (uint64_t)C};
+    const uint64_t str[1] = {(uint64_t)ldw2 * 2};
+    const uint32_t box[2] = {64, 80};
+    if ((rc = encode_map_f16(&p.w2map, w2, 2, dims, str, box))) return rc;
+  }
+  {
+    const void* ident = identity_matrix();
+    LDX_CHECK_ARG(ident != nullptr, "identity matrix allocation failed");
+    const uint64_t n = (uint64_t)identity_matrix_n();
+    const uint64_t dims[2] = {n, n};
+    const uint64_t str[1] = {n * 2};
+    const uint32_t box[2] = {64, 32};
+    if ((rc = encode_map_f16(&p.idmap, ident, 2, dims, str, box))) return rc;
+  }
+  p.bias1 = bias1; p.gsum1 = gsum1; p.bias2 = bias2; p.rowstats = rowstats;
+  p.parts = parts; p.M = M; p.nchunks = F / 64;
+  p.num_tiles = (M + 255) / 256;
+  p.ln_eps = eps;
+  p.ln_inv_c = 1.0f / (float)C;
+  const int workers = num_sms() / 2;
+  L->grid = 2 * (p.num_tiles < workers ? p.num_tiles : workers);
+  return LDX_OK;
+}
+
+static int ff_fused_launch(const FfLaunch* L, cudaStream_t st) {
+  static std::atomic<uint64_t> attr_done{0};
+  int arc = set_max_dyn_smem_once(ldx_ff_fused_kernel, 227 * 1024, attr_done);
+  if (arc) return arc;
+  LDX_CUDA(launch_k(ldx_ff_fused_kernel, dim3(L->grid), dim3(FF_THREADS), (size_t)FF_SMEM, st, 2, L->p));
+  return LDX_OK;
+}
+
+// program support (api.cu).  p: x, w1p, bias1, gsum1, w2, bias2, rowstats, out ; l: ldx, ldw1, ldw2, ldo ;
+// i: M, C, F, parts ; f: eps
+int ff_fused_prepare_op(const ldx_generic_op_t* op, void** handle) {
+  FfLaunch* L = new FfLaunch;
+  int rc = ff_fused_prepare(op->p[0], op->l[0], op->i[0], op->p[1], op->l[1], (const float*)op->p[2], (const float*)op->p[3],
+                            op->p[4], op->l[2], (const float*)op->p[5], (const float*)op->p[6], op->i[3], op->f[0], op->i[1],
+                            op->i[2], (void*)op->p[7], op->l[3], L);
+  if (rc) {
+    delete L;
+    return rc;
+  }
+  *handle = L;
+  return LDX_OK;
+}
+int ff_fused_run_handle(void* handle, cudaStream_t st) { return ff_fused_launch((FfLaunch*)handle, st); }
+void ff_fused_free_handle(void* handle) { delete (FfLaunch*)handle; }
+
+}  // namespace ldx
+
+using namespace ldx;
+
+extern "C" int ldx_ff_geglu_fused(const void* x, int64_t ldx_, int M, const void* w1_packed, int64_t ldw1, const float* bias1,
+                                  const float* gsum1, const void* w2, int64_t ldw2, const float* bias2,
+                                  const float* rowstats, int parts, float eps, int C, int F, void* out, int64_t ldo,
+                                  ldx_stream_t stream) {
+  FfLaunch L;
+  int rc = ff_fused_prepare(x, ldx_, M, w1_packed, ldw1, bias1, gsum1, w2, ldw2, bias2, rowstats, parts, eps, C, F, out, ldo, &L);
+  if (rc) return rc;
+  return ff_fused_launch(&L, as_stream(stream));
+}

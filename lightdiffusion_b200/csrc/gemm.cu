@@ -762,6 +762,9 @@ static const void* identity256() {
   return dev_ptr[dev];
 }
 
+const void* identity_matrix() { return identity256(); }      // for the other translation units (ff_fused.cu)
+int identity_matrix_n() { return IDENT_N; }
+
 // Zero fp32 vector: stands in for a missing bias so the TMA-store epilogue needs no null checks.
 static const float* zeros_f32(int n) {
   static float* dev_ptr[LDX_MAX_DEVICES] = {};

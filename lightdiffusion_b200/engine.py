@@ -65,6 +65,9 @@ HALO_MIN_TILES = int(os.environ.get("LDX_HALO_MIN_TILES", "32"))
 # slower on B200 (UNet step +0.17 ms: with one MMA chain of 5-20 K steps per item instead of nine, the three-deep
 # operand ring cannot cover TMA latency + transform), so it is off by default; LDX_HALO_1X1=1 enables it.
 HALO_1X1 = os.environ.get("LDX_HALO_1X1", "0") == "1"
+# The feed-forward of the 320-channel transformer blocks (GEGLU projection + second Linear + residual, LD.py:4155-4162) as
+# ONE kernel whose 4C-wide intermediate stays on chip (csrc/ff_fused.cu).  LDX_FF_FUSED=0 keeps the two GEMMs (A/B).
+FF_FUSED = os.environ.get("LDX_FF_FUSED", "1") == "1"
 FUSE_GN_STATS = os.environ.get("LDX_FUSE_GN_STATS", "1") == "1"
 GN_STATS_MIN_HW = int(os.environ.get("LDX_GN_STATS_MIN_HW", "16384"))
 
@@ -287,6 +290,9 @@ class UNetEngine:
                                            *ln("norm3"))
             w[p + ".ff1.w"], w[p + ".ff1.b"] = K.pack_geglu(wf, bf, 128)
             _, w[p + ".ff1.g"] = K.pack_geglu(wf, gf, 128)
+            if FF_FUSED and s.ch == 320:           # the fused feed-forward kernel interleaves value / gate rows by 64
+                w[p + ".ff1.w64"], w[p + ".ff1.b64"] = K.pack_geglu(wf, bf, 64)
+                _, w[p + ".ff1.g64"] = K.pack_geglu(wf, gf, 64)
         else:
             w[p + ".norm3.g"], w[p + ".norm3.b"] = _f32(sd, t + ".norm3.weight", dev), _f32(sd, t + ".norm3.bias", dev)
             w[p + ".ff1.w"], w[p + ".ff1.b"] = K.pack_geglu(sd[t + ".ff.net.0.proj.weight"],
@@ -506,6 +512,17 @@ class UNetPlan(_GnStatsMixin):
         self.prog.add(d)
         pool.free(a2); pool.free(t2); pool.free(q2)
         # feed-forward (the GEGLU gate lives in the first GEMM's epilogue)
+        if (p + ".ff1.w64") in w:
+            t4 = pool.alloc(m, c)
+            self.prog.add(K.ff_fused_op(t3, w[p + ".ff1.w64"], w[p + ".ff1.b64"], w[p + ".ff1.g64"], w[p + ".ff2.w"],
+                                        w[p + ".ff2.b"], st3, t4))
+            pool.free(t3)
+            out = pool.alloc(Bn, h, wd, c)
+            self._produce(K.linear_desc(t4, w[p + ".pout.w"], out, bias=w[p + ".pout.b"], residual=x), out)
+            pool.free(t4)
+            if expand:
+                pool.free(x)
+            return out
         g = pool.alloc(m, 4 * c)
         if FUSE_LN3:
             self.prog.add(K.linear_desc(t3, w[p + ".ff1.w"], g, bias=w[p + ".ff1.b"], flags=L.EPI_GEGLU, bn=256,

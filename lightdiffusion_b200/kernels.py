@@ -417,6 +417,19 @@ def group_norm_coef_op(x0, x1, gamma, beta, coef, stats, tickets, eps: float, co
                       l=[x0.stride(2), 0 if x1 is None else x1.stride(2)], f=[eps])
 
 
+def ff_fused_op(x2, w1p, bias1, gsum1, w2, bias2, rowstats, out2, eps=1e-5) -> L.GenericOp:
+    """out = x + W2 . GEGLU(LayerNorm(x) . W1^T + b1) + b2 in one launch (C = 320).  w1p / bias1 / gsum1: the LayerNorm-folded
+    GEGLU projection packed with pack_geglu(half_bn=64); rowstats [M, parts, 2]: row statistics of x from its producer."""
+    m, c = x2.shape
+    f = w2.shape[1]
+    assert x2.dtype == torch.float16 and out2.dtype == torch.float16 and tuple(out2.shape) == (m, c)
+    assert w1p.shape[0] == 2 * f and w1p.stride(1) == 1 and w2.shape[0] == c and w2.stride(1) == 1
+    assert rowstats.dtype == torch.float32 and rowstats.is_contiguous() and rowstats.shape[0] == m and rowstats.shape[2] == 2
+    return generic_op(L.OP_FF_FUSED, p=[x2.data_ptr(), w1p.data_ptr(), bias1.data_ptr(), gsum1.data_ptr(), w2.data_ptr(),
+                                        bias2.data_ptr(), rowstats.data_ptr(), out2.data_ptr()],
+                      l=[x2.stride(0), w1p.stride(0), w2.stride(0), out2.stride(0)], i=[m, c, f, rowstats.shape[1]], f=[eps])
+
+
 def layer_norm_op(x2, gamma, beta, y2, eps=1e-5) -> L.GenericOp:
     rows, c = x2.shape
     return generic_op(L.OP_LAYER_NORM, p=[x2.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y2.data_ptr()],
@@ -466,6 +479,9 @@ class Program:
             if op.kind == L.OP_ATTENTION:
                 b, nq, nk, heads, d = (op.i[j] for j in range(5))
                 flops, tag = 4.0 * b * nq * nk * heads * d, (b, nq, nk, heads, d)
+            elif op.kind == L.OP_FF_FUSED:
+                m, c, f = op.i[0], op.i[1], op.i[2]
+                flops, tag = 2.0 * m * c * 3 * f, (m, c, f)
             elif op.kind == L.OP_CONV_SMALL:
                 b, h, w, cin, cout = (op.i[j] for j in range(5))
                 flops, tag = 2.0 * b * h * w * 9 * cin * cout, (b * h * w, cout, 9 * cin)
@@ -473,7 +489,7 @@ class Program:
                 tag = (op.i[2], op.i[3], op.i[0] + op.i[1])         # B, HW, C
             elif op.kind == L.OP_LAYER_NORM:
                 tag = (op.i[0], op.i[1])                            # rows, C
-            self.meta.append(({L.OP_ATTENTION: "attention", L.OP_GROUP_NORM: "group_norm",
+            self.meta.append(({L.OP_ATTENTION: "attention", L.OP_GROUP_NORM: "group_norm", L.OP_FF_FUSED: "ff_fused",
                                L.OP_GROUP_NORM_COEF: "group_norm",
                                L.OP_LAYER_NORM: "layer_norm", L.OP_CONV_SMALL: "conv_small"}.get(op.kind, "other"),
                               flops, tag))

@@ -7,7 +7,7 @@ NAME=$1; EXTRA=$2
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr $EXTRA"
 mkdir -p build/$NAME ../../gpurun_variants
-for f in api gemm elementwise attention conv_small conv_halo xattn; do
+for f in api gemm elementwise attention conv_small conv_halo xattn ff_fused; do
   $NVCC $FLAGS -c $f.cu -o build/$NAME/$f.o 2> build/$NAME/$f.log &
 done
 wait

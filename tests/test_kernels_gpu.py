@@ -643,3 +643,25 @@ def test_gemm_colstats_upsample_phases_share_a_buffer():
         K.run_gemm(d)
     got, ref = buf.sum(1), _cs_reference(out)
     assert rel(got[..., 0], ref[..., 0]) < 1e-5 and rel(got[..., 1], ref[..., 1]) < 1e-5
+
+
+@pytest.mark.parametrize("M", [256, 4096 + 130, 37])
+def test_ff_geglu_fused(M):
+    """x + ff(norm3(x)) (LD.py:4155-4162, FeedForward / GEGLU LD.py:4508-4536) in one launch at C = 320: the GEGLU
+    intermediate goes epilogue -> shared memory -> second GEMM; ragged M, several tiles per CTA pair."""
+    C, Fd = 320, 1280
+    x = h16(rnd(M, C, seed=200) * 1.2 + 0.3)
+    gamma, beta = 1.0 + 0.2 * rnd(C, seed=201), 0.3 * rnd(C, seed=202)
+    w1, b1 = h16(rnd(2 * Fd, C, seed=203, scale=C ** -0.5)), rnd(2 * Fd, seed=204, scale=0.3)
+    w2, b2 = h16(rnd(C, Fd, seed=205, scale=Fd ** -0.5)), rnd(C, seed=206, scale=0.3)
+    wf, gsum, bf = K.fold_layer_norm(w1, b1, gamma, beta)
+    w1p, b1p = K.pack_geglu(wf, bf, 64)
+    _, g1p = K.pack_geglu(wf, gsum, 64)
+    xs = x.float()
+    stats = torch.stack([xs.sum(1), (xs * xs).sum(1)], 1).view(M, 1, 2).contiguous()
+    out = torch.full((M, C), 3.0, dtype=torch.float16, device=DEV)
+    K.run_op(K.ff_fused_op(x, w1p, b1p, g1p, K.pack_linear(w2), b2, stats, out))
+    y = F.layer_norm(xs, (C,), gamma, beta, 1e-5) @ w1.float().t() + b1
+    g = h16(y[:, :Fd] * F.gelu(y[:, Fd:])).float()            # the reference's fp16 intermediate
+    ref = xs + g @ w2.float().t() + b2
+    assert rel(out, ref) < 1.5e-3, rel(out, ref)
