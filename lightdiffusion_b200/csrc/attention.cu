@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = ch * 8 + 2 * i;
-              const float x0 = fmaf(__uint_as_float(r[e]), c, -mc), x1 = fmaf(__uint_as_float(r[e + 1]), c, -mc);
+              float x0, x1;                     // one FFMA2 for the pair (bit-identical to two fmaf)
+              f2_unpack(f2_fma(f2_pack(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), f2_pack(c, c), f2_pack(-mc, -mc)), x0, x1);
               float p0, p1;
               if (LDX_ATT_DBG == 1) {
                 p0 = x0;
@@ -477,10 +478,8 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
                 p1 = (LDX_ATT_POLY_MOD > 0 && (e + 1) % (LDX_ATT_POLY_MOD > 0 ? LDX_ATT_POLY_MOD : 1) == LDX_ATT_POLY_MOD - 1)
                          ? ex2_poly(x1) : ex2_approx(x1);
               }
-              if constexpr (!C::ONES) {
-                l0 += p0;
-                l1 += p1;
-              }
+              if constexpr (!C::ONES)
+                f2_unpack(f2_fma(f2_pack(p0, p1), f2_pack(1.0f, 1.0f), f2_pack(l0, l1)), l0, l1);   // l0 += p0, l1 += p1
               pk[i] = pack_h2(p0, p1);
             }
             *reinterpret_cast<uint4*>(prow + (((ch0 + ch) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -607,7 +606,8 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int e = ch * 8 + 2 * i;
-            const float x0 = fmaf(s[e], c, -mc), x1 = fmaf(s[e + 1], c, -mc);
+            float x0, x1;
+            f2_unpack(f2_fma(f2_pack(s[e], s[e + 1]), f2_pack(c, c), f2_pack(-mc, -mc)), x0, x1);
             float p0, p1;
             if (LDX_ATT_DBG == 1) {
               p0 = x0;

@@ -373,6 +373,58 @@ LDX_DEVICE float gelu_erf_fast(float x) {
   return x * r;
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two IEEE fp32 results per issue slot, bit-identical to the scalar ops).
+// Epilogues whose limiter is the warp scheduler's issue rate, not the FMA lanes, halve their arithmetic instruction count.
+typedef unsigned long long f32x2_t;
+LDX_DEVICE f32x2_t f2_pack(float a, float b) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+LDX_DEVICE void f2_unpack(f32x2_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+#ifndef LDX_PACKED_F32
+#define LDX_PACKED_F32 1      // 0: the same helpers through scalar fmaf / mul / add (A/B builds; results are bit-identical)
+#endif
+#if LDX_PACKED_F32
+LDX_DEVICE f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+LDX_DEVICE f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+#else
+LDX_DEVICE f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+  float a0, a1, b0, b1, c0, c1;
+  f2_unpack(a, a0, a1); f2_unpack(b, b0, b1); f2_unpack(c, c0, c1);
+  return f2_pack(__fmaf_rn(a0, b0, c0), __fmaf_rn(a1, b1, c1));
+}
+LDX_DEVICE f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+  float a0, a1, b0, b1;
+  f2_unpack(a, a0, a1); f2_unpack(b, b0, b1);
+  return f2_pack(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
+}
+#endif
+// gelu_erf_fast on a pair: the same operations in the same order (bit-identical results), 8 packed + 4 MUFU instructions
+LDX_DEVICE f32x2_t gelu_erf_fast2(f32x2_t x) {
+  const f32x2_t x2 = f2_mul(x, x);
+  f32x2_t p = f2_fma(f2_pack(-3.2919935e-06f, -3.2919935e-06f), x2, f2_pack(8.9313635e-05f, 8.9313635e-05f));
+  p = f2_fma(p, x2, f2_pack(3.5481673e-04f, 3.5481673e-04f));
+  p = f2_fma(p, x2, f2_pack(-1.0521783e-01f, -1.0521783e-01f));
+  p = f2_fma(p, x2, f2_pack(-2.3020485e+00f, -2.3020485e+00f));
+  float t0, t1;
+  f2_unpack(f2_mul(x, p), t0, t1);
+  float d0, d1;
+  f2_unpack(f2_fma(f2_pack(ex2_approx(t0), ex2_approx(t1)), f2_pack(1.0f, 1.0f), f2_pack(1.0f, 1.0f)), d0, d1);   // e * 1 + 1 == 1 + e
+  float r0, r1;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
+  return f2_mul(x, f2_pack(r0, r1));
+}
+
 LDX_DEVICE uint32_t pack_h2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -32,7 +32,21 @@ int identity_matrix_n();
 
 static constexpr int FF_C = 320;                      // model width this kernel is built for
 static constexpr int FF_KCH = FF_C / 64;              // K chunks of the first GEMM = 64-column blocks of the output
-static constexpr int FF_THREADS = 384;
+// Epilogue warps per TMEM lane quarter (build knob): each takes 64 / FF_EG of a chunk's value columns and the matching gate
+// columns.  4 (sixteen epilogue warps, four per scheduler, <= 96 registers) hides the MUFU / FMA latency of the GEGLU
+// chains that 2 (eight warps, 168 registers) left exposed.
+#ifndef LDX_FF_EG
+#define LDX_FF_EG 2
+#endif
+#ifndef LDX_FF_PACKED
+#define LDX_FF_PACKED 1
+#endif
+LDX_DEVICE void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+LDX_DEVICE void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16(taddr, r); }
+static constexpr int FF_EG = LDX_FF_EG;
+static constexpr int FF_CW = 64 / FF_EG;                // value (= gate) columns of a chunk per epilogue warp
+static_assert(FF_EG == 2 || FF_EG == 4, "epilogue groups");
+static constexpr int FF_THREADS = 128 + 128 * FF_EG;
 static constexpr int FF_NW1 = 4, FF_NW2 = 2;
 static constexpr int FF_A1_BYTES = FF_KCH * BM * 128;         // 80 KB
 static constexpr int FF_W1_STAGE = 64 * 128;                  // this CTA's 64 of the chunk's 128 rows x 64 K
@@ -96,8 +110,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ldx_ff_fused_kernel(const __gri
     for (int i = 0; i < FF_NW1; ++i) { mbar_init(&bars->w1_full[i], 1); mbar_init(&bars->w1_empty[i], 1); }
     for (int i = 0; i < FF_NW2; ++i) { mbar_init(&bars->w2_full[i], 1); mbar_init(&bars->w2_empty[i], 1); }
     mbar_init(&bars->s_full, 1);
-    mbar_init(&bars->s_free, 16);
-    for (int i = 0; i < 2; ++i) { mbar_init(&bars->a2_full[i], 16); mbar_init(&bars->a2_empty[i], 1); }
+    mbar_init(&bars->s_free, 8 * FF_EG);
+    for (int i = 0; i < 2; ++i) { mbar_init(&bars->a2_full[i], 8 * FF_EG); mbar_init(&bars->a2_empty[i], 1); }
     mbar_init(&bars->o_full, 1);
     mbar_init(&bars->o_free, 16);
     fence_barrier_init();
@@ -275,22 +289,50 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ldx_ff_fused_kernel(const __gri
       }
       for (int j = 0; j < nch; ++j) {
         const int g = gch + j, buf = g & 1;
-        uint32_t ra[32], rg[32];
+        uint32_t ra[FF_CW], rg[FF_CW];
         mbar_wait(&bars->s_full, (uint32_t)(g & 1));
         tc_fence_after();
-        tmem_ld32(tS + 32 * hsel, ra);
-        tmem_ld32(tS + 64 + 32 * hsel, rg);
+        tmem_ld_cols(tS + FF_CW * hsel, ra);
+        tmem_ld_cols(tS + 64 + FF_CW * hsel, rg);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(r_sfree);
-        const float4* bv = reinterpret_cast<const float4*>(p.bias1 + j * 128 + 32 * hsel);
-        const float4* gv = reinterpret_cast<const float4*>(p.gsum1 + j * 128 + 32 * hsel);
+        const float4* bv = reinterpret_cast<const float4*>(p.bias1 + j * 128 + FF_CW * hsel);
+        const float4* gv = reinterpret_cast<const float4*>(p.gsum1 + j * 128 + FF_CW * hsel);
         if (g >= 2) mbar_wait(&bars->a2_empty[buf], (uint32_t)(((g >> 1) - 1) & 1));   // O += A2(g - 2) has read the buffer
         uint8_t* arow = sA2 + buf * FF_A2_BYTES + row * 128;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < FF_CW / 8; ++ch) {
           float v[8];
+#ifdef LDX_FF_DBG_NOGELU
+          // variant-build timing experiment (wrong results): the epilogue only converts, which leaves what the tensor
+          // side alone sustains (136 vs 174 us at M = 65536)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(ra[ch * 8 + i]) * ln_a + __uint_as_float(rg[ch * 8 + i]) + ln_b;
+          (void)bv; (void)gv;
+#else
+#if LDX_FF_PACKED
+          // packed fp32 pairs: the same operations as the scalar form below (bit-identical), ~9 instead of ~15.5 issue
+          // slots per hidden unit
+          const f32x2_t lna2 = f2_pack(ln_a, ln_a), lnb2 = f2_pack(ln_b, ln_b);
+#pragma unroll
+          for (int h4 = 0; h4 < 2; ++h4) {
+            const int j4 = ch * 2 + h4;
+            const float4 ba = __ldg(bv + j4), bg = __ldg(bv + 16 + j4);
+            const float4 ga = __ldg(gv + j4), gg = __ldg(gv + 16 + j4);
+            const f32x2_t ba0 = f2_fma(f2_pack(ga.x, ga.y), lnb2, f2_pack(ba.x, ba.y));
+            const f32x2_t ba1 = f2_fma(f2_pack(ga.z, ga.w), lnb2, f2_pack(ba.z, ba.w));
+            const f32x2_t bg0 = f2_fma(f2_pack(gg.x, gg.y), lnb2, f2_pack(bg.x, bg.y));
+            const f32x2_t bg1 = f2_fma(f2_pack(gg.z, gg.w), lnb2, f2_pack(bg.z, bg.w));
+            const f32x2_t a0 = f2_fma(f2_pack(__uint_as_float(ra[j4 * 4 + 0]), __uint_as_float(ra[j4 * 4 + 1])), lna2, ba0);
+            const f32x2_t a1 = f2_fma(f2_pack(__uint_as_float(ra[j4 * 4 + 2]), __uint_as_float(ra[j4 * 4 + 3])), lna2, ba1);
+            const f32x2_t g0 = f2_fma(f2_pack(__uint_as_float(rg[j4 * 4 + 0]), __uint_as_float(rg[j4 * 4 + 1])), lna2, bg0);
+            const f32x2_t g1 = f2_fma(f2_pack(__uint_as_float(rg[j4 * 4 + 2]), __uint_as_float(rg[j4 * 4 + 3])), lna2, bg1);
+            f2_unpack(f2_mul(a0, gelu_erf_fast2(g0)), v[h4 * 4 + 0], v[h4 * 4 + 1]);
+            f2_unpack(f2_mul(a1, gelu_erf_fast2(g1)), v[h4 * 4 + 2], v[h4 * 4 + 3]);
+          }
+#else
 #pragma unroll
           for (int h4 = 0; h4 < 2; ++h4) {
             const int j4 = ch * 2 + h4;
@@ -303,9 +345,11 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ldx_ff_fused_kernel(const __gri
             v[h4 * 4 + 2] = fmaf(__uint_as_float(ra[j4 * 4 + 2]), ln_a, ba.z) * gelu_erf_fast(fmaf(__uint_as_float(rg[j4 * 4 + 2]), ln_a, bg.z));
             v[h4 * 4 + 3] = fmaf(__uint_as_float(ra[j4 * 4 + 3]), ln_a, ba.w) * gelu_erf_fast(fmaf(__uint_as_float(rg[j4 * 4 + 3]), ln_a, bg.w));
           }
+#endif
+#endif
           uint4 o;
           o.x = pack_h2(v[0], v[1]); o.y = pack_h2(v[2], v[3]); o.z = pack_h2(v[4], v[5]); o.w = pack_h2(v[6], v[7]);
-          *reinterpret_cast<uint4*>(arow + (((hsel * 4 + ch) ^ (row & 7)) << 4)) = o;
+          *reinterpret_cast<uint4*>(arow + (((hsel * (FF_CW / 8) + ch) ^ (row & 7)) << 4)) = o;
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -315,7 +359,8 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ldx_ff_fused_kernel(const __gri
       // ---- output rows: O (already holds x + sum_j A2_j W2_j^T) + b2 -> fp16 -> TMA store
       mbar_wait(&bars->o_full, (uint32_t)(it & 1));
       tc_fence_after();
-      const int npass = FF_KCH;                      // 64-column passes; this warp takes hsel, hsel + 2, ...
+      const int npass = FF_KCH;                      // 64-column passes; warps hsel = 0 / 1 take hsel, hsel + 2, ...
+      if (hsel < 2)
       for (int ps = hsel; ps < npass; ps += 2) {
         uint32_t r0[32], r1[32];
         tmem_ld32(tO + ps * 64, r0);

@@ -463,18 +463,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               const float ln_a = rownorm ? ln_rstd : 1.0f, ln_b = rownorm ? -ln_mean * ln_rstd : 0.0f;
               const float4* gv = reinterpret_cast<const float4*>((rownorm ? p.ln_gsum : p.bias) + nt * p.bn + c);
               const float4* ggp = gv + (p.bn >> 3);
+              // packed fp32 pairs (FFMA2 / FMUL2): the same operations as the scalar form, about half the issue slots of
+              // an epilogue whose limiter is the warp schedulers
+              const f32x2_t lna2 = f2_pack(ln_a, ln_a), lnb2 = f2_pack(ln_b, ln_b);
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
-                float4 ba = __ldg(bv + j4), bg = __ldg(bgp + j4);
+                const float4 ba = __ldg(bv + j4), bg = __ldg(bgp + j4);
+                f32x2_t ba0 = f2_pack(ba.x, ba.y), ba1 = f2_pack(ba.z, ba.w), bg0 = f2_pack(bg.x, bg.y), bg1 = f2_pack(bg.z, bg.w);
                 if (rownorm) {
                   const float4 ga = __ldg(gv + j4), gg = __ldg(ggp + j4);
-                  ba.x = fmaf(ga.x, ln_b, ba.x); ba.y = fmaf(ga.y, ln_b, ba.y); ba.z = fmaf(ga.z, ln_b, ba.z); ba.w = fmaf(ga.w, ln_b, ba.w);
-                  bg.x = fmaf(gg.x, ln_b, bg.x); bg.y = fmaf(gg.y, ln_b, bg.y); bg.z = fmaf(gg.z, ln_b, bg.z); bg.w = fmaf(gg.w, ln_b, bg.w);
+                  ba0 = f2_fma(f2_pack(ga.x, ga.y), lnb2, ba0);
+                  ba1 = f2_fma(f2_pack(ga.z, ga.w), lnb2, ba1);
+                  bg0 = f2_fma(f2_pack(gg.x, gg.y), lnb2, bg0);
+                  bg1 = f2_fma(f2_pack(gg.z, gg.w), lnb2, bg1);
                 }
-                v[j4 * 4 + 0] = fmaf(__uint_as_float(r[j4 * 4 + 0]), ln_a, ba.x) * gelu_erf_fast(fmaf(__uint_as_float(g[j4 * 4 + 0]), ln_a, bg.x));
-                v[j4 * 4 + 1] = fmaf(__uint_as_float(r[j4 * 4 + 1]), ln_a, ba.y) * gelu_erf_fast(fmaf(__uint_as_float(g[j4 * 4 + 1]), ln_a, bg.y));
-                v[j4 * 4 + 2] = fmaf(__uint_as_float(r[j4 * 4 + 2]), ln_a, ba.z) * gelu_erf_fast(fmaf(__uint_as_float(g[j4 * 4 + 2]), ln_a, bg.z));
-                v[j4 * 4 + 3] = fmaf(__uint_as_float(r[j4 * 4 + 3]), ln_a, ba.w) * gelu_erf_fast(fmaf(__uint_as_float(g[j4 * 4 + 3]), ln_a, bg.w));
+                const f32x2_t a0 = f2_fma(f2_pack(__uint_as_float(r[j4 * 4 + 0]), __uint_as_float(r[j4 * 4 + 1])), lna2, ba0);
+                const f32x2_t a1 = f2_fma(f2_pack(__uint_as_float(r[j4 * 4 + 2]), __uint_as_float(r[j4 * 4 + 3])), lna2, ba1);
+                const f32x2_t g0 = f2_fma(f2_pack(__uint_as_float(g[j4 * 4 + 0]), __uint_as_float(g[j4 * 4 + 1])), lna2, bg0);
+                const f32x2_t g1 = f2_fma(f2_pack(__uint_as_float(g[j4 * 4 + 2]), __uint_as_float(g[j4 * 4 + 3])), lna2, bg1);
+                f2_unpack(f2_mul(a0, gelu_erf_fast2(g0)), v[j4 * 4 + 0], v[j4 * 4 + 1]);
+                f2_unpack(f2_mul(a1, gelu_erf_fast2(g1)), v[j4 * 4 + 2], v[j4 * 4 + 3]);
               }
             } else {
               // bias / rowadd values are fetched while the TMEM load is in flight
@@ -488,21 +496,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               PH(3)
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-              if (rownorm) {                   // N % 32 == 0 is checked on the host
+              if (rownorm) {                   // N % 32 == 0 is checked on the host (so bias_vec holds)
+                // rstd * (acc - mean * gsum[n]) + bias[n] = acc * ln_a + (gsum[n] * ln_b + bias[n]): two FFMA2 per column pair
                 const float4* gv = reinterpret_cast<const float4*>(p.ln_gsum + n_glob);
+                const float ln_b = -ln_mean * ln_rstd;
+                const f32x2_t lna2 = f2_pack(ln_rstd, ln_rstd), lnb2 = f2_pack(ln_b, ln_b);
+                if (!bias_vec) {                // cannot happen with N % 32 == 0; keeps the registers defined
+#pragma unroll
+                  for (int j4 = 0; j4 < 8; ++j4) bb4[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
                   const float4 ga = __ldg(gv + j4);
-                  v[j4 * 4 + 0] = (v[j4 * 4 + 0] - ln_mean * ga.x) * ln_rstd;
-                  v[j4 * 4 + 1] = (v[j4 * 4 + 1] - ln_mean * ga.y) * ln_rstd;
-                  v[j4 * 4 + 2] = (v[j4 * 4 + 2] - ln_mean * ga.z) * ln_rstd;
-                  v[j4 * 4 + 3] = (v[j4 * 4 + 3] - ln_mean * ga.w) * ln_rstd;
+                  const f32x2_t b0 = f2_fma(f2_pack(ga.x, ga.y), lnb2, f2_pack(bb4[j4].x, bb4[j4].y));
+                  const f32x2_t b1 = f2_fma(f2_pack(ga.z, ga.w), lnb2, f2_pack(bb4[j4].z, bb4[j4].w));
+                  f2_unpack(f2_fma(f2_pack(v[j4 * 4 + 0], v[j4 * 4 + 1]), lna2, b0), v[j4 * 4 + 0], v[j4 * 4 + 1]);
+                  f2_unpack(f2_fma(f2_pack(v[j4 * 4 + 2], v[j4 * 4 + 3]), lna2, b1), v[j4 * 4 + 2], v[j4 * 4 + 3]);
                 }
-              }
-              if (bias_vec) {
+              } else if (bias_vec) {
+                const f32x2_t one2 = f2_pack(1.0f, 1.0f);       // v * 1 + b == v + b, one FFMA2 per pair
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                  v[j4 * 4 + 0] += bb4[j4].x; v[j4 * 4 + 1] += bb4[j4].y; v[j4 * 4 + 2] += bb4[j4].z; v[j4 * 4 + 3] += bb4[j4].w;
+                  f2_unpack(f2_fma(f2_pack(v[j4 * 4 + 0], v[j4 * 4 + 1]), one2, f2_pack(bb4[j4].x, bb4[j4].y)), v[j4 * 4 + 0], v[j4 * 4 + 1]);
+                  f2_unpack(f2_fma(f2_pack(v[j4 * 4 + 2], v[j4 * 4 + 3]), one2, f2_pack(bb4[j4].z, bb4[j4].w)), v[j4 * 4 + 2], v[j4 * 4 + 3]);
                 }
               } else {
 #pragma unroll

@@ -287,10 +287,10 @@ __global__ void __launch_bounds__(XaCfg<D>::THREADS, 1) ldx_xattn_kernel(const _
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int e = ch * 8 + 2 * i;
-            float p0 = fmaf(__uint_as_float(r[e]), c, -mc), p1 = fmaf(__uint_as_float(r[e + 1]), c, -mc);
+            float p0, p1;                       // one FFMA2 for the pair (bit-identical to two fmaf)
+            f2_unpack(f2_fma(f2_pack(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), f2_pack(c, c), f2_pack(-mc, -mc)), p0, p1);
             if (!(LDX_XA_DBG & 1)) { p0 = ex2_approx(p0); p1 = ex2_approx(p1); }
-            l0 += p0;
-            l1 += p1;
+            f2_unpack(f2_fma(f2_pack(p0, p1), f2_pack(1.0f, 1.0f), f2_pack(l0, l1)), l0, l1);   // l0 += p0, l1 += p1
             pk[i] = pack_h2(p0, p1);
           }
           *reinterpret_cast<uint4*>(prow + (((ch0 + ch) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);

@@ -665,3 +665,37 @@ def test_ff_geglu_fused(M):
     g = h16(y[:, :Fd] * F.gelu(y[:, Fd:])).float()            # the reference's fp16 intermediate
     ref = xs + g @ w2.float().t() + b2
     assert rel(out, ref) < 1.5e-3, rel(out, ref)
+
+
+def test_ff_geglu_fused_is_repeatable_and_row_local():
+    """Four producer / issuer warps, eight epilogue warps and a CTA pair hand S, A2, O and three rings around through
+    mbarriers: 30 launches at a multi-tile-per-pair size (ragged last tile) must be bit-identical, and a row's result must not
+    depend on which tile / CTA pair computed it (the same rows placed at another offset of a larger batch)."""
+    C, Fd, M = 320, 1280, 256 * 74 * 2 + 256 * 9 + 77
+    x = h16(rnd(M, C, seed=210) * 1.1 - 0.2)
+    gamma, beta = 1.0 + 0.2 * rnd(C, seed=211), 0.3 * rnd(C, seed=212)
+    w1, b1 = h16(rnd(2 * Fd, C, seed=213, scale=C ** -0.5)), rnd(2 * Fd, seed=214, scale=0.3)
+    w2, b2 = h16(rnd(C, Fd, seed=215, scale=Fd ** -0.5)), rnd(C, seed=216, scale=0.3)
+    wf, gsum, bf = K.fold_layer_norm(w1, b1, gamma, beta)
+    w1p, b1p = K.pack_geglu(wf, bf, 64)
+    _, g1p = K.pack_geglu(wf, gsum, 64)
+    w2p = K.pack_linear(w2)
+
+    def run(xin):
+        xs = xin.float()
+        stats = torch.stack([xs.sum(1), (xs * xs).sum(1)], 1).view(xin.shape[0], 1, 2).contiguous()
+        out = torch.zeros_like(xin)
+        prog = K.Program()
+        prog.add(K.ff_fused_op(xin, w1p, b1p, g1p, w2p, b2, stats, out))
+        prog.run()
+        return prog, out
+
+    prog, out = run(x)
+    first = out.clone()
+    for _ in range(30):
+        out.zero_()
+        prog.run()
+        assert torch.equal(out, first)
+    # rows 1024 .. 1024 + 5000 of x as the head of their own (smaller) launch: other tiles, other CTA pairs, same bits
+    _, sub = run(x[1024:1024 + 5000].contiguous())
+    assert torch.equal(sub, first[1024:1024 + 5000])
