@@ -435,7 +435,7 @@ def run_ours(args):
     achieved = GF_UNET_GEMM_SAMPLE * 1e9 * 2 * b / (gemm_ms * 1e-3) / 1e12
     executed = gemm_flops / (gemm_ms * 1e-3) / 1e12
     traffic, traffic_src = None, None
-    for name in ("r02b_gemm_traffic.json", "r02_gemm_traffic.json", "r01_gemm_traffic.json"):   # committed ncu measurement (per launch)
+    for name in ("r02c_gemm_traffic.json", "r02b_gemm_traffic.json", "r02_gemm_traffic.json", "r01_gemm_traffic.json"):   # committed ncu measurement (per launch)
         tpath = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tpath):
             with open(tpath) as f:

@@ -319,8 +319,14 @@ __global__ void __launch_bounds__(FF_THREADS, 1) ldx_ff_fused_kernel(const __gri
 #pragma unroll
           for (int h4 = 0; h4 < 2; ++h4) {
             const int j4 = ch * 2 + h4;
+#ifdef LDX_FF_DBG_NOBIAS
+            // variant-build timing experiment (wrong results): no bias / gsum loads
+            const float4 ba = make_float4(0.1f, 0.2f, 0.3f, 0.4f), bg = ba, ga = ba, gg = ba;
+            (void)bv; (void)gv;
+#else
             const float4 ba = __ldg(bv + j4), bg = __ldg(bv + 16 + j4);
             const float4 ga = __ldg(gv + j4), gg = __ldg(gv + 16 + j4);
+#endif
             const f32x2_t ba0 = f2_fma(f2_pack(ga.x, ga.y), lnb2, f2_pack(ba.x, ba.y));
             const f32x2_t ba1 = f2_fma(f2_pack(ga.z, ga.w), lnb2, f2_pack(ba.z, ba.w));
             const f32x2_t bg0 = f2_fma(f2_pack(gg.x, gg.y), lnb2, f2_pack(bg.x, bg.y));

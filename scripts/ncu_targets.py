@@ -49,6 +49,16 @@ elif case == "gn_colstats_vae":       # GroupNorm + SiLU of a 8 x 512 x 512 x 12
     gam, bet = rnd(128) * 0.1 + 1, rnd(128) * 0.1; y = torch.empty_like(x)
     st = torch.empty(8 * L.GN_STATS_FLOATS_PER_BATCH, dtype=torch.float32, device=dev)
     op = K.group_norm_op(x, None, gam, bet, y, st, 1e-6, True, colstats=(cs, None)); keep += [xin, wp, b, x, cs, gam, bet, y, st]
+elif case == "ff_fused":              # x + ff(norm3(x)) at the 64 x 64 level in one launch (C = 320, 16 samples)
+    M, C, Fd = 65536, 320, 1280
+    x = (rnd(M, C) * 1.2 + 0.3).half(); gam, bet = rnd(C) * 0.1 + 1, rnd(C) * 0.1
+    w1, b1 = rnd(2 * Fd, C, sc=C ** -0.5).half(), rnd(2 * Fd) * 0.3
+    w2, b2 = rnd(C, Fd, sc=Fd ** -0.5).half(), rnd(C) * 0.3
+    wf, gsum, bf = K.fold_layer_norm(w1, b1, gam, bet)
+    w1p, b1p = K.pack_geglu(wf, bf, 64); _, g1p = K.pack_geglu(wf, gsum, 64)
+    xs = x.float(); stats = torch.stack([xs.sum(1), (xs * xs).sum(1)], 1).view(M, 1, 2).contiguous()
+    out = torch.empty(M, C, dtype=torch.float16, device=dev); w2p = K.pack_linear(w2)
+    op = K.ff_fused_op(x, w1p, b1p, g1p, w2p, b2, stats, out); keep += [x, w1p, b1p, g1p, w2p, b2, stats, out]
 else:
     raise SystemExit("unknown case " + case)
 prog = K.Program(); prog.add(op)

@@ -44,15 +44,16 @@ print(f"one UNet step (B=16, 64x64 latent): {len(step)} launches, {tot/1e6:.3f} 
 print(f"{'kernel':48s} {'launches':>8s} {'ms':>8s} {'share':>6s} {'DRAM rd MB':>10s} {'DRAM wr MB':>10s}")
 for name, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print(f"{name[:48]:48s} {a[0]:8d} {a[1]/1e6:8.3f} {100*a[1]/tot:5.1f}% {a[2]/1e6:10.1f} {a[3]/1e6:10.1f}")
-g = [a for n, a in agg.items() if "ldx_gemm_kernel" in n or "ldx_conv_halo_kernel" in n]
+FAMILY = ("ldx_gemm_kernel", "ldx_conv_halo_kernel", "ldx_ff_fused_kernel")
+g = [a for n, a in agg.items() if any(f in n for f in FAMILY)]
 n = sum(a[0] for a in g)
 per = {}
-for nm in ("ldx_gemm_kernel", "ldx_conv_halo_kernel"):
+for nm in FAMILY:
     gg = [a for n2, a in agg.items() if nm in n2]
     if gg:
         k = sum(a[0] for a in gg)
         per[nm] = {"launches": k, "ms": sum(a[1] for a in gg) / 1e6, "dram_bytes_per_launch": (sum(a[2] for a in gg) + sum(a[3] for a in gg)) / k}
-out = {"kernel": "ldx_gemm_kernel + ldx_conv_halo_kernel", "per_kernel": per, "launches_per_unet_step": n,
+out = {"kernel": " + ".join(per), "per_kernel": per, "launches_per_unet_step": n,
        "dram_bytes_read_per_launch": sum(a[2] for a in g) / n, "dram_bytes_write_per_launch": sum(a[3] for a in g) / n,
        "dram_bytes_per_launch": (sum(a[2] for a in g) + sum(a[3] for a in g)) / n,
        "share_of_step_kernel_time": sum(a[1] for a in g) / tot,
