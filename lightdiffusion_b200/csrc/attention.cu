@@ -62,6 +62,17 @@ static constexpr int ATT_MAX_ST = 6;        // K / V ring depth bound
 #define LDX_ATT_TOKENS 0
 #endif
 static_assert(LDX_ATT_TOKENS >= 0 && LDX_ATT_TOKENS <= 2, "with three tokens a group can lap its successor's barrier phase");
+// Bit i set: pair i of each 32-key half tile (the NG = 4 kernels, d <= 64) takes its two exponentials from the FMA pipe as packed
+// fp32 (ex2_poly2, 5 issue slots per exponential) instead of MUFU.EX2 (the unit this kernel queues on: 75 % busy).  Which
+// pairs matters as much as how many -- the mask changes ptxas's schedule of the whole tile: measured at 16 x 8 x 4096^2,
+// d = 40 (scripts/gpu_poly_sweep.sh, one box, us): 0 -> 643; 0x4144 (4 of 16 pairs) -> 609; 0x4244 610; 0x4124 613; 0x4924
+// (5 pairs) 620; 0x0144 (3 pairs) 632; 0x4344 643; 0x2492 662; 0x4140 697; 0xAAAA (8 pairs) 746.
+// OFF by default: the 5 % it gains on the kernel timed alone disappears in the pipeline, which runs at the 1 kW power cap --
+// the extra FMA-pipe instructions cost energy and the SM clock drops from 1750 to 1720 MHz (scripts/gpu_ab9.sh, same box,
+// bench conditions: 24.33 / 24.34 images/s off, 24.31 / 24.29 on; UNet graph replay 14.73 vs 14.75 ms).
+#ifndef LDX_ATT_POLY_MASK
+#define LDX_ATT_POLY_MASK 0
+#endif
 #ifndef LDX_ATT_POLY_MOD
 #define LDX_ATT_POLY_MOD 0      // every POLY_MOD-th exponential runs on the FMA pipe (0 = all on MUFU); measured: no gain
 #endif
@@ -160,6 +171,26 @@ LDX_DEVICE float ex2_poly(float x) {
   p = fmaf(p, fr, 0.695833683013916f);
   p = fmaf(p, fr, 0.9999251961708069f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// The same on a pair of values with packed fp32 (FFMA2): 2 FMNMX + 6 FFMA2 + 2 LEA per pair = 5 issue slots per exponential
+// (10 for the scalar form) against one issue slot + 8 MUFU-pipe clocks per warp for ex2.approx.
+LDX_DEVICE void ex2_poly2(float x0, float x1, float& r0, float& r1) {
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  const f32x2_t x = f2_pack(x0, x1), one = f2_pack(1.0f, 1.0f);
+  f32x2_t t;                                              // x + 1.5 * 2^23 rounded down: floor(x) in the low mantissa bits
+  asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(t) : "l"(x), "l"(one), "l"(f2_pack(12582912.0f, 12582912.0f)));
+  const f32x2_t fl = f2_fma(t, one, f2_pack(-12582912.0f, -12582912.0f));       // floor(x), exact
+  const f32x2_t fr = f2_fma(fl, f2_pack(-1.0f, -1.0f), x);                      // [0, 1)
+  f32x2_t p = f2_fma(f2_pack(0.07802422344684601f, 0.07802422344684601f), fr, f2_pack(0.22606723010540009f, 0.22606723010540009f));
+  p = f2_fma(p, fr, f2_pack(0.695833683013916f, 0.695833683013916f));
+  p = f2_fma(p, fr, f2_pack(0.9999251961708069f, 0.9999251961708069f));
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  r0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  r1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
 // CAUSAL (the CLIP text tower's mask, LD.py:4443-4449: -inf above the diagonal) is a compile-time variant so
@@ -472,6 +503,8 @@ __global__ void __launch_bounds__(AttnCfg<D, NG_>::THREADS, AttnCfg<D, NG_>::MIN
               if (LDX_ATT_DBG == 1) {
                 p0 = x0;
                 p1 = x1;
+              } else if ((LDX_ATT_POLY_MASK >> (ch * 4 + i)) & 1) {
+                ex2_poly2(x0, x1, p0, p1);
               } else {
                 p0 = (LDX_ATT_POLY_MOD > 0 && e % (LDX_ATT_POLY_MOD > 0 ? LDX_ATT_POLY_MOD : 1) == LDX_ATT_POLY_MOD - 1)
                          ? ex2_poly(x0) : ex2_approx(x0);

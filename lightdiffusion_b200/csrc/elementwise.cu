@@ -44,10 +44,19 @@ __device__ __forceinline__ void gn_write_coef(const float* partial, int b, int n
   const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
   double s = 0.0, ss = 0.0;
   if (g < 32) {
-    for (int k = sub; k < nslab; k += 8) {
-      const float2 pr = __ldcg(reinterpret_cast<const float2*>(partial + (((size_t)b * nslab + k) * 32 + g) * 2));
-      s += (double)pr.x;
-      ss += (double)pr.y;
+    // (up to 8 slabs per thread: the loads go out together, the sums keep their order)
+    for (int k0 = sub; k0 < nslab; k0 += 64) {
+      float2 pr[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + 8 * u;
+        pr[u] = k < nslab ? __ldcg(reinterpret_cast<const float2*>(partial + (((size_t)b * nslab + k) * 32 + g) * 2)) : make_float2(0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s += (double)pr[u].x;
+        ss += (double)pr[u].y;
+      }
     }
   }
 #pragma unroll
@@ -105,11 +114,15 @@ __global__ void gn_stats_kernel(const GnArgs a) {
   const int p_end = min(a.HW, p_begin + a.pix_per_slab);
   if (pl < a.P) {
     int pix = p_begin + pl;
-#if LDX_GN_STATS_U16
-    for (; pix + 15 * a.P < p_end; pix += 16 * a.P) {   // 16 independent 16-byte loads in flight
+    // 16 independent 16-byte loads in flight per round, the ragged last round predicated (zeros add nothing): a slab is
+    // usually 8 - 16 pixels per thread, so the whole slab is ONE memory round trip.  (The earlier form ran the remainder as
+    // 8-deep and then single loads: a thread with 11 pixels paid four dependent DRAM latencies.)  Same per-thread summation
+    // order as before: bit-identical statistics.
+    for (; pix < p_end; pix += 16 * a.P) {
       uint4 v[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = gn_load(a, b, pix + u * a.P, vec);
+      for (int u = 0; u < 16; ++u)
+        v[u] = pix + u * a.P < p_end ? gn_load(a, b, pix + u * a.P, vec) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
         const float2 f0 = unpack_h2(v[u].x), f1 = unpack_h2(v[u].y), f2 = unpack_h2(v[u].z), f3 = unpack_h2(v[u].w);
@@ -117,26 +130,6 @@ __global__ void gn_stats_kernel(const GnArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
       }
-    }
-#endif
-    for (; pix + 7 * a.P < p_end; pix += 8 * a.P) {     // 8 independent 16-byte loads in flight
-      uint4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = gn_load(a, b, pix + u * a.P, vec);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float2 f0 = unpack_h2(v[u].x), f1 = unpack_h2(v[u].y), f2 = unpack_h2(v[u].z), f3 = unpack_h2(v[u].w);
-        const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
-      }
-    }
-    for (; pix < p_end; pix += a.P) {
-      const uint4 v = gn_load(a, b, pix, vec);
-      const float2 f0 = unpack_h2(v.x), f1 = unpack_h2(v.y), f2 = unpack_h2(v.z), f3 = unpack_h2(v.w);
-      const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] += f[j] * f[j]; }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {

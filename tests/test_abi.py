@@ -81,6 +81,10 @@ def test_argument_validation_returns_error_codes(lib):
         l.ldx_cfg_dpmpp2m_step(addr, 8, addr, None, None, 1.0, 7.0, 0.5, 0.5, 0.0, 0, 0, 0.5, None, 1, 4, 8, 8, None),
         l.ldx_cfg_dpmpp2m_step(addr, 2, addr, addr, None, 1.0, 7.0, 0.5, 0.5, 0.0, 0, 0, 0.5, None, 1, 4, 8, 8, None),  # pitch < C
         l.ldx_vae_postprocess_u8(addr, 8, None, 16, None),
+        # fused feed-forward: built for C = 320 only; F a multiple of 64; no null operands
+        l.ldx_ff_geglu_fused(addr, 640, 256, addr, 640, addr, addr, addr, 2560, addr, addr, 1, 1e-5, 640, 2560, addr, 640, None),
+        l.ldx_ff_geglu_fused(addr, 320, 256, addr, 320, addr, addr, addr, 1280, addr, addr, 1, 1e-5, 320, 1250, addr, 320, None),
+        l.ldx_ff_geglu_fused(addr, 320, 256, addr, 320, addr, None, addr, 1280, addr, addr, 1, 1e-5, 320, 1280, addr, 320, None),
     ]
     assert all(rc != 0 for rc in bad), bad
     assert l.ldx_last_error_string()
