@@ -1,7 +1,7 @@
 """End-to-end device times of BASELINE.json configurations 4 and 5 (synthetic inputs, random-init SD1.5 weights):
   config 4: hires-fix = 20-step DPM++ 2M at 64x64 -> bislerp 2x -> 10-step/0.45 Euler-ancestral pass at 128x128 -> decode
   config 5: img2img at 1024x1024, batch 4 = VAE encode -> 10-step/0.45 Euler-ancestral pass at 128x128 -> VAE decode
-Prints one JSON line per configuration (CUDA-event time of the second of two runs)."""
+Prints one JSON line per configuration (CUDA-event time of the third of three runs)."""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -19,7 +19,7 @@ rn = lambda *s: torch.randn(*s, device=dev, generator=g)
 
 
 def timed(fn):
-    fn(); torch.cuda.synchronize()
+    fn(); fn(); torch.cuda.synchronize()          # two untimed runs: plans are built on the first, their CUDA graphs captured on the second
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); out = fn(); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1), out
