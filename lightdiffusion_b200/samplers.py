@@ -143,35 +143,35 @@ def sample_euler_ancestral(model, x, sigmas, extra_args=None, callback=None, dis
 
 
 class PIDStepSizeController:
-    """Step-size controller of dpm_solver_adaptive.  Host scalar arithmetic that has to reproduce the reference's
-    accept / reject sequence bit for bit, so it deliberately follows LD.py:944-973 statement by statement (same
-    coefficients b1..b3, same error history update, same atan limiter); nothing here touches the device."""
+    """Step-size controller of dpm_solver_adaptive (interface of LD.py:944-973: the constructor arguments, ``h`` and
+    ``propose_step(error) -> accepted``).  Pure host scalar arithmetic; it has to reproduce the reference's accept / reject
+    sequence and step sizes bit for bit, so the floating-point expression of the factor -- newest ** k0 * previous ** k1 *
+    oldest ** k2, evaluated left to right, then 1 + atan(f - 1) -- is the reference's; the bookkeeping is a two-entry history
+    of ACCEPTED inverse errors instead of the reference's three-slot list (tests/test_host_logic.py checks both against each
+    other on random error sequences)."""
+
+    __slots__ = ("h", "_k", "_threshold", "_eps", "_accepted")
 
     def __init__(self, h, pcoeff, icoeff, dcoeff, order=1, accept_safety=0.81, eps=1e-8):
         self.h = h
-        self.b1 = (pcoeff + icoeff + dcoeff) / order
-        self.b2 = -(pcoeff + 2 * dcoeff) / order
-        self.b3 = dcoeff / order
-        self.accept_safety = accept_safety
-        self.eps = eps
-        self.errs = []
+        # exponents of the newest, the last accepted and the one-before-last accepted inverse error
+        self._k = ((pcoeff + icoeff + dcoeff) / order, -(pcoeff + 2 * dcoeff) / order, dcoeff / order)
+        self._threshold = accept_safety
+        self._eps = eps
+        self._accepted = None              # (last, one before last); seeded with the first proposal's own inverse error
 
-    def limiter(self, x):
-        return 1 + math.atan(x - 1)
-
-    def propose_step(self, error):
-        inv_error = 1 / (float(error) + self.eps)
-        if not self.errs:
-            self.errs = [inv_error, inv_error, inv_error]
-        self.errs[0] = inv_error
-        factor = self.errs[0] ** self.b1 * self.errs[1] ** self.b2 * self.errs[2] ** self.b3
-        factor = self.limiter(factor)
-        accept = factor >= self.accept_safety
-        if accept:
-            self.errs[2] = self.errs[1]
-            self.errs[1] = self.errs[0]
+    def propose_step(self, error) -> bool:
+        newest = 1 / (float(error) + self._eps)
+        if self._accepted is None:
+            self._accepted = (newest, newest)
+        last, before = self._accepted
+        k0, k1, k2 = self._k
+        factor = 1 + math.atan(newest ** k0 * last ** k1 * before ** k2 - 1)
+        accepted = factor >= self._threshold
+        if accepted:
+            self._accepted = (newest, last)
         self.h *= factor
-        return accept
+        return accepted
 
 
 @torch.no_grad()

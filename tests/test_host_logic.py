@@ -102,6 +102,42 @@ def test_host_side_tables_and_controllers():
     assert abs(pid2.h - 0.05) < 1e-6                              # unit error leaves the step size unchanged
 
 
+def test_pid_controller_matches_three_slot_restatement_bit_for_bit():
+    """The product's two-entry-history controller against the reference's three-slot bookkeeping (LD.py:944-973, as restated
+    inline in oracle/ldm_oracle.py's dpm_adaptive): identical accept sequences and bit-identical step sizes on random error
+    sequences, including rejected first steps and long reject runs."""
+    import math
+    import random
+    from lightdiffusion_b200.samplers import PIDStepSizeController
+
+    def three_slot(h, p, i, d, order, safety, errors, eps=1e-8):
+        b1, b2, b3 = (p + i + d) / order, -(p + 2 * d) / order, d / order
+        errs, out = [], []
+        for e in errors:
+            inv = 1 / (float(e) + eps)
+            if not errs:
+                errs = [inv, inv, inv]
+            errs[0] = inv
+            f = 1 + math.atan(errs[0] ** b1 * errs[1] ** b2 * errs[2] ** b3 - 1)
+            ok = f >= safety
+            if ok:
+                errs[2], errs[1] = errs[1], errs[0]
+            h *= f
+            out.append((ok, h))
+        return out
+
+    rng = random.Random(7)
+    for trial in range(200):
+        p, i, d = rng.uniform(0, 0.3), rng.uniform(0.3, 1.2), rng.uniform(0, 0.2)
+        order, safety = rng.choice([1, 1.5, 2, 3]), rng.choice([0.81, 0.9, 0.5])
+        errors = [10 ** rng.uniform(-3, 2.5) for _ in range(rng.randint(1, 40))]
+        if trial % 5 == 0:
+            errors[0] = 500.0                   # rejected first proposal: the history stays seeded with it
+        pid = PIDStepSizeController(0.05, p, i, d, order, safety)
+        got = [(pid.propose_step(e), pid.h) for e in errors]
+        assert got == three_slot(0.05, p, i, d, order, safety, errors)
+
+
 def test_shard_range_partitions_everything():
     for n, w in [(64, 8), (64, 2), (10, 4), (3, 8), (1, 1)]:
         got = []
