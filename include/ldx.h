@@ -123,6 +123,13 @@ typedef struct {
   const float* gn_coef;
   int32_t gn_ctot;
   int32_t gn_silu;
+  /* Per-sample weights and bias (0 = shared): batch element b reads rows [b * w_batch_rows, b * w_batch_rows + N) of w and
+   * bias + b * bias_batch_stride.  This is how a GroupNorm in front of a 1x1 conv (SpatialTransformer.norm -> proj_in,
+   * LD.py:4242-4250) is folded into the conv: ldx_gn_fold_weights writes w'[b] = w * scale[b] and bias'[b], and the conv
+   * reads the un-normalised map.  Needs tiles that do not straddle batch elements (H * W a multiple of the 128 / 256-row
+   * tile), the fp16 TMA-store epilogue, no split-K, no halo sources. */
+  int32_t w_batch_rows;
+  int32_t bias_batch_stride;
 } ldx_gemm_desc_t;
 
 int ldx_gemm(const ldx_gemm_desc_t* d, ldx_stream_t stream);
@@ -167,6 +174,14 @@ int ldx_conv3x3_small_packed_elems(int cout, int cin);
 int ldx_ff_geglu_fused(const void* x, int64_t ldx_, int M, const void* w1_packed, int64_t ldw1, const float* bias1,
                        const float* gsum1, const void* w2, int64_t ldw2, const float* bias2, const float* rowstats,
                        int parts, float eps, int C, int F, void* out, int64_t ldo, ldx_stream_t stream);
+/* GroupNorm folded into the 1x1 conv / linear that consumes it (SpatialTransformer.norm + proj_in, LD.py:4242-4250):
+ *   w_out[b, n, c]  = fp16(w[n, c] * scale[b, c])                               (coef[b, c] = (scale, shift) from ldx_group_norm_coef)
+ *   bias_out[b, n]  = bias[n] + sum_c (w[n, c] * beta[c] - mean[b, g(c)] * w_out[b, n, c])
+ * so that  w_out[b] . x + bias_out[b]  ==  w . (x * scale + shift) + bias  with the rounding of w_out cancelled against the
+ * group mean (mean is recovered from beta, shift and scale).  w [N, ldw] fp16, w_out [B, N, ldw] fp16, C % 8 == 0,
+ * C <= 2048, groups = 32.  One CTA per (32 output rows, sample); fixed summation order. */
+int ldx_gn_fold_weights(const void* w, int64_t ldw, const float* bias, const float* beta, const float* coef, int B, int N,
+                        int C, void* w_out, float* bias_out, ldx_stream_t stream);
 /* GEGLU proj weight [2*F, K] (+ bias[2*F]) -> rows interleaved in blocks of `half_bn` so that one
  * output tile holds matching value/gate columns. */
 int ldx_pack_geglu(const void* w, const float* bias, void* w_packed, float* bias_packed, int two_f, int k,
@@ -312,6 +327,7 @@ enum {
   /* LDX_OP_ATTENTION takes i[5] = 1 for the causal variant (ldx_attention_causal) */
   LDX_OP_GROUP_NORM_COEF = 17, /* ldx_group_norm_coef.  p: x0, x1, gamma, beta, coef, stats, colstats0, colstats1, tickets ;
                                   i: c0, c1, B, HW, -, slots0, slots1 ; l: ld0, ld1 ; f: eps */
+  LDX_OP_GN_FOLD_WEIGHTS = 19, /* ldx_gn_fold_weights.  p: w, bias, beta, coef, w_out, bias_out ; l: ldw ; i: B, N, C */
   LDX_OP_FF_FUSED = 18,      /* ldx_ff_geglu_fused.  p: x, w1_packed, bias1, gsum1, w2, bias2, rowstats, out ;
                                 l: ldx, ldw1, ldw2, ldo ; i: M, C, F, parts ; f: eps */
   LDX_OP_CONV_SMALL = 16,    /* ldx_conv3x3_small.  p: x, w_packed, bias, out16, out_img ; i: B, H, W, Cin, Cout, post ;

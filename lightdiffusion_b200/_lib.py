@@ -25,6 +25,7 @@ OP_NCHW_TO_NHWC, OP_TIMESTEP_EMB, OP_UPSAMPLE2X, OP_EPS_TO_DENOISED = 5, 6, 7, 8
 OP_CFG_DENOISED, OP_VAE_POST, OP_SOFTMAX = 9, 10, 11
 OP_DUP, OP_VAE_PRE, OP_VAE_SAMPLE, OP_CLIP_EMBED, OP_CONV_SMALL, OP_GROUP_NORM_COEF = 12, 13, 14, 15, 16, 17
 OP_FF_FUSED = 18
+OP_GN_FOLD_WEIGHTS = 19
 
 GN_STATS_FLOATS_PER_BATCH = 64 * 32 * 2      # ldx_group_norm workspace: B * this many floats
 
@@ -56,7 +57,8 @@ class GemmDesc(C.Structure):
                 ("ln_eps", C.c_float), ("ln_gsum", C.c_void_p), ("ln_c", C.c_int32),
                 ("colstats_out", C.c_void_p), ("colstats_slots", C.c_int32), ("colstats_slot_base", C.c_int32),
                 ("rowstats_out_parts", C.c_int32),
-                ("halo_nsrc", C.c_int32), ("gn_coef", C.c_void_p), ("gn_ctot", C.c_int32), ("gn_silu", C.c_int32)]
+                ("halo_nsrc", C.c_int32), ("gn_coef", C.c_void_p), ("gn_ctot", C.c_int32), ("gn_silu", C.c_int32),
+                ("w_batch_rows", C.c_int32), ("bias_batch_stride", C.c_int32)]
 
 
 class GenericOp(C.Structure):
@@ -93,6 +95,8 @@ _SIGS = {
     "ldx_ff_geglu_fused": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_void_p,
                                      C.c_int64, C.c_void_p]),
+    "ldx_gn_fold_weights": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
     "ldx_layer_norm": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                  C.c_void_p, C.c_int64, C.c_void_p]),
     "ldx_attention": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

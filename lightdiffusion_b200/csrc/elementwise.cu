@@ -973,6 +973,88 @@ __global__ void euler_ancestral_step_kernel(float* __restrict__ x, const float* 
   }
 }
 
+// GroupNorm folded into the 1x1 conv that consumes it (ldx_gn_fold_weights, include/ldx.h): CTA (32 output rows, sample b),
+// one warp per output row at a time.  w_out[b][n][c] = fp16(w[n][c] * scale[b][c]); bias_out[b][n] = bias[n] + sum_c (w[n][c] * beta[c] -
+// mean[b][g(c)] * w_out[b][n][c]) with the lanes' partial sums combined in a fixed butterfly order (bit-reproducible).  The
+// group mean comes back out of the coefficients, (beta - shift) / scale, from the channel of the group with the largest
+// |scale| (a group whose scales are all zero contributes nothing whatever the mean).
+static constexpr int GN_FOLD_ROWS = 32;
+__global__ void __launch_bounds__(256) gn_fold_weights_kernel(const __half* __restrict__ w, int64_t ldw,
+                                                              const float* __restrict__ bias, const float* __restrict__ beta,
+                                                              const float* __restrict__ coef, int N, int C,
+                                                              __half* __restrict__ w_out, float* __restrict__ bias_out) {
+  extern __shared__ float fsm[];          // scale[C], beta[C], shift[C] -> mean of the channel's group [C]
+  float* s_scale = fsm;
+  float* s_beta = fsm + C;
+  float* s_mean = fsm + 2 * C;
+  __shared__ float g_mean[32];
+  pdl_prologue();
+  const int b = blockIdx.y, cpg = C / 32;
+  const float2* cf = reinterpret_cast<const float2*>(coef) + (size_t)b * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float2 q = __ldg(&cf[c]);
+    s_scale[c] = q.x;
+    s_mean[c] = q.y;                      // shift, until the group means are known
+    s_beta[c] = __ldg(beta + c);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x;
+    float best = 0.f, mean = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const float sc = s_scale[c];
+      if (fabsf(sc) > best) { best = fabsf(sc); mean = (s_beta[c] - s_mean[c]) / sc; }
+    }
+    g_mean[g] = mean;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_mean[c] = g_mean[c / cpg];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // GN_FOLD_ROWS output rows per CTA, warp w takes rows w, w + 8, ...: the per-sample set-up above is shared by all of them
+  for (int n = blockIdx.x * GN_FOLD_ROWS + warp; n < min(N, (int)(blockIdx.x + 1) * GN_FOLD_ROWS); n += 8) {
+    const uint4* wr = reinterpret_cast<const uint4*>(w + (size_t)n * ldw);
+    uint4* wo = reinterpret_cast<uint4*>(w_out + ((size_t)b * N + n) * ldw);
+    float acc = 0.f;
+    for (int v = lane; v < C / 8; v += 32) {
+      const uint4 q = __ldg(wr + v);
+      const float2 f0 = unpack_h2(q.x), f1 = unpack_h2(q.y), f2 = unpack_h2(q.z), f3 = unpack_h2(q.w);
+      const float f[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = v * 8 + 2 * j;
+        const uint32_t pk = pack_h2(f[2 * j] * s_scale[c], f[2 * j + 1] * s_scale[c + 1]);
+        const float2 r = unpack_h2(pk);                     // the ROUNDED folded weights, as the GEMM will read them
+        acc = fmaf(f[2 * j], s_beta[c], acc);
+        acc = fmaf(-s_mean[c], r.x, acc);
+        acc = fmaf(f[2 * j + 1], s_beta[c + 1], acc);
+        acc = fmaf(-s_mean[c + 1], r.y, acc);
+        o[j] = pk;
+      }
+      wo[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    // K padding (ldw > C columns, zero in w) stays zero in w_out
+    for (int v = C / 8 + lane; v < (int)(ldw / 8); v += 32) wo[v] = __ldg(wr + v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) bias_out[(size_t)b * N + n] = (bias ? __ldg(bias + n) : 0.f) + acc;
+  }
+}
+
+static int gn_fold_weights_impl(const void* w, int64_t ldw, const float* bias, const float* beta, const float* coef, int B,
+                                int N, int C, void* w_out, float* bias_out, cudaStream_t st) {
+  LDX_CHECK_ARG(w && beta && coef && w_out && bias_out, "gn_fold_weights: null pointer");
+  LDX_CHECK_ARG(B >= 1 && N >= 1 && C >= 32 && C % 32 == 0 && C % 8 == 0 && C <= 2048 && ldw >= C && ldw % 8 == 0,
+                "gn_fold_weights: bad extents (B=%d N=%d C=%d ldw=%lld)", B, N, C, (long long)ldw);
+  LDX_CHECK_ARG(reinterpret_cast<uintptr_t>(w) % 16 == 0 && reinterpret_cast<uintptr_t>(w_out) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(coef) % 8 == 0,
+                "gn_fold_weights: alignment");
+  LDX_CUDA(launch_k(gn_fold_weights_kernel, dim3((N + GN_FOLD_ROWS - 1) / GN_FOLD_ROWS, B), dim3(256), (size_t)3 * C * sizeof(float), st, 1,
+                    (const __half*)w, ldw, bias, beta, coef, N, C, (__half*)w_out, bias_out));
+  return LDX_OK;
+}
+
 static inline int ew_blocks(int64_t n, int threads = 256) {
   int64_t b = (n + threads - 1) / threads;
   const int64_t cap = (int64_t)num_sms() * 8;
@@ -999,6 +1081,10 @@ int run_generic_op(const ldx_generic_op_t* op, cudaStream_t st) {
       return group_norm_impl(p[0], i[0], l[0], p[1], i[1], l[1], i[2], i[3], f[0], (const float*)p[2],
                              (const float*)p[3], 0, nullptr, 0, (float*)p[5], st, (const float*)p[6], i[5],
                              (const float*)p[7], i[6], (float*)p[4], (unsigned*)p[8]);
+    case LDX_OP_GN_FOLD_WEIGHTS:
+      // p: w, bias, beta, coef, w_out, bias_out ; l: ldw ; i: B, N, C
+      return gn_fold_weights_impl(p[0], l[0], (const float*)p[1], (const float*)p[2], (const float*)p[3], i[0], i[1], i[2],
+                                  (void*)p[4], (float*)p[5], st);
     case LDX_OP_LAYER_NORM:
       // p: x, gamma, beta, y ; i: rows, C ; l: ldx, ldy ; f: eps
       return layer_norm_impl(p[0], l[0], i[0], i[1], f[0], (const float*)p[1], (const float*)p[2], (void*)p[3], l[1], st);
@@ -1115,6 +1201,11 @@ extern "C" int ldx_group_norm_coef(const void* x0, int c0, int64_t ld0, const vo
   LDX_CHECK_ARG(coef && tickets, "group_norm_coef: null coefficient / ticket buffer");
   return group_norm_impl(x0, c0, ld0, x1, c1, ld1, B, HW, eps, gamma, beta, 0, nullptr, 0, stats, as_stream(stream),
                          colstats0, slots0, colstats1, slots1, coef, tickets);
+}
+
+extern "C" int ldx_gn_fold_weights(const void* w, int64_t ldw, const float* bias, const float* beta, const float* coef, int B,
+                                   int N, int C, void* w_out, float* bias_out, ldx_stream_t stream) {
+  return gn_fold_weights_impl(w, ldw, bias, beta, coef, B, N, C, w_out, bias_out, as_stream(stream));
 }
 
 extern "C" int ldx_layer_norm(const void* x, int64_t ldx_, int rows, int C, float eps, const float* gamma,

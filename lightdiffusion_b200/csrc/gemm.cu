@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
         tile_coords<kCtas>(p, tile - split * p.base_tiles, (int)cta_rank, nt, tx, ty, tb);
         const int k_lo = split * p.ksplit, k_hi = min(p.nk, k_lo + p.ksplit);   // this tile's K steps
         // rows of B this CTA fetches for accumulator j: bn0 + j * (bn / nsub) (the pair splits each accumulator's rows)
-        const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb, n0 = nt * p.bn + (int)cta_rank * sub_rows;
+        const int x0 = tx * p.bw, y0 = ty * p.bh, b0 = tb * p.bb;
+        const int n0 = nt * p.bn + (int)cta_rank * sub_rows + b0 * p.w_batch_rows;   // per-sample weights: bb == 1
         const int sub_step = p.bn / nsub;
         int kcol = 0;
         // b_bytes: bytes of B this CTA loads for the step (the whole stage, or the 64-column identity block)
@@ -425,6 +426,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
           ln_mean = s1 * p.ln_inv_c;
           ln_rstd = rsqrtf(fmaxf(s2 * p.ln_inv_c - ln_mean * ln_mean, 0.f) + p.ln_eps);
         }
+        const float* bias_b = p.bias + (int64_t)(p.bias_bstride ? min(b, p.B - 1) : 0) * p.bias_bstride;   // per-sample bias
         float rs1 = 0.f, rs2 = 0.f;             // row statistics of this warp's output columns
         // column statistics: the warp's 32 rows are one slot of one batch element (gemm_prepare checks bw * bh >= 32)
         int64_t cs_base = -1;
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               const bool bias_vec = n_glob + EPI_CHUNK <= p.N;      // p.bias is never null on this path
               if (bias_vec) {
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) bb4[j4] = __ldg(reinterpret_cast<const float4*>(p.bias + n_glob) + j4);
+                for (int j4 = 0; j4 < 8; ++j4) bb4[j4] = __ldg(reinterpret_cast<const float4*>(bias_b + n_glob) + j4);
               }
               tmem_ld_wait();
               PH(3)
@@ -523,7 +525,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) ldx_gemm_kernel(const __grid_
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                  if (n_glob + j < p.N) v[j] += __ldg(p.bias + n_glob + j);
+                  if (n_glob + j < p.N) v[j] += __ldg(bias_b + n_glob + j);
               }
               if (rowadd_row) {
 #pragma unroll
@@ -1092,7 +1094,8 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
     if (rc) return rc;
   }
   {
-    const uint64_t dims[2] = {(uint64_t)k_weights * BK, (uint64_t)d->N};
+    const uint64_t w_rows = d->w_batch_rows ? (uint64_t)d->w_batch_rows * (uint64_t)(d->B - 1) + (uint64_t)d->N : (uint64_t)d->N;
+    const uint64_t dims[2] = {(uint64_t)k_weights * BK, w_rows};
     const uint64_t str[1] = {(uint64_t)d->ldw * 2};
     const uint32_t box[2] = {(uint32_t)BK, (uint32_t)(bn / (ctas * nsub))};
     int rc = encode_map_f16(&p.bmap, d->w, 2, dims, str, box);
@@ -1180,6 +1183,15 @@ int gemm_prepare(const ldx_gemm_desc_t* d, GemmLaunch* g) {
       p.ln_gsum = d->ln_gsum;
       p.ln_eps = d->ln_eps;
       p.ln_inv_c = 1.0f / (float)d->ln_c;
+    }
+    if (d->w_batch_rows || d->bias_batch_stride) {
+      LDX_CHECK_ARG(d->w_batch_rows >= d->N && d->bias && d->bias_batch_stride >= d->N && d->bias_batch_stride % 4 == 0 &&
+                        bb == 1 && (p.tiles_x * p.tiles_y) % ctas == 0 && nsplit == 1 && !halo &&
+                        !(d->flags & (LDX_EPI_GEGLU | LDX_EPI_ROWNORM)),
+                    "w_batch_rows / bias_batch_stride: need both, tiles inside one batch element (got %d per tile), the plain "
+                    "epilogue, no split-K, no halo sources", bb);
+      p.w_batch_rows = d->w_batch_rows;
+      p.bias_bstride = d->bias_batch_stride;
     }
     if (!p.bias) {
       p.bias = zeros_f32(d->N);

@@ -141,6 +141,7 @@ struct alignas(64) GemmKParams {
   int32_t na_stages, nb_stages;
   const float* gn_coef;             // [B][gn_ctot][2] (scale, shift) or null: GroupNorm (+SiLU) applied to the landed tile
   int32_t gn_ctot, gn_silu;
+  int32_t w_batch_rows, bias_bstride;   // per-sample weights / bias (ldx_gemm_desc_t.w_batch_rows), 0 = shared
 };
 
 // second launch of a split-K GEMM: out = act(sum_s partial[s] + bias + rowadd + residual) as fp16

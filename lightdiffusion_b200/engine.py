@@ -68,6 +68,13 @@ HALO_1X1 = os.environ.get("LDX_HALO_1X1", "0") == "1"
 # The feed-forward of the 320-channel transformer blocks (GEGLU projection + second Linear + residual, LD.py:4155-4162) as
 # ONE kernel whose 4C-wide intermediate stays on chip (csrc/ff_fused.cu).  LDX_FF_FUSED=0 keeps the two GEMMs (A/B).
 FF_FUSED = os.environ.get("LDX_FF_FUSED", "1") == "1"
+# SpatialTransformer.norm folded into proj_in's weights per sample (ldx_gn_fold_weights + ldx_gemm_desc_t.w_batch_rows) where the
+# map is large enough for the two-pass GroupNorm (the 64x64 and 32x32 levels): the normalised map is never written or read.
+# Correct (tests/test_kernels_gpu.py::test_group_norm_folded_into_proj_in_weights, UNet eps 1.50e-3 vs 1.48e-3) but measured
+# SLOWER and therefore off: the ten weight-scaling launches cost ~19 us each against the 9 us of the gn_apply pass they
+# replace (graph replay 14.97 / 14.98 vs 14.80 / 14.96 ms; bench conditions 24.39 / 24.38 vs 24.58 / 24.58 images/s,
+# scripts/gpu_ab10.sh).
+GN_FOLD = os.environ.get("LDX_GN_FOLD", "0") == "1"
 FUSE_GN_STATS = os.environ.get("LDX_FUSE_GN_STATS", "1") == "1"
 GN_STATS_MIN_HW = int(os.environ.get("LDX_GN_STATS_MIN_HW", "16384"))
 
@@ -182,6 +189,15 @@ class _GnStatsMixin:
         return (HALO and h * w >= HALO_MIN_HW and w % 8 == 0 and h % 16 == 0 and c0 % 8 == 0 and
                 bn * (h // 16) * (w // 8) >= HALO_MIN_TILES and
                 (x1 is None or (c0 % 64 == 0 and x1.shape[-1] % 8 == 0)))
+
+    @staticmethod
+    def _gn_fold_ok(x):
+        """Per-sample weights need GEMM tiles (128 pixels, CTA pairs: 256) that stay inside one sample and the two-pass
+        GroupNorm regime (small maps take the one-launch gn_small kernel)."""
+        bn, h, w, c = x.shape
+        cpg = c // 32
+        small = cpg % 8 == 0 and h * w * (cpg // 8) <= 2048
+        return (not small) and (h * w) % 256 == 0 and w in (8, 16, 32, 64, 128) and c % 64 == 0 and c <= 2048
 
     def _colstats(self, x0, x1):
         a = self._cs.get(x0.data_ptr())
@@ -470,6 +486,19 @@ class UNetPlan(_GnStatsMixin):
             st1 = self._rowstats(d, m, 0)      # row statistics of t for norm1, folded into the QKV GEMM
             self.prog.add(d)
             pool.free(coef)
+        elif GN_FOLD and self._gn_fold_ok(x):
+            # SpatialTransformer.norm folded into proj_in's WEIGHTS: statistics-only GroupNorm launch, one small launch that
+            # scales proj_in's weight per sample (w'[b] = w * scale[b], bias'[b]), then the 1x1 conv reads x itself: the
+            # normalised map is never written or read (gn_apply: 2 x the map per block)
+            coef = self._gn_coef(x, None, w[p + ".gn.g"], w[p + ".gn.b"], 1e-6)
+            wb = pool.alloc(Bn * c, w[p + ".pin.w"].stride(0)).view(Bn, c, w[p + ".pin.w"].stride(0))
+            bb = torch.empty(Bn, c, dtype=torch.float32, device=x.device)
+            self.prog.add(K.gn_fold_weights_op(w[p + ".pin.w"], w[p + ".pin.b"], w[p + ".gn.b"], coef, wb, bb), keep=[bb])
+            d = K.conv1x1_batched_desc(x, wb, bb, t.view(Bn, h, wd, c))
+            st1 = self._rowstats(d, m, 0)      # row statistics of t for norm1, folded into the QKV GEMM
+            self.prog.add(d)
+            pool.free(coef)
+            pool.free(wb)
         else:
             y = self._gn(x, None, w[p + ".gn.g"], w[p + ".gn.b"], 1e-6, False)
             d = K.linear_desc(y, w[p + ".pin.w"], t, bias=w[p + ".pin.b"])

@@ -417,6 +417,29 @@ def group_norm_coef_op(x0, x1, gamma, beta, coef, stats, tickets, eps: float, co
                       l=[x0.stride(2), 0 if x1 is None else x1.stride(2)], f=[eps])
 
 
+def gn_fold_weights_op(w: torch.Tensor, bias: Optional[torch.Tensor], beta: torch.Tensor, coef: torch.Tensor,
+                       w_out: torch.Tensor, bias_out: torch.Tensor) -> L.GenericOp:
+    """GroupNorm folded into the linear / 1x1 conv that consumes it (ldx_gn_fold_weights): w [N, ldw] fp16 (pack_linear),
+    coef [B, C, 2] from group_norm_coef_op, w_out [B, N, ldw] fp16, bias_out [B, N] fp32."""
+    B, C = coef.shape[0], coef.shape[1]
+    N = w.shape[0]
+    assert w.dtype == torch.float16 and w.stride(1) == 1 and w_out.is_contiguous() and tuple(w_out.shape) == (B, N, w.stride(0))
+    assert bias_out.dtype == torch.float32 and bias_out.is_contiguous() and tuple(bias_out.shape) == (B, N)
+    assert coef.dtype == torch.float32 and coef.is_contiguous() and beta.dtype == torch.float32 and beta.numel() == C
+    return generic_op(L.OP_GN_FOLD_WEIGHTS, p=[_ptr(w), _ptr(bias), _ptr(beta), _ptr(coef), _ptr(w_out), _ptr(bias_out)],
+                      l=[w.stride(0)], i=[B, N, C])
+
+
+def conv1x1_batched_desc(x: torch.Tensor, w_b: torch.Tensor, bias_b: torch.Tensor, out: torch.Tensor, **kw) -> L.GemmDesc:
+    """1x1 conv with per-sample weights and bias (ldx_gemm_desc_t.w_batch_rows): x [B, H, W, C], w_b [B, N, ldw] fp16 and
+    bias_b [B, N] fp32 from gn_fold_weights_op, out [B, H, W, N]."""
+    B, N, ldw = w_b.shape
+    assert x.dim() == 4 and x.shape[0] == B and bias_b.dtype == torch.float32 and tuple(bias_b.shape) == (B, N)
+    d = gemm_desc([x], [(0, 0, 0, 0, ceil64(x.shape[-1]) // 64)], w_b.view(B * N, ldw), out, N, bias=bias_b.view(-1), **kw)
+    d.w_batch_rows, d.bias_batch_stride = N, N
+    return d
+
+
 def ff_fused_op(x2, w1p, bias1, gsum1, w2, bias2, rowstats, out2, eps=1e-5) -> L.GenericOp:
     """out = x + W2 . GEGLU(LayerNorm(x) . W1^T + b1) + b2 in one launch (C = 320).  w1p / bias1 / gsum1: the LayerNorm-folded
     GEGLU projection packed with pack_geglu(half_bn=64); rowstats [M, parts, 2]: row statistics of x from its producer."""
@@ -490,7 +513,7 @@ class Program:
             elif op.kind == L.OP_LAYER_NORM:
                 tag = (op.i[0], op.i[1])                            # rows, C
             self.meta.append(({L.OP_ATTENTION: "attention", L.OP_GROUP_NORM: "group_norm", L.OP_FF_FUSED: "ff_fused",
-                               L.OP_GROUP_NORM_COEF: "group_norm",
+                               L.OP_GROUP_NORM_COEF: "group_norm", L.OP_GN_FOLD_WEIGHTS: "group_norm",
                                L.OP_LAYER_NORM: "layer_norm", L.OP_CONV_SMALL: "conv_small"}.get(op.kind, "other"),
                               flops, tag))
         self._keep.extend(keep)

@@ -699,3 +699,39 @@ def test_ff_geglu_fused_is_repeatable_and_row_local():
     # rows 1024 .. 1024 + 5000 of x as the head of their own (smaller) launch: other tiles, other CTA pairs, same bits
     _, sub = run(x[1024:1024 + 5000].contiguous())
     assert torch.equal(sub, first[1024:1024 + 5000])
+
+
+@pytest.mark.parametrize("B,H,C", [(3, 32, 640), (2, 64, 320), (2, 16, 320)])
+def test_group_norm_folded_into_proj_in_weights(B, H, C):
+    """SpatialTransformer.norm -> proj_in (LD.py:4242-4250) with the GroupNorm folded into per-sample weights
+    (ldx_gn_fold_weights + ldx_gemm_desc_t.w_batch_rows): the 1x1 conv reads the UN-normalised map.  The inputs carry a group
+    mean several times their spread, the case in which rounding the folded weights would be amplified if the bias did not
+    cancel it; row statistics of the output (for the LayerNorm folded into the next GEMM) are checked as well."""
+    x = h16(rnd(B, H, H, C, seed=301) * 0.7 + rnd(B, 1, 1, 32, seed=302).repeat_interleave(C // 32, -1) * 3.0 + 1.5)
+    gamma, beta = 1.0 + 0.3 * rnd(C, seed=303), 0.4 * rnd(C, seed=304)
+    w, bias = h16(rnd(C, C, seed=305, scale=C ** -0.5)), 0.3 * rnd(C, seed=306)
+    wp = K.pack_linear(w)
+    coef = torch.empty(B, C, 2, dtype=torch.float32, device=DEV)
+    stats = torch.empty(B * L.GN_STATS_FLOATS_PER_BATCH, dtype=torch.float32, device=DEV)
+    tickets = torch.zeros(B, dtype=torch.int32, device=DEV)
+    K.run_op(K.group_norm_coef_op(x, None, gamma, beta, coef, stats, tickets, 1e-6))
+    wb = torch.empty(B, C, wp.stride(0), dtype=torch.float16, device=DEV)
+    bb = torch.empty(B, C, dtype=torch.float32, device=DEV)
+    K.run_op(K.gn_fold_weights_op(wp, bias, beta, coef, wb, bb))
+    out = torch.full((B, H, H, C), 7.0, dtype=torch.float16, device=DEV)
+    d = K.conv1x1_batched_desc(x, wb, bb, out)
+    rs = K.attach_rowstats(d, B * H * H)
+    K.run_gemm(d)
+    xf = x.float().permute(0, 3, 1, 2)
+    y = F.group_norm(xf, 32, gamma, beta, 1e-6).permute(0, 2, 3, 1)
+    ref = y @ w.float().t() + bias
+    assert rel(out, ref) < 1.5e-3, rel(out, ref)
+    # the two-pass path (normalised map rounded to fp16, shared weights) for comparison: same error class
+    y16 = torch.empty_like(x)
+    K.run_op(K.group_norm_op(x, None, gamma, beta, y16, stats, 1e-6, False))
+    out2 = torch.empty_like(out)
+    K.run_gemm(K.linear_desc(y16, wp, out2, bias=bias))
+    assert rel(out, ref) < 2.0 * rel(out2, ref) + 1e-4, (rel(out, ref), rel(out2, ref))
+    got = rs.sum(1)
+    o32 = out.float().reshape(-1, C)
+    assert rel(got[:, 0], o32.sum(1)) < 2e-3 and rel(got[:, 1], (o32 * o32).sum(1)) < 2e-3
