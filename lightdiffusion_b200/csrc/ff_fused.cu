@@ -17,7 +17,7 @@
 //     O += A2_j · W2[:, 64j : 64j + 64]^T (two N = 160 chains: UMMA N <= 256) accumulates the 320 output columns in TMEM;
 //   * a final epilogue adds b2 and stores the fp16 rows by TMA.
 // warp 0: TMA producer of A1 and the W1 ring; warp 2: TMA producer of the W2 ring and the identity; warp 1: MMA issuer
-// (leader CTA); warps 4-11: epilogue.  TMEM: S 128 columns + O 320 columns.  Shared memory per CTA: A1 80 KB, W1 ring
+// (leader CTA); warps 4-11: epilogue (FF_EG = 2).  TMEM: S 128 columns + O 320 columns.  Shared memory per CTA: A1 80 KB, W1 ring
 // 4 x 8 KB, W2 ring 2 x 20 KB, A2 2 x 16 KB, identity 4 KB, store staging 8 x 4 KB = 220 KB.
 // Roofline: the GEGLU epilogue (issue / MUFU) and the tensor pipe (2 * M * (8C * C + 4C * C) FLOPs); HBM traffic is x in,
 // out, and the weights once per pair tile from L2.
@@ -33,11 +33,13 @@ int identity_matrix_n();
 static constexpr int FF_C = 320;                      // model width this kernel is built for
 static constexpr int FF_KCH = FF_C / 64;              // K chunks of the first GEMM = 64-column blocks of the output
 // Epilogue warps per TMEM lane quarter (build knob): each takes 64 / FF_EG of a chunk's value columns and the matching gate
-// columns.  4 (sixteen epilogue warps, four per scheduler, <= 96 registers) hides the MUFU / FMA latency of the GEGLU
-// chains that 2 (eight warps, 168 registers) left exposed.
+// columns.  2 = eight epilogue warps (168 registers).  4 = sixteen warps, four per scheduler, 96 registers: measured SLOWER
+// (188 - 193 vs 167 us at M = 65536): the per-warp barrier / TMEM round trips double and the GEGLU chains were not latency bound.
 #ifndef LDX_FF_EG
 #define LDX_FF_EG 2
 #endif
+// GEGLU math as packed fp32 pairs (FFMA2 / FMUL2, common.cuh f2_*): the same operations, bit-identical results, 285 instead of
+// ~420 instructions per chunk and thread: 167 -> 161 us on one box, 183 -> 154 - 166 us on another.  0 = the scalar form (A/B).
 #ifndef LDX_FF_PACKED
 #define LDX_FF_PACKED 1
 #endif
